@@ -1,0 +1,181 @@
+/*
+ * include/tess_b200.h -- C ABI of libtess_b200.so, the B200 (sm_100a) implementation of the
+ * Lloyd / centroidal-Voronoi (CVT, WVT) hot path of jonathansick/tess.
+ *
+ * The reference has no C ABI for this path: it is a Python-callable Cython function,
+ *     cpdef lloyd(double[:, :] xy, double[:] w, double[:, :] node_xy, long max_iters)
+ *                                                       (reference tess/lloyd.pyx:10-11)
+ * called from exactly one site (reference tess/voronoi.py:301-302), plus SciPy nearest-
+ * neighbour calls for the segmentation map (tess/voronoi.py:113-114) and point partition
+ * (tess/voronoi.py:171-172).  Its historic ctypes binding (reference
+ * examples/test_clloyds.py:21-39: `cvt.lloyd(n, x, y, w, nNode, xNode, yNode, vBinNum)`,
+ * plain pointers, status return) is the shape this header echoes.  Each entry point below
+ * names the reference lines it replaces.  INTEGRATION.md shows the ctypes stub a tess
+ * maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 (TESS_OK) or a negative TESS_ERR_* code; never throws;
+ *     tess_last_error() gives a thread-local message for the last failure.
+ *   - ALL data pointers are DEVICE pointers on the context's device (e.g. torch CUDA tensor
+ *     data_ptr()).  Input arrays are BORROWED: they must stay alive and unchanged until they
+ *     are replaced by another tess_set_* call or the context is destroyed.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls are
+ *     asynchronous on that stream unless stated (tess_lloyd_run and tess_get_iter_stats
+ *     synchronise it because they return host values).
+ *   - one context per device; a context is not thread-safe, distinct contexts are.
+ *   - labels are int32 (the reference returns int64, widened by the Python layer);
+ *     coordinates, weights and moments are fp64.
+ *
+ * Arithmetic contract (bit-exact with the reference on tie-free input; see oracle/oracle.py):
+ *   d2(i,j) = fl( fl(dx*dx) + fl(dy*dy) )   fp64, no FMA        [cKDTree via lloyd.pyx:54-55]
+ *   label_i = argmin_j d2(i,j) [* inv_s2_j when scales are given], ties -> lowest j
+ *   moments per bin: count, sum w, sum w*x, sum w*y (+ sum S, sum N*N in signal/noise mode),
+ *     products rounded separately; the summation ORDER differs from the reference's
+ *     sequential loop (lloyd.pyx:58-65), so sums agree to ~1e-15 relative, not bitwise.
+ */
+#ifndef TESS_B200_H
+#define TESS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tess_ctx tess_ctx;
+
+enum {
+    TESS_OK = 0,
+    TESS_ERR_ARG = -1,       /* bad argument (null pointer, non-positive size, ...)            */
+    TESS_ERR_CUDA = -2,      /* CUDA runtime failure; text in tess_last_error()                */
+    TESS_ERR_STATE = -3,     /* call order violated (no image/points or no generators set)     */
+    TESS_ERR_NONFINITE = -4, /* a generator coordinate / scale is NaN or Inf.  The reference   */
+                             /* raises ValueError from cKDTree in that case (bin with count>0  */
+                             /* and sum w == 0, lloyd.pyx:66-70 -> :54 next iteration)         */
+    TESS_ERR_NOMEM = -5      /* device allocation failed                                       */
+};
+
+/* Moment columns of tess_get_moments / tess_moments_ptr. */
+enum {
+    TESS_MOM_COUNT = 0, /* pixels/points in the bin   (lloyd.pyx:62 node_population)          */
+    TESS_MOM_W = 1,     /* sum w                      (lloyd.pyx:63 weight_sum)               */
+    TESS_MOM_WX = 2,    /* sum fl(w*x)                (lloyd.pyx:64-65)                       */
+    TESS_MOM_WY = 3,    /* sum fl(w*y)                (lloyd.pyx:64-65)                       */
+    TESS_MOM_S = 4,     /* sum signal                 (pixel_accretion.py:513)                */
+    TESS_MOM_N2 = 5     /* sum fl(noise*noise)        (pixel_accretion.py:514)                */
+};
+
+/* Options for tess_set_option. */
+enum {
+    TESS_OPT_WVT_SCALE_UPDATE = 1, /* 0 (default): scales stay as given.  1: after each node   */
+                                   /* update set scale_j = sqrt(count_j / (S/N)_j) (Diehl &   */
+                                   /* Statler 2006 eq. 4); needs signal/noise mode.  No        */
+                                   /* reference counterpart.              */
+    TESS_OPT_UNIFORM_WEIGHT = 2    /* signal/noise mode only. 0 (default): w = fl(fl(S/N)^2)  */
+                                   /* (scripts/demo_iso_sn_voronoi.py:26,37). 1: w = 1         */
+                                   /* (geometric centroids, WVT).                              */
+};
+
+int tess_version(void);
+const char* tess_last_error(void);
+
+int tess_ctx_create(int device, tess_ctx** out);
+int tess_ctx_destroy(tess_ctx* ctx);
+int tess_set_option(tess_ctx* ctx, int option, long value);
+
+/*
+ * Image mode -- replaces the point-set construction of CVTessellation.from_image
+ * (reference tess/voronoi.py:281-287): pixel (row r, col c) is the point (x0 + c, y0 + r);
+ * it is never materialised.  H x W row-major fp64 maps.  Give EITHER `density` (CVT parity
+ * mode: w = density, 4 moments) OR `signal` and `noise` (S/N mode: w = (S/N)^2, 6 moments).
+ * Pixels whose weight (or signal/noise) is non-finite are excluded from every sum, exactly
+ * like voronoi.py:285 drops them, but still receive a label (so the label map doubles as the
+ * segmap of voronoi.py:75-81).  For a row-sharded multi-GPU run each rank passes its own
+ * rows with y0 = first global row.
+ */
+int tess_set_image(tess_ctx* ctx, long H, long W, double x0, double y0, const double* density,
+                   const double* signal, const double* noise, void* stream);
+
+/*
+ * Point mode -- the `xy`, `w` arguments of lloyd() (reference tess/lloyd.pyx:10-11):
+ * xy is AoS [n][2], w is [n].  Points are binned once into spatial tiles (a sorted copy is
+ * kept in the context's workspace); labels are returned in the caller's point order.
+ */
+int tess_set_points(tess_ctx* ctx, long n, const double* xy, const double* w, void* stream);
+
+/*
+ * Generators -- the `node_xy` argument of lloyd() ([k][2], (x, y) order, voronoi.py:273-277).
+ * COPIED into the context (the reference does not mutate its input either, lloyd.pyx:49,59).
+ * `scale` ([k], nullable) are WVT scale lengths; NULL = plain Euclidean (reference parity).
+ * Resets the iteration counter and convergence state.  TESS_ERR_NONFINITE if any is NaN/Inf.
+ */
+int tess_set_generators(tess_ctx* ctx, long k, const double* node_xy, const double* scale,
+                        void* stream);
+
+/*
+ * One Lloyd iteration = tess_lloyd_accumulate + tess_lloyd_update.
+ *
+ * accumulate: rebuild the generator grid index, assign every pixel/point to its nearest
+ *   generator (lloyd.pyx:54-55) and form the per-bin moments (lloyd.pyx:58-65) -- LOCAL to
+ *   this context's pixels.  Also evaluates "did any label change since the last iteration".
+ * tess_moments_ptr: device pointer to the packed vector [k*M moments | tail], M = 4 or 6;
+ *   `n_doubles` is its full length.  A multi-GPU host sums THIS vector across ranks
+ *   (one allreduce) between accumulate and update; nothing else crosses GPUs.
+ * update: nodes = (sum wx, sum wy)/sum w where count > 0 else (0,0) (lloyd.pyx:66-74),
+ *   delta = sum |old-new|^2 (lloyd.pyx:76-81), convergence latch (see tess_lloyd_run).
+ */
+int tess_lloyd_accumulate(tess_ctx* ctx, void* stream);
+int tess_moments_ptr(tess_ctx* ctx, double** dev_ptr, long* n_doubles, int* n_moments);
+int tess_lloyd_update(tess_ctx* ctx, void* stream);
+
+/* n_steps iterations back to back, no host synchronisation (benchmarks, fixed-step use). */
+int tess_lloyd_step(tess_ctx* ctx, long n_steps, void* stream);
+
+/*
+ * The reference loop and stop rule (lloyd.pyx:47-90): iterate until the node table is a
+ * fixed point (reference: delta == 0; here, equivalently and robustly to summation order:
+ * no label changed since the previous iteration, or delta == 0) -> *converged = 1, or until
+ * max_iters + 2 loop bodies have run -> *converged = 0.  *n_iters = loop bodies executed.
+ * Synchronises `stream`.  Afterwards tess_get_generators gives the reference's returned
+ * node_xy and tess_get_labels its returned idx (assignment w.r.t. the previous node table,
+ * lloyd.pyx:55 vs :86/:88).
+ */
+int tess_lloyd_run(tess_ctx* ctx, long max_iters, int* converged, long* n_iters, void* stream);
+
+/* Results (device-to-device copies into caller memory, asynchronous on `stream`). */
+int tess_get_labels(tess_ctx* ctx, int32_t* out, void* stream);      /* [H*W] or [n]          */
+int tess_get_moments(tess_ctx* ctx, double* out, void* stream);      /* [k][6], unused cols 0 */
+int tess_get_generators(tess_ctx* ctx, double* out, void* stream);   /* [k][2]                */
+int tess_get_scales(tess_ctx* ctx, double* out, void* stream);       /* [k]                   */
+/*
+ * delta of the last update (lloyd.pyx:82's printed value), number of labels that changed in
+ * the last accumulate (-1 = "some changed, not counted": counting is skipped when a per-bin
+ * population already differs), iterations done since tess_set_generators.  Synchronises.
+ */
+int tess_get_iter_stats(tess_ctx* ctx, double* delta, long* n_changed, long* n_iters_done,
+                        void* stream);
+
+/*
+ * Assignment only -- the segmentation map of VoronoiTessellation.segmap /
+ * render_voronoi_field (reference tess/voronoi.py:75-114): labels_out[r*W + c] = nearest
+ * generator of (x0 + c, y0 + r).  Uses the context's generators; no image needs to be set.
+ */
+int tess_assign_grid(tess_ctx* ctx, double x0, double y0, long H, long W, int32_t* labels_out,
+                     void* stream);
+/* partition_points (reference tess/voronoi.py:154-173): out[i] = nearest generator of xy[i]. */
+int tess_assign_points(tess_ctx* ctx, long m, const double* xy, int32_t* out, void* stream);
+
+/*
+ * Validation aids: exhaustive O(n*k) assignment on the GPU with the same pinned arithmetic,
+ * no index, no pruning.  Used by the tests to check the tiled kernels at sizes the CPU oracle
+ * cannot reach.  Not a fallback: nothing in the library calls them.
+ */
+int tess_assign_grid_exhaustive(tess_ctx* ctx, double x0, double y0, long H, long W,
+                                int32_t* labels_out, void* stream);
+int tess_assign_points_exhaustive(tess_ctx* ctx, long m, const double* xy, int32_t* out,
+                                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TESS_B200_H */

@@ -1,0 +1,710 @@
+// tess_b200.cu -- host side of libtess_b200.so: context, workspace and the C ABI declared in
+// include/tess_b200.h.  Built for sm_100a only (tess_b200/build.py); there is no CPU path.
+//
+// One Lloyd iteration (reference tess/lloyd.pyx:47-90) is the launch sequence
+//   k_cell_count -> k_cell_scan -> k_cell_scatter        generator grid (replaces cKDTree build, :54)
+//   k_build_lists                                        per-tile candidate lists
+//   k_image_main | k_points_main                         assignment (:55) fused with the sums (:58-65)
+//   k_count_prefilter -> k_compare_labels                "did any label change" (convergence, :85)
+//   [multi-GPU: the host all-reduces the moment vector here]
+//   k_update_nodes                                       node update, delta, latch (:66-90)
+// with no host synchronisation in between; the convergence latch lives on the device.
+#include "../../include/tess_b200.h"
+
+#include "tess_common.cuh"
+#include "tess_index.cuh"
+#include "tess_image.cuh"
+#include "tess_points.cuh"
+#include "tess_update.cuh"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#define TESS_VERSION_NUM 100
+
+static thread_local char g_err[512] = "";
+
+static int tess_fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU_TRY(expr)                                                                              \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return tess_fail(e_ == cudaErrorMemoryAllocation ? TESS_ERR_NOMEM : TESS_ERR_CUDA,    \
+                             "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define TRY(expr)               \
+    do {                        \
+        int r_ = (expr);        \
+        if (r_ != TESS_OK) return r_; \
+    } while (0)
+
+enum { SRC_NONE = 0, SRC_IMAGE = 1, SRC_POINTS = 2 };
+
+struct tess_ctx {
+    int device;
+    int sm_count;
+    // ---- borrowed inputs
+    int source;
+    int img_mode;   // 1: density, 2: signal + noise
+    long H, W;
+    double x0, y0;
+    const double *dens, *sig, *noise;
+    long n_pts;
+    const double *pts_xy, *pts_w;
+    double pb[4];   // bounding box of the points (x0, x1, y0, y1)
+    // ---- generators (owned)
+    int k, k_cap;
+    double* node;     // [k][2]
+    double* scale;    // [k] or unused
+    double* inv_s2;   // [k]
+    int has_scale;
+    // ---- options
+    int wvt_update, uniform_weight;
+    // ---- workspace (owned)
+    TessState* st;
+    int *cell_cnt, *cell_start, *cell_of, *cell_items;
+    double2* cell_xy;
+    double* cell_inv;
+    long cells_cap;
+    int *list_off, *list_cnt, *list_items;
+    long tiles_cap;
+    unsigned list_cap;
+    int32_t* lab[2];
+    long lab_cap;
+    double* mom;
+    long mom_cap;
+    double* prev_count;
+    double* scratch;   // 8 doubles (bounding-box reduction)
+    TessState* h_st;   // pinned mirror
+};
+
+static cudaStream_t S(void* s) { return (cudaStream_t)s; }
+
+static int bind(tess_ctx* c) {
+    if (!c) return tess_fail(TESS_ERR_ARG, "null context");
+    CU_TRY(cudaSetDevice(c->device));
+    return TESS_OK;
+}
+
+// ------------------------------------------------------------------------------------ misc
+extern "C" int tess_version(void) { return TESS_VERSION_NUM; }
+extern "C" const char* tess_last_error(void) { return g_err; }
+
+extern "C" int tess_ctx_create(int device, tess_ctx** out) {
+    if (!out) return tess_fail(TESS_ERR_ARG, "tess_ctx_create: out is null");
+    *out = nullptr;
+    int ndev = 0;
+    CU_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return tess_fail(TESS_ERR_ARG, "tess_ctx_create: no CUDA device %d", device);
+    CU_TRY(cudaSetDevice(device));
+    tess_ctx* c = new tess_ctx();
+    memset(c, 0, sizeof(*c));
+    c->device = device;
+    int r = TESS_OK;
+    do {
+        cudaError_t e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+        if (e != cudaSuccess) { r = tess_fail(TESS_ERR_CUDA, "device attribute: %s", cudaGetErrorString(e)); break; }
+        e = cudaMalloc((void**)&c->st, sizeof(TessState));
+        if (e != cudaSuccess) { r = tess_fail(TESS_ERR_NOMEM, "cudaMalloc(state): %s", cudaGetErrorString(e)); break; }
+        cudaMemset(c->st, 0, sizeof(TessState));
+        e = cudaMalloc((void**)&c->scratch, 8 * sizeof(double));
+        if (e != cudaSuccess) { r = tess_fail(TESS_ERR_NOMEM, "cudaMalloc(scratch): %s", cudaGetErrorString(e)); break; }
+        e = cudaMallocHost((void**)&c->h_st, sizeof(TessState) + 8 * sizeof(double));
+        if (e != cudaSuccess) { r = tess_fail(TESS_ERR_NOMEM, "cudaMallocHost: %s", cudaGetErrorString(e)); break; }
+    } while (0);
+    if (r != TESS_OK) {
+        tess_ctx_destroy(c);
+        return r;
+    }
+    *out = c;
+    return TESS_OK;
+}
+
+extern "C" int tess_ctx_destroy(tess_ctx* c) {
+    if (!c) return TESS_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    void* ptrs[] = {c->node, c->scale, c->inv_s2, c->st, c->cell_cnt, c->cell_start, c->cell_of, c->cell_items,
+                    c->cell_xy, c->cell_inv, c->list_off, c->list_cnt, c->list_items, c->lab[0], c->lab[1],
+                    c->mom, c->prev_count, c->scratch};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (c->h_st) cudaFreeHost(c->h_st);
+    delete c;
+    return TESS_OK;
+}
+
+extern "C" int tess_set_option(tess_ctx* c, int option, long value) {
+    TRY(bind(c));
+    switch (option) {
+        case TESS_OPT_WVT_SCALE_UPDATE: c->wvt_update = value ? 1 : 0; return TESS_OK;
+        case TESS_OPT_UNIFORM_WEIGHT: c->uniform_weight = value ? 1 : 0; return TESS_OK;
+        default: return tess_fail(TESS_ERR_ARG, "tess_set_option: unknown option %d", option);
+    }
+}
+
+static int n_moments(const tess_ctx* c) { return (c->source == SRC_IMAGE && c->img_mode == 2) ? 6 : 4; }
+
+static int reset_iteration_state(tess_ctx* c, cudaStream_t s) {
+    // iteration counter, latch and "previous labels" start over; error flags are kept by the caller
+    TessState z;
+    memset(&z, 0, sizeof(z));
+    z.min_inv_s2 = 1.0;
+    z.conv_iter = -1;
+    memcpy(c->h_st, &z, sizeof(z));
+    CU_TRY(cudaMemcpyAsync(c->st, c->h_st, sizeof(TessState), cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaStreamSynchronize(s));   // h_st is reused
+    return TESS_OK;
+}
+
+__global__ void __launch_bounds__(256) k_fill(double* p, long n, double v) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// prev_count <- -1 and min 1/scale^2 (after the state block was reset)
+static int restart_tail(tess_ctx* c, cudaStream_t s) {
+    if (c->k > 0) {
+        TESS_LAUNCH((k_fill), (c->k + 255) / 256, 256, s, c->prev_count, (long)c->k, -1.0);
+        if (c->has_scale) TESS_LAUNCH((k_min_inv_s2), 1, 1024, s, c->st, c->inv_s2, c->k);
+        CU_TRY(cudaGetLastError());
+    }
+    return TESS_OK;
+}
+
+// new inputs: the iteration starts over
+static int restart(tess_ctx* c, cudaStream_t s) {
+    TRY(reset_iteration_state(c, s));
+    return restart_tail(c, s);
+}
+
+static int ensure_labels(tess_ctx* c, long n) {
+    if (n <= c->lab_cap) return TESS_OK;
+    for (int i = 0; i < 2; ++i) {
+        if (c->lab[i]) cudaFree(c->lab[i]);
+        c->lab[i] = nullptr;
+    }
+    c->lab_cap = 0;
+    CU_TRY(cudaMalloc((void**)&c->lab[0], sizeof(int32_t) * (size_t)n));
+    CU_TRY(cudaMalloc((void**)&c->lab[1], sizeof(int32_t) * (size_t)n));
+    c->lab_cap = n;
+    return TESS_OK;
+}
+
+// ------------------------------------------------------------------------------------ inputs
+extern "C" int tess_set_image(tess_ctx* c, long H, long W, double x0, double y0, const double* density,
+                              const double* signal, const double* noise, void* stream) {
+    TRY(bind(c));
+    if (H <= 0 || W <= 0) return tess_fail(TESS_ERR_ARG, "tess_set_image: H and W must be positive");
+    if ((double)H * (double)W > 2.0e9 * 64.0) return tess_fail(TESS_ERR_ARG, "tess_set_image: image too large");
+    const bool cvt = density && !signal && !noise, sn = !density && signal && noise;
+    if (!cvt && !sn) return tess_fail(TESS_ERR_ARG, "tess_set_image: give either density or signal+noise");
+    c->source = SRC_IMAGE;
+    c->img_mode = cvt ? 1 : 2;
+    c->H = H; c->W = W; c->x0 = x0; c->y0 = y0;
+    c->dens = density; c->sig = signal; c->noise = noise;
+    c->n_pts = 0; c->pts_xy = c->pts_w = nullptr;
+    TRY(ensure_labels(c, H * W));
+    TRY(restart(c, S(stream)));
+    return TESS_OK;
+}
+
+// bounding box of a point set: block partial min/max -> atomics on the bit patterns is avoided by
+// a single-CTA pass (n is at most a few million in point mode)
+__global__ void __launch_bounds__(1024) k_points_bbox(const double* xy, long n, double* out) {
+    __shared__ double s_v[4][32];
+    double x0 = INFINITY, x1 = -INFINITY, y0 = INFINITY, y1 = -INFINITY;
+    for (long i = threadIdx.x; i < n; i += blockDim.x) {
+        double x = xy[2 * i], y = xy[2 * i + 1];
+        if (isfinite(x) && isfinite(y)) {
+            x0 = fmin(x0, x); x1 = fmax(x1, x); y0 = fmin(y0, y); y1 = fmax(y1, y);
+        }
+    }
+    x0 = tess_warp_min(x0); y0 = tess_warp_min(y0);
+    x1 = -tess_warp_min(-x1); y1 = -tess_warp_min(-y1);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { s_v[0][w] = x0; s_v[1][w] = x1; s_v[2][w] = y0; s_v[3][w] = y1; }
+    __syncthreads();
+    if (w == 0) {
+        const int nw = blockDim.x >> 5;
+        x0 = l < nw ? s_v[0][l] : INFINITY; x1 = l < nw ? s_v[1][l] : -INFINITY;
+        y0 = l < nw ? s_v[2][l] : INFINITY; y1 = l < nw ? s_v[3][l] : -INFINITY;
+        x0 = tess_warp_min(x0); y0 = tess_warp_min(y0);
+        x1 = -tess_warp_min(-x1); y1 = -tess_warp_min(-y1);
+        if (l == 0) { out[0] = x0; out[1] = x1; out[2] = y0; out[3] = y1; }
+    }
+}
+
+static int points_bbox(tess_ctx* c, long n, const double* xy, double* box, cudaStream_t s) {
+    TESS_LAUNCH((k_points_bbox), 1, 1024, s, xy, n, c->scratch);
+    CU_TRY(cudaGetLastError());
+    double* h = (double*)(c->h_st + 1);
+    CU_TRY(cudaMemcpyAsync(h, c->scratch, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    memcpy(box, h, 4 * sizeof(double));
+    if (!(box[0] <= box[1]) || !(box[2] <= box[3])) { box[0] = box[2] = 0.0; box[1] = box[3] = 1.0; }
+    return TESS_OK;
+}
+
+extern "C" int tess_set_points(tess_ctx* c, long n, const double* xy, const double* w, void* stream) {
+    TRY(bind(c));
+    if (n <= 0 || !xy || !w) return tess_fail(TESS_ERR_ARG, "tess_set_points: need n > 0, xy and w");
+    if (n > 2000000000L) return tess_fail(TESS_ERR_ARG, "tess_set_points: n too large");
+    c->source = SRC_POINTS;
+    c->img_mode = 0;
+    c->n_pts = n; c->pts_xy = xy; c->pts_w = w;
+    c->dens = c->sig = c->noise = nullptr;
+    TRY(points_bbox(c, n, xy, c->pb, S(stream)));
+    TRY(ensure_labels(c, n));
+    TRY(restart(c, S(stream)));
+    return TESS_OK;
+}
+
+extern "C" int tess_set_generators(tess_ctx* c, long k, const double* node_xy, const double* scale, void* stream) {
+    TRY(bind(c));
+    if (k <= 0 || !node_xy) return tess_fail(TESS_ERR_ARG, "tess_set_generators: need k > 0 and node_xy");
+    if (k > 1000000000L) return tess_fail(TESS_ERR_ARG, "tess_set_generators: k too large");
+    cudaStream_t s = S(stream);
+    if (k > c->k_cap) {
+        void** ps[] = {(void**)&c->node, (void**)&c->scale, (void**)&c->inv_s2, (void**)&c->cell_of,
+                       (void**)&c->cell_items, (void**)&c->cell_xy, (void**)&c->cell_inv, (void**)&c->prev_count};
+        for (void** p : ps) { if (*p) cudaFree(*p); *p = nullptr; }
+        c->k_cap = 0;
+        CU_TRY(cudaMalloc((void**)&c->node, sizeof(double) * 2 * k));
+        CU_TRY(cudaMalloc((void**)&c->scale, sizeof(double) * k));
+        CU_TRY(cudaMalloc((void**)&c->inv_s2, sizeof(double) * k));
+        CU_TRY(cudaMalloc((void**)&c->cell_of, sizeof(int) * k));
+        CU_TRY(cudaMalloc((void**)&c->cell_items, sizeof(int) * k));
+        CU_TRY(cudaMalloc((void**)&c->cell_xy, sizeof(double2) * k));
+        CU_TRY(cudaMalloc((void**)&c->cell_inv, sizeof(double) * k));
+        CU_TRY(cudaMalloc((void**)&c->prev_count, sizeof(double) * k));
+        c->k_cap = (int)k;
+    }
+    c->k = (int)k;
+    // WVT scale updates need a scale table: start from unit scales when none is given
+    c->has_scale = (scale || c->wvt_update) ? 1 : 0;
+    const int nb = (int)((k + 255) / 256);
+    CU_TRY(cudaMemcpyAsync(c->node, node_xy, sizeof(double) * 2 * k, cudaMemcpyDeviceToDevice, s));
+    if (scale) CU_TRY(cudaMemcpyAsync(c->scale, scale, sizeof(double) * k, cudaMemcpyDeviceToDevice, s));
+    else if (c->has_scale) TESS_LAUNCH((k_fill), nb, 256, s, c->scale, k, 1.0);
+    TRY(reset_iteration_state(c, s));
+    TESS_LAUNCH((k_check_generators), nb, 256, s, c->st, c->node, c->has_scale ? c->scale : nullptr, c->inv_s2, (int)k);
+    TRY(restart_tail(c, s));
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(c->h_st, c->st, sizeof(TessState), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    if (c->h_st->flags & TESS_FLAG_NONFINITE)
+        return tess_fail(TESS_ERR_NONFINITE, "tess_set_generators: a generator coordinate or scale is not finite");
+    return TESS_OK;
+}
+
+// ------------------------------------------------------------------------------------ index
+struct Geometry {
+    TessGrid g;
+    TessTiles T;   // image/grid queries only
+    int n_cells;
+};
+
+// Grid for an H x W pixel window at (x0, y0): one cell per 64-px super-tile, generators outside
+// the window are clamped into the border cells.
+static Geometry window_geometry(double x0, double y0, long H, long W) {
+    Geometry q;
+    q.T.x0 = x0; q.T.y0 = y0; q.T.W = W; q.T.H = H;
+    q.T.tiles_x = (int)((W + TESS_TS - 1) / TESS_TS);
+    q.T.tiles_y = (int)((H + TESS_TS - 1) / TESS_TS);
+    q.T.n_tiles = q.T.tiles_x * q.T.tiles_y;
+    q.g.ox = x0; q.g.oy = y0; q.g.cs = (double)TESS_TS; q.g.inv_cs = 1.0 / (double)TESS_TS;
+    q.g.gw = q.T.tiles_x; q.g.gh = q.T.tiles_y;
+    const double ext = fmax(fabs(x0) + (double)W, fabs(y0) + (double)H) + q.g.cs;
+    q.g.tol = ext * 9.094947017729282e-13 /* 2^-40 */;
+    q.n_cells = q.g.gw * q.g.gh;
+    return q;
+}
+
+// Grid for a point query: covers the box, about two generators per cell.
+static Geometry box_geometry(const double* box, int k) {
+    Geometry q;
+    memset(&q, 0, sizeof(q));
+    const double w = fmax(box[1] - box[0], 1e-300), h = fmax(box[3] - box[2], 1e-300);
+    double cs = sqrt(w * h / fmax((double)k / 2.0, 1.0));
+    if (!(cs > 0.0) || !isfinite(cs)) cs = fmax(w, h);
+    cs = fmax(cs, fmax(w, h) / 4096.0);
+    int gw = (int)fmin(floor(w / cs) + 1.0, 4097.0), gh = (int)fmin(floor(h / cs) + 1.0, 4097.0);
+    q.g.ox = box[0]; q.g.oy = box[2]; q.g.cs = cs; q.g.inv_cs = 1.0 / cs;
+    q.g.gw = gw < 1 ? 1 : gw; q.g.gh = gh < 1 ? 1 : gh;
+    const double ext = fmax(fmax(fabs(box[0]), fabs(box[1])), fmax(fabs(box[2]), fabs(box[3]))) + cs;
+    q.g.tol = ext * 9.094947017729282e-13;
+    q.n_cells = q.g.gw * q.g.gh;
+    return q;
+}
+
+static int ensure_cells(tess_ctx* c, int n_cells) {
+    if (n_cells + 1 <= c->cells_cap) return TESS_OK;
+    if (c->cell_cnt) cudaFree(c->cell_cnt);
+    if (c->cell_start) cudaFree(c->cell_start);
+    c->cell_cnt = c->cell_start = nullptr;
+    c->cells_cap = 0;
+    CU_TRY(cudaMalloc((void**)&c->cell_cnt, sizeof(int) * (size_t)(n_cells + 1)));
+    CU_TRY(cudaMemset(c->cell_cnt, 0, sizeof(int) * (size_t)(n_cells + 1)));   // scatter keeps it zero
+    CU_TRY(cudaMalloc((void**)&c->cell_start, sizeof(int) * (size_t)(n_cells + 1)));
+    c->cells_cap = n_cells + 1;
+    return TESS_OK;
+}
+
+static int ensure_lists(tess_ctx* c, int n_tiles) {
+    if (n_tiles > c->tiles_cap) {
+        if (c->list_off) cudaFree(c->list_off);
+        if (c->list_cnt) cudaFree(c->list_cnt);
+        c->list_off = c->list_cnt = nullptr;
+        c->tiles_cap = 0;
+        CU_TRY(cudaMalloc((void**)&c->list_off, sizeof(int) * (size_t)n_tiles));
+        CU_TRY(cudaMalloc((void**)&c->list_cnt, sizeof(int) * (size_t)n_tiles));
+        c->tiles_cap = n_tiles;
+    }
+    // arena: a generator is listed by every tile it can win in -- its own bin plus a margin
+    double want = 128.0 * (double)n_tiles + 32.0 * (double)c->k + 65536.0;
+    if (want > 2.0e9) want = 2.0e9;
+    if ((unsigned)want > c->list_cap) {
+        if (c->list_items) cudaFree(c->list_items);
+        c->list_items = nullptr;
+        c->list_cap = 0;
+        CU_TRY(cudaMalloc((void**)&c->list_items, sizeof(int) * (size_t)want));
+        c->list_cap = (unsigned)want;
+    }
+    return TESS_OK;
+}
+
+static int ensure_moments(tess_ctx* c) {
+    const long need = (long)c->k * 6 + TESS_TAIL;
+    if (need <= c->mom_cap) return TESS_OK;
+    if (c->mom) cudaFree(c->mom);
+    c->mom = nullptr;
+    c->mom_cap = 0;
+    CU_TRY(cudaMalloc((void**)&c->mom, sizeof(double) * (size_t)need));
+    CU_TRY(cudaMemset(c->mom, 0, sizeof(double) * (size_t)need));
+    c->mom_cap = need;
+    return TESS_OK;
+}
+
+// counting sort of the generators into q.g; `mom`/n_mom: moment vector to clear (or null/0)
+static int build_index(tess_ctx* c, const Geometry& q, int honor, double* mom, long n_mom, cudaStream_t s) {
+    TRY(ensure_cells(c, q.n_cells));
+    const int k = c->k;
+    int nb = (int)(((long)k + 255) / 256);
+    int nbz = (int)((n_mom + 255) / 256);
+    int grid = nb > nbz ? nb : nbz;
+    if (grid > c->sm_count * 16) grid = c->sm_count * 16;
+    TESS_LAUNCH((k_cell_count), grid, 256, s, c->st, honor, q.g, c->node, k, c->cell_cnt, c->cell_of, mom, n_mom);
+    TESS_LAUNCH((k_cell_scan), 1, 1024, s, c->st, honor, c->cell_cnt, c->cell_start, q.n_cells);
+    TESS_LAUNCH((k_cell_scatter), nb, 256, s, c->st, honor, c->cell_of, k, c->cell_start, c->cell_cnt, c->node,
+                                      c->has_scale ? c->inv_s2 : nullptr, c->cell_items, c->cell_xy, c->cell_inv);
+    CU_TRY(cudaGetLastError());
+    return TESS_OK;
+}
+
+static int build_lists(tess_ctx* c, const Geometry& q, int honor, cudaStream_t s) {
+    TRY(ensure_lists(c, q.T.n_tiles));
+    int grid = (q.T.n_tiles + TESS_LIST_WARPS - 1) / TESS_LIST_WARPS;
+    if (grid > c->sm_count * 16) grid = c->sm_count * 16;
+    if (c->has_scale)
+        TESS_LAUNCH((k_build_lists<true>), grid, TESS_LIST_WARPS * 32, s, c->st, honor, q.T, q.g, c->cell_start, c->cell_items,
+                                                                c->cell_xy, c->cell_inv, c->list_off, c->list_cnt,
+                                                                c->list_items, c->list_cap);
+    else
+        TESS_LAUNCH((k_build_lists<false>), grid, TESS_LIST_WARPS * 32, s, c->st, honor, q.T, q.g, c->cell_start, c->cell_items,
+                                                                 c->cell_xy, c->cell_inv, c->list_off, c->list_cnt,
+                                                                 c->list_items, c->list_cap);
+    CU_TRY(cudaGetLastError());
+    return TESS_OK;
+}
+
+template <int MODE>
+static void launch_image(tess_ctx* c, const TessImgArgs& a, bool vec, int grid, cudaStream_t s) {
+    if (c->has_scale) {
+        if (vec) TESS_LAUNCH((k_image_main<MODE, true, true>), grid, TESS_MAIN_THREADS, s, a);
+        else TESS_LAUNCH((k_image_main<MODE, true, false>), grid, TESS_MAIN_THREADS, s, a);
+    } else {
+        if (vec) TESS_LAUNCH((k_image_main<MODE, false, true>), grid, TESS_MAIN_THREADS, s, a);
+        else TESS_LAUNCH((k_image_main<MODE, false, false>), grid, TESS_MAIN_THREADS, s, a);
+    }
+}
+
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
+
+static int run_image(tess_ctx* c, const Geometry& q, int mode, int honor, int32_t* labels_ext, cudaStream_t s) {
+    TessImgArgs a;
+    memset(&a, 0, sizeof(a));
+    a.dens = c->dens; a.sig = c->sig; a.noise = c->noise;
+    a.labels_ext = labels_ext; a.lab0 = c->lab[0]; a.lab1 = c->lab[1];
+    a.mom = c->mom; a.node = c->node; a.inv_s2 = c->inv_s2;
+    a.list_off = c->list_off; a.list_cnt = c->list_cnt; a.list_items = c->list_items;
+    a.st = c->st;
+    a.H = q.T.H; a.W = q.T.W; a.x0 = q.T.x0; a.y0 = q.T.y0;
+    a.tiles_x = q.T.tiles_x; a.tiles_y = q.T.tiles_y;
+    a.k = c->k;
+    a.uniform_weight = c->uniform_weight;
+    a.honor = honor;
+    bool vec = (q.T.W % 2 == 0);
+    if (labels_ext) vec = vec && (((uintptr_t)labels_ext & 7u) == 0);
+    if (mode == 1) vec = vec && aligned16(c->dens);
+    if (mode == 2) vec = vec && aligned16(c->sig) && aligned16(c->noise);
+    int grid = q.T.n_tiles;
+    if (grid > c->sm_count * 8) grid = c->sm_count * 8;
+    if (mode == 0) launch_image<0>(c, a, vec, grid, s);
+    else if (mode == 1) launch_image<1>(c, a, vec, grid, s);
+    else launch_image<2>(c, a, vec, grid, s);
+    CU_TRY(cudaGetLastError());
+    return TESS_OK;
+}
+
+static int run_points(tess_ctx* c, const Geometry& q, int mode, int honor, long n, const double* xy, const double* w,
+                      int32_t* labels_ext, cudaStream_t s) {
+    const int nb = (int)((n + 255) / 256);
+    if (mode == 1) {
+        if (c->has_scale)
+            TESS_LAUNCH((k_points_main<1, true>), nb, 256, s, c->st, honor, q.g, c->cell_start, c->cell_items, c->cell_xy,
+                                                     c->cell_inv, n, xy, w, labels_ext, c->lab[0], c->lab[1], c->mom);
+        else
+            TESS_LAUNCH((k_points_main<1, false>), nb, 256, s, c->st, honor, q.g, c->cell_start, c->cell_items, c->cell_xy,
+                                                      c->cell_inv, n, xy, w, labels_ext, c->lab[0], c->lab[1], c->mom);
+    } else {
+        if (c->has_scale)
+            TESS_LAUNCH((k_points_main<0, true>), nb, 256, s, c->st, honor, q.g, c->cell_start, c->cell_items, c->cell_xy,
+                                                     c->cell_inv, n, xy, w, labels_ext, c->lab[0], c->lab[1], c->mom);
+        else
+            TESS_LAUNCH((k_points_main<0, false>), nb, 256, s, c->st, honor, q.g, c->cell_start, c->cell_items, c->cell_xy,
+                                                      c->cell_inv, n, xy, w, labels_ext, c->lab[0], c->lab[1], c->mom);
+    }
+    CU_TRY(cudaGetLastError());
+    return TESS_OK;
+}
+
+static int check_ready(tess_ctx* c, const char* who) {
+    TRY(bind(c));
+    if (c->source == SRC_NONE) return tess_fail(TESS_ERR_STATE, "%s: call tess_set_image or tess_set_points first", who);
+    if (c->k <= 0) return tess_fail(TESS_ERR_STATE, "%s: call tess_set_generators first", who);
+    return TESS_OK;
+}
+
+// ------------------------------------------------------------------------------------ iteration
+extern "C" int tess_lloyd_accumulate(tess_ctx* c, void* stream) {
+    TRY(check_ready(c, "tess_lloyd_accumulate"));
+    cudaStream_t s = S(stream);
+    TRY(ensure_moments(c));
+    const int M = n_moments(c);
+    const long n_mom = (long)c->k * M + TESS_TAIL;
+    long n;
+    if (c->source == SRC_IMAGE) {
+        Geometry q = window_geometry(c->x0, c->y0, c->H, c->W);
+        TRY(build_index(c, q, 1, c->mom, n_mom, s));
+        TRY(build_lists(c, q, 1, s));
+        TRY(run_image(c, q, c->img_mode, 1, nullptr, s));
+        n = c->H * c->W;
+    } else {
+        Geometry q = box_geometry(c->pb, c->k);
+        TRY(build_index(c, q, 1, c->mom, n_mom, s));
+        TRY(run_points(c, q, 1, 1, c->n_pts, c->pts_xy, c->pts_w, nullptr, s));
+        n = c->n_pts;
+    }
+    const int nb = (c->k + 255) / 256;
+    TESS_LAUNCH((k_count_prefilter), nb, 256, s, c->st, 1, c->mom, M, c->k, c->prev_count);
+    long want = (n + 256L * 8 - 1) / (256L * 8);
+    int grid = (int)(want < 1 ? 1 : (want > c->sm_count * 8 ? c->sm_count * 8 : want));
+    double* tail = c->mom + (long)c->k * M;
+    if (c->source == SRC_IMAGE && c->img_mode == 1)
+        TESS_LAUNCH((k_compare_labels<1>), grid, 256, s, c->st, 1, c->lab[0], c->lab[1], n, c->dens, nullptr, nullptr, 0, tail);
+    else if (c->source == SRC_IMAGE)
+        TESS_LAUNCH((k_compare_labels<2>), grid, 256, s, c->st, 1, c->lab[0], c->lab[1], n, nullptr, c->sig, c->noise,
+                                                c->uniform_weight, tail);
+    else
+        TESS_LAUNCH((k_compare_labels<0>), grid, 256, s, c->st, 1, c->lab[0], c->lab[1], n, nullptr, nullptr, nullptr, 0, tail);
+    CU_TRY(cudaGetLastError());
+    return TESS_OK;
+}
+
+extern "C" int tess_moments_ptr(tess_ctx* c, double** dev_ptr, long* n_doubles, int* n_mom) {
+    TRY(check_ready(c, "tess_moments_ptr"));
+    TRY(ensure_moments(c));
+    const int M = n_moments(c);
+    if (dev_ptr) *dev_ptr = c->mom;
+    if (n_doubles) *n_doubles = (long)c->k * M + TESS_TAIL;
+    if (n_mom) *n_mom = M;
+    return TESS_OK;
+}
+
+extern "C" int tess_lloyd_update(tess_ctx* c, void* stream) {
+    TRY(check_ready(c, "tess_lloyd_update"));
+    if (!c->mom) return tess_fail(TESS_ERR_STATE, "tess_lloyd_update: no accumulate has run");
+    cudaStream_t s = S(stream);
+    const int M = n_moments(c);
+    const int nb = (c->k + 255) / 256;
+    double* tail = c->mom + (long)c->k * M;
+    if (M == 6)
+        TESS_LAUNCH((k_update_nodes<6>), nb, 256, s, c->st, 1, c->mom, tail, c->k, c->node, c->has_scale ? c->scale : nullptr,
+                                            c->inv_s2, c->wvt_update);
+    else
+        TESS_LAUNCH((k_update_nodes<4>), nb, 256, s, c->st, 1, c->mom, tail, c->k, c->node, nullptr, c->inv_s2, 0);
+    CU_TRY(cudaGetLastError());
+    return TESS_OK;
+}
+
+extern "C" int tess_lloyd_step(tess_ctx* c, long n_steps, void* stream) {
+    for (long i = 0; i < n_steps; ++i) {
+        TRY(tess_lloyd_accumulate(c, stream));
+        TRY(tess_lloyd_update(c, stream));
+    }
+    return TESS_OK;
+}
+
+static int fetch_state(tess_ctx* c, cudaStream_t s) {
+    CU_TRY(cudaMemcpyAsync(c->h_st, c->st, sizeof(TessState), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    return TESS_OK;
+}
+
+extern "C" int tess_lloyd_run(tess_ctx* c, long max_iters, int* converged, long* n_iters, void* stream) {
+    TRY(check_ready(c, "tess_lloyd_run"));
+    cudaStream_t s = S(stream);
+    // lloyd.pyx:85-90: at most max_iters + 2 loop bodies (and at least one)
+    long budget = max_iters + 2;
+    if (budget < 1) budget = 1;
+    TRY(fetch_state(c, s));
+    const long long start = c->h_st->iters_done;
+    long done = 0;
+    int conv = c->h_st->converged;
+    while (!conv && done < budget) {
+        long chunk = budget - done;
+        if (chunk > 4) chunk = 4;
+        TRY(tess_lloyd_step(c, chunk, stream));
+        TRY(fetch_state(c, s));
+        done = (long)(c->h_st->iters_done - start);
+        conv = c->h_st->converged;
+        if (c->h_st->flags & TESS_FLAG_NONFINITE) {
+            // the reference's next cKDTree build raises ValueError on NaN nodes (lloyd.pyx:54);
+            // if the budget ended on this very iteration it returns them with converged = False
+            if (converged) *converged = 0;
+            if (n_iters) *n_iters = done;
+            if (done < budget)
+                return tess_fail(TESS_ERR_NONFINITE,
+                                 "tess_lloyd_run: a bin with pixels has zero total weight: generator became NaN/Inf "
+                                 "after iteration %ld", done);
+            return TESS_OK;
+        }
+    }
+    if (converged) *converged = conv;
+    if (n_iters) *n_iters = done;
+    return TESS_OK;
+}
+
+// ------------------------------------------------------------------------------------ results
+extern "C" int tess_get_labels(tess_ctx* c, int32_t* out, void* stream) {
+    TRY(check_ready(c, "tess_get_labels"));
+    if (!out) return tess_fail(TESS_ERR_ARG, "tess_get_labels: out is null");
+    const long n = c->source == SRC_IMAGE ? c->H * c->W : c->n_pts;
+    long want = (n + 256L * 8 - 1) / (256L * 8);
+    int grid = (int)(want < 1 ? 1 : (want > c->sm_count * 16 ? c->sm_count * 16 : want));
+    TESS_LAUNCH((k_export_labels), grid, 256, S(stream), c->st, c->lab[0], c->lab[1], n, out);
+    CU_TRY(cudaGetLastError());
+    return TESS_OK;
+}
+
+extern "C" int tess_get_moments(tess_ctx* c, double* out, void* stream) {
+    TRY(check_ready(c, "tess_get_moments"));
+    if (!out) return tess_fail(TESS_ERR_ARG, "tess_get_moments: out is null");
+    if (!c->mom) return tess_fail(TESS_ERR_STATE, "tess_get_moments: no accumulate has run");
+    TESS_LAUNCH((k_export_moments), (c->k + 255) / 256, 256, S(stream), c->mom, n_moments(c), c->k, out);
+    CU_TRY(cudaGetLastError());
+    return TESS_OK;
+}
+
+extern "C" int tess_get_generators(tess_ctx* c, double* out, void* stream) {
+    TRY(bind(c));
+    if (c->k <= 0) return tess_fail(TESS_ERR_STATE, "tess_get_generators: no generators set");
+    if (!out) return tess_fail(TESS_ERR_ARG, "tess_get_generators: out is null");
+    CU_TRY(cudaMemcpyAsync(out, c->node, sizeof(double) * 2 * (size_t)c->k, cudaMemcpyDeviceToDevice, S(stream)));
+    return TESS_OK;
+}
+
+extern "C" int tess_get_scales(tess_ctx* c, double* out, void* stream) {
+    TRY(bind(c));
+    if (c->k <= 0) return tess_fail(TESS_ERR_STATE, "tess_get_scales: no generators set");
+    if (!out) return tess_fail(TESS_ERR_ARG, "tess_get_scales: out is null");
+    if (c->has_scale)
+        CU_TRY(cudaMemcpyAsync(out, c->scale, sizeof(double) * (size_t)c->k, cudaMemcpyDeviceToDevice, S(stream)));
+    else
+        TESS_LAUNCH((k_fill), (c->k + 255) / 256, 256, S(stream), out, c->k, 1.0);
+    CU_TRY(cudaGetLastError());
+    return TESS_OK;
+}
+
+extern "C" int tess_get_iter_stats(tess_ctx* c, double* delta, long* n_changed, long* n_iters_done, void* stream) {
+    TRY(bind(c));
+    TRY(fetch_state(c, S(stream)));
+    if (delta) *delta = c->h_st->delta;
+    if (n_changed) *n_changed = c->h_st->counted ? (long)c->h_st->n_changed : -1;
+    if (n_iters_done) *n_iters_done = (long)c->h_st->iters_done;
+    return TESS_OK;
+}
+
+// ------------------------------------------------------------------------------------ assignment only
+extern "C" int tess_assign_grid(tess_ctx* c, double x0, double y0, long H, long W, int32_t* labels_out, void* stream) {
+    TRY(bind(c));
+    if (c->k <= 0) return tess_fail(TESS_ERR_STATE, "tess_assign_grid: call tess_set_generators first");
+    if (H <= 0 || W <= 0 || !labels_out) return tess_fail(TESS_ERR_ARG, "tess_assign_grid: bad arguments");
+    cudaStream_t s = S(stream);
+    Geometry q = window_geometry(x0, y0, H, W);
+    TRY(build_index(c, q, 0, nullptr, 0, s));
+    TRY(build_lists(c, q, 0, s));
+    TRY(run_image(c, q, 0, 0, labels_out, s));
+    return TESS_OK;
+}
+
+extern "C" int tess_assign_points(tess_ctx* c, long m, const double* xy, int32_t* out, void* stream) {
+    TRY(bind(c));
+    if (c->k <= 0) return tess_fail(TESS_ERR_STATE, "tess_assign_points: call tess_set_generators first");
+    if (m <= 0 || !xy || !out) return tess_fail(TESS_ERR_ARG, "tess_assign_points: bad arguments");
+    cudaStream_t s = S(stream);
+    double box[4];
+    TRY(points_bbox(c, m, xy, box, s));
+    Geometry q = box_geometry(box, c->k);
+    TRY(build_index(c, q, 0, nullptr, 0, s));
+    TRY(run_points(c, q, 0, 0, m, xy, nullptr, out, s));
+    return TESS_OK;
+}
+
+extern "C" int tess_assign_grid_exhaustive(tess_ctx* c, double x0, double y0, long H, long W, int32_t* labels_out,
+                                           void* stream) {
+    TRY(bind(c));
+    if (c->k <= 0) return tess_fail(TESS_ERR_STATE, "tess_assign_grid_exhaustive: call tess_set_generators first");
+    if (H <= 0 || W <= 0 || !labels_out) return tess_fail(TESS_ERR_ARG, "tess_assign_grid_exhaustive: bad arguments");
+    const long n = H * W;
+    const int nb = (int)((n + 255) / 256);
+    if (c->has_scale)
+        TESS_LAUNCH((k_assign_exhaustive<true, true>), nb, 256, S(stream), c->node, c->inv_s2, c->k, n, W, x0, y0, nullptr, labels_out);
+    else
+        TESS_LAUNCH((k_assign_exhaustive<false, true>), nb, 256, S(stream), c->node, c->inv_s2, c->k, n, W, x0, y0, nullptr, labels_out);
+    CU_TRY(cudaGetLastError());
+    return TESS_OK;
+}
+
+extern "C" int tess_assign_points_exhaustive(tess_ctx* c, long m, const double* xy, int32_t* out, void* stream) {
+    TRY(bind(c));
+    if (c->k <= 0) return tess_fail(TESS_ERR_STATE, "tess_assign_points_exhaustive: call tess_set_generators first");
+    if (m <= 0 || !xy || !out) return tess_fail(TESS_ERR_ARG, "tess_assign_points_exhaustive: bad arguments");
+    const int nb = (int)((m + 255) / 256);
+    if (c->has_scale)
+        TESS_LAUNCH((k_assign_exhaustive<true, false>), nb, 256, S(stream), c->node, c->inv_s2, c->k, m, 1, 0.0, 0.0, xy, out);
+    else
+        TESS_LAUNCH((k_assign_exhaustive<false, false>), nb, 256, S(stream), c->node, c->inv_s2, c->k, m, 1, 0.0, 0.0, xy, out);
+    CU_TRY(cudaGetLastError());
+    return TESS_OK;
+}

@@ -1,0 +1,123 @@
+// tess_common.cuh -- shared definitions for the sm_100a kernels of libtess_b200.so.
+//
+// Geometry of the pruning hierarchy (image mode):
+//   super-tile  64 x 64 px   one CTA work unit; candidate list built by k_build_lists
+//   warp tile   32 x  8 px   one warp step; each lane owns a 2-column x 4-row patch (8 px),
+//                            so every row of a warp tile is 16 lanes x 16 B = 256 B contiguous
+//   leaf         8 x  8 px   8 lanes (4 across x 2 down); shortest candidate list
+// A generator g can be the nearest one somewhere in a rectangle T only if
+//   mind2(g,T) <= min_h maxd2(h,T)        (times the scale weights in WVT mode)
+// so each level keeps exactly those (plus a 2^-39 relative slack that covers every fp64
+// rounding difference between these bounds and the pinned per-pixel formula).
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#ifdef TESS_EMU
+#define TESS_LAUNCH(kern, grid, block, stream, ...) emu::launch(kern, dim3(grid), dim3(block), __VA_ARGS__)
+#else
+#include <cuda_runtime.h>
+#define TESS_LAUNCH(kern, grid, block, stream, ...) kern<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#endif
+
+#define TESS_TS 64            // super-tile edge, px
+#define TESS_WT_W 32          // warp-tile width, px
+#define TESS_WT_H 8           // warp-tile height, px
+#define TESS_CAP 1024         // candidates of one tile staged in shared memory
+#define TESS_LEAF_CAP 32      // candidates of one 8x8 leaf
+#define TESS_MAIN_THREADS 128 // image main kernel: 4 warps
+#define TESS_FULL 0xffffffffu
+#define TESS_BRUTE (-1)       // list_cnt marker: list did not fit, scan every generator
+
+// relative slack on bound comparisons, 1 + 2^-39
+#define TESS_SLACK 1.0000000000018189894035458564758300781250
+
+struct TessRect {
+    double x0, x1, y0, y1;   // closed ranges of point coordinates
+};
+
+// Uniform grid of generators (counting sort).  Cell (i,j) holds generators with
+// floor((gx-ox)/cs) == i (clamped to [0,gw-1]: border cells extend to infinity).
+struct TessGrid {
+    double ox, oy, cs, inv_cs, tol;
+    int gw, gh;
+};
+
+// Device-resident iteration state (one per context).
+struct TessState {
+    double delta;                    // sum |old-new|^2 of the last update   (lloyd.pyx:76-81)
+    double min_inv_s2;               // min_j 1/scale_j^2 (1 when unscaled): bounds the search radius
+    unsigned long long min_inv_next; // bit pattern of the running min while scales are being updated
+    unsigned long long n_changed;    // labels changed in the last accumulate (valid if counted)
+    long long iters_done;            // loop bodies executed since set_generators
+    long long conv_iter;             // iteration index (0-based) at which the latch closed
+    int count_changed;               // 1 if some bin's population differs from the previous iteration
+    int counted;                     // 1 if n_changed was actually counted this iteration
+    int converged;                   // latch: once set every kernel of later iterations is a no-op
+    int flags;                       // TESS_FLAG_*; non-zero also stops the iteration kernels
+    int tile_counter;                // dynamic tile scheduler of the main kernel
+    int have_prev;                   // previous-iteration labels exist
+    int n_brute;                     // tiles that fell back to the exhaustive scan (diagnostic)
+    unsigned list_cursor;            // bump allocator of the candidate-list arena
+    unsigned ticket;                 // "last block done" counters of the fused tail kernels
+    unsigned ticket2;
+};
+#define TESS_FLAG_NONFINITE 1
+// iteration kernels are no-ops once the latch closed or an error flag is up (unless forced)
+#define TESS_STOPPED(st, honor) ((honor) && ((st)->converged | (st)->flags))
+
+__host__ __device__ __forceinline__ double tess_sq(double a) { return a * a; }
+
+// max over the rectangle of the squared distance to (gx,gy) -- an upper bound (to rounding)
+__host__ __device__ __forceinline__ double tess_maxd2(const TessRect& r, double gx, double gy) {
+    double ax = fmax(fabs(gx - r.x0), fabs(gx - r.x1));
+    double ay = fmax(fabs(gy - r.y0), fabs(gy - r.y1));
+    return ax * ax + ay * ay;
+}
+// min over the rectangle of the squared distance to (gx,gy)
+__host__ __device__ __forceinline__ double tess_mind2(const TessRect& r, double gx, double gy) {
+    double ax = fmax(fmax(r.x0 - gx, gx - r.x1), 0.0);
+    double ay = fmax(fmax(r.y0 - gy, gy - r.y1), 0.0);
+    return ax * ax + ay * ay;
+}
+
+__host__ __device__ __forceinline__ int tess_cell_coord(double g, double o, double inv_cs, int n) {
+    double f = floor((g - o) * inv_cs);
+    f = fmin(fmax(f, 0.0), (double)(n - 1));   // NaN -> 0
+    return (int)f;
+}
+
+#ifndef TESS_EMU
+#define TESS_DEVFN __device__ __forceinline__
+#else
+#define TESS_DEVFN inline
+#endif
+
+TESS_DEVFN double tess_warp_min(double v) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v = fmin(v, __shfl_xor_sync(TESS_FULL, v, m));
+    return v;
+}
+TESS_DEVFN double tess_warp_sum(double v) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(TESS_FULL, v, m);
+    return v;
+}
+TESS_DEVFN unsigned tess_lanemask_lt(int lane) { return (1u << lane) - 1u; }
+
+// The pinned squared distance: fl(fl(dx*dx) + fl(dy*dy)), never contracted to an FMA.
+TESS_DEVFN double tess_d2_pinned(double px, double py, double gx, double gy) {
+    double dx = __dsub_rn(px, gx);
+    double dy = __dsub_rn(py, gy);
+    return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+}
+
+// (distance, generator index) packed so that one unsigned compare is the lexicographic
+// "smaller distance, then lower index" order.  d2 >= +0 always, so its bit pattern orders
+// like the value; NaN/Inf patterns sort last.
+typedef unsigned __int128 tess_key_t;
+TESS_DEVFN tess_key_t tess_make_key(double d, int gid) {
+    return ((tess_key_t)(unsigned long long)__double_as_longlong(d) << 32) | (unsigned)gid;
+}
+#define TESS_KEY_MAX (~(tess_key_t)0)
+TESS_DEVFN int tess_key_gid(tess_key_t k) { return (int)(unsigned)k; }

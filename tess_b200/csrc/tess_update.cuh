@@ -1,0 +1,192 @@
+// tess_update.cuh -- the O(k) tail of a Lloyd iteration and the convergence test.
+//
+//   k_count_prefilter : did any bin's population change since the previous iteration?
+//   k_compare_labels  : only if not -- count labels that differ from the previous iteration;
+//                       its last block writes the local "changed" flag into the tail slot of the
+//                       moment vector (so a multi-GPU host sums it in the same allreduce as the
+//                       moments)
+//   k_update_nodes    : node update (reference tess/lloyd.pyx:66-74), delta (lloyd.pyx:76-81),
+//                       convergence latch (lloyd.pyx:85-86), optional WVT scale update
+//
+// Convergence.  The reference stops when the node table is an exact fixed point (delta == 0,
+// lloyd.pyx:85).  With its sequential sums that happens exactly when the labels of two
+// consecutive iterations are identical.  The GPU sums are order-nondeterministic in the last
+// bits, so the latch uses the order-independent form of the same test: no label changed since
+// the previous iteration.  When the latch closes the node table is NOT rewritten (and delta is
+// reported as 0), which reproduces the reference's bitwise node_{t+1} == node_t.
+#pragma once
+#include "tess_common.cuh"
+
+// moment-vector tail layout (after k*M doubles)
+#define TESS_TAIL 2
+#define TESS_TAIL_CHANGED 0   // sum over ranks of (labels changed ? 1 : 0)
+#define TESS_TAIL_SPARE 1
+
+__global__ void __launch_bounds__(256)
+k_count_prefilter(TessState* st, int honor, const double* mom, int M, int k, double* prev_count) {
+    if (TESS_STOPPED(st, honor)) return;
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= k) return;
+    double c = mom[(long)j * M];
+    if (c != prev_count[j]) st->count_changed = 1;   // benign race: every writer stores 1
+    prev_count[j] = c;
+}
+
+// Compares the two label buffers on the pixels/points that take part in the sums.
+// MASK_MODE 0: all; 1: finite density; 2: finite signal, noise and weight
+template <int MASK_MODE>
+__global__ void __launch_bounds__(256)
+k_compare_labels(TessState* st, int honor, int32_t* lab0, int32_t* lab1, long n, const double* dens,
+                 const double* sig, const double* noise, int uniform_weight, double* mom_tail) {
+    if (TESS_STOPPED(st, honor)) return;
+    __shared__ int s_last;
+    const bool need = (!st->count_changed) && st->have_prev;
+    if (need) {
+        const int32_t* cur = (st->iters_done & 1) ? lab1 : lab0;
+        const int32_t* prev = (st->iters_done & 1) ? lab0 : lab1;
+        long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+        const long stride = (long)gridDim.x * blockDim.x;
+        unsigned long long diff = 0;
+        for (; i < n; i += stride) {
+            bool ok = true;
+            if (MASK_MODE == 1) ok = isfinite(dens[i]);
+            if (MASK_MODE == 2) {
+                const double S = sig[i], N = noise[i];
+                double wv = 1.0;
+                if (!uniform_weight) { const double q = __ddiv_rn(S, N); wv = __dmul_rn(q, q); }
+                ok = isfinite(S) && isfinite(N) && isfinite(wv);
+            }
+            if (ok && cur[i] != prev[i]) ++diff;
+        }
+        for (int m = 16; m >= 1; m >>= 1) diff += __shfl_xor_sync(TESS_FULL, diff, m);
+        if ((threadIdx.x & 31) == 0 && diff) atomicAdd(&st->n_changed, diff);
+    }
+    // last block done: publish the flag
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        const unsigned long long nch = *((volatile unsigned long long*)&st->n_changed);
+        const bool changed = !need || nch != 0ull;
+        st->counted = need ? 1 : 0;
+        mom_tail[TESS_TAIL_CHANGED] = changed ? 1.0 : 0.0;
+        mom_tail[TESS_TAIL_SPARE] = 0.0;
+        st->ticket = 0u;
+    }
+}
+
+// One thread per generator.  `mom` holds the (globally reduced) moments, `mom_tail` the summed
+// "changed" flags.  Nodes are rewritten in place unless the latch closes.
+template <int M>
+__global__ void __launch_bounds__(256)
+k_update_nodes(TessState* st, int honor, const double* mom, const double* mom_tail, int k, double* node,
+               double* scale, double* inv_s2, int wvt_update) {
+    if (TESS_STOPPED(st, honor)) return;
+    __shared__ double s_red[8];
+    __shared__ int s_last;
+    const bool changed = mom_tail[TESS_TAIL_CHANGED] != 0.0;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (changed) {
+        double d = 0.0;
+        if (j < k) {
+            const double* m = mom + (long)j * M;
+            double nx = 0.0, ny = 0.0;
+            if (m[0] > 0.0) {   // population test, not weight (lloyd.pyx:68)
+                nx = __ddiv_rn(m[2], m[1]);
+                ny = __ddiv_rn(m[3], m[1]);
+            }
+            if (!(isfinite(nx) && isfinite(ny))) atomicOr(&st->flags, TESS_FLAG_NONFINITE);
+            const double dx = __dsub_rn(node[2 * (long)j], nx), dy = __dsub_rn(node[2 * (long)j + 1], ny);
+            d = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+            node[2 * (long)j] = nx;
+            node[2 * (long)j + 1] = ny;
+            if (M == 6 && wvt_update && scale) {
+                // WVT scale length (Diehl & Statler 2006 eq. 4, as in vorbin): sqrt(area / (S/N));
+                // bins with no pixels or no signal keep their scale.
+                const double sn = __ddiv_rn(m[4], __dsqrt_rn(m[5]));
+                if (m[0] > 0.0 && sn > 0.0 && isfinite(sn)) {
+                    const double sc = __dsqrt_rn(__ddiv_rn(m[0], sn));
+                    scale[j] = sc;
+                    inv_s2[j] = __ddiv_rn(1.0, __dmul_rn(sc, sc));
+                }
+                atomicMin(&st->min_inv_next, (unsigned long long)__double_as_longlong(inv_s2[j]));
+            }
+        }
+        // block reduction of delta (reporting only: the reference's sequential order is not reproduced)
+        double s = tess_warp_sum(d);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            double v = (threadIdx.x < (blockDim.x >> 5)) ? s_red[threadIdx.x] : 0.0;
+            v = tess_warp_sum(v);
+            if (threadIdx.x == 0) atomicAdd(&st->delta, v);
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&st->ticket2, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        if (!changed) {
+            st->converged = 1;
+            st->conv_iter = st->iters_done;
+            st->delta = 0.0;
+        } else if (M == 6 && wvt_update && scale) {
+            st->min_inv_s2 = __longlong_as_double((long long)*((volatile unsigned long long*)&st->min_inv_next));
+        }
+        st->iters_done += 1;
+        st->have_prev = 1;
+        st->ticket2 = 0u;
+    }
+}
+
+// finiteness of the generator table / scales, inv_s2 (run at set_generators)
+__global__ void __launch_bounds__(256)
+k_check_generators(TessState* st, const double* node, const double* scale, double* inv_s2, int k) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= k) return;
+    bool bad = !(isfinite(node[2 * (long)j]) && isfinite(node[2 * (long)j + 1]));
+    if (scale) {
+        const double s = scale[j];
+        const double inv = __ddiv_rn(1.0, __dmul_rn(s, s));
+        inv_s2[j] = inv;
+        if (!(isfinite(inv) && inv > 0.0)) bad = true;
+    }
+    if (bad) atomicOr(&st->flags, TESS_FLAG_NONFINITE);
+}
+
+// min over inv_s2 (the largest scale length bounds the search radius); single CTA
+__global__ void __launch_bounds__(1024)
+k_min_inv_s2(TessState* st, const double* inv_s2, int k) {
+    __shared__ double s_red[32];
+    double v = INFINITY;
+    for (int j = threadIdx.x; j < k; j += blockDim.x) v = fmin(v, inv_s2[j]);
+    v = tess_warp_min(v);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double u = (threadIdx.x < (blockDim.x >> 5)) ? s_red[threadIdx.x] : INFINITY;
+        u = tess_warp_min(u);
+        if (threadIdx.x == 0) st->min_inv_s2 = u;
+    }
+}
+
+// moments [k][M] -> [k][6] with zero padding (tess_get_moments)
+__global__ void __launch_bounds__(256)
+k_export_moments(const double* mom, int M, int k, double* out) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= k) return;
+    for (int c = 0; c < 6; ++c) out[(long)j * 6 + c] = (c < M) ? mom[(long)j * M + c] : 0.0;
+}
+
+// widen / copy labels of the iteration that ran last (buffer parity lives on the device)
+__global__ void __launch_bounds__(256)
+k_export_labels(const TessState* st, const int32_t* lab0, const int32_t* lab1, long n, int32_t* out) {
+    const int32_t* cur = ((st->iters_done - 1) & 1) ? lab1 : lab0;
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = cur[i];
+}
