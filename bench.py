@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""
+bench.py -- throughput of the Lloyd / WVT iteration (BASELINE.json: "WVT Lloyd ms/iter and Gpix/s,
+8192^2 px x 1e5 bins; 1/2/4/8 B200 vs HBM roofline").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c4|c2] [--mode cvt|sn]
+
+A "step" is one Lloyd iteration (grid index rebuild + assignment + per-bin sums + node update) over
+the whole synthetic map.  N = 1: configs[2], 8192^2 px x 1e5 generators (headline).  N > 1 (under
+torchrun, one rank per GPU): configs[3], 32768^2 px x 1e6 generators, pixel rows sharded across
+ranks, one NCCL all-reduce of the per-bin moment vector per iteration (strong scaling: the map is
+fixed); rank 0 additionally times the same map on one GPU so the speed-up is apples to apples.
+Synthetic data (no network): the demo's Gaussian S/N map scaled to N, generators
+drawn from the same Gaussian (p ~ w) with continuous coordinates (tie-free).
+
+Prints ONE JSON line (rank 0).  `value` = Gpix/s with inputs resident in HBM; `e2e` = the same
+through the public API with pinned HOST buffers (H2D of the map + generators and D2H of labels +
+nodes inside the timed region); `roofline` = algorithmic bytes of the dominant kernel / its device
+time measured live with CUDA events, against MEASURED_PEAKS.json; `cpu_baseline` = the compiled
+reference (oracle/_ref, tess/lloyd.pyx unmodified) timed on a bounded slab of the same workload.
+`--impl reference` times only that CPU reference.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "lloyd_wvt_iteration_throughput"
+UNIT = "Gpix/s"
+WORKLOADS = {
+    "c3": dict(N=8192, k=100000, name="synthetic 8192^2 px S/N map, 1e5 bins (configs[2], headline)"),
+    "c4": dict(N=32768, k=1000000, name="synthetic 32768^2 px S/N map, 1e6 bins, row-sharded (configs[3])"),
+    "small": dict(N=2048, k=6250, name="synthetic 2048^2 px S/N map, 6250 bins (debug)"),
+}
+BYTES_PER_PX = {"cvt": 12.0, "sn": 20.0}     # 8 (density) + 4 (label) | 8 + 8 + 4
+
+
+# ------------------------------------------------------------------------------------ synthetic data
+def sigma(N):
+    return 50.0 * N / 256.0
+
+
+def gauss_seeds(N, k, seed=0):
+    """k generators drawn with density ~ w = (S/N)^2 (a Gaussian of std sigma/sqrt2), inside the map."""
+    rng = np.random.default_rng(seed)
+    s = sigma(N) / np.sqrt(2.0)
+    out = np.empty((0, 2))
+    while out.shape[0] < k:
+        c = rng.normal(N / 2.0, s, (2 * k, 2))
+        c = c[(c[:, 0] > 0) & (c[:, 0] < N - 1) & (c[:, 1] > 0) & (c[:, 1] < N - 1)]
+        out = np.vstack((out, c))
+    return np.ascontiguousarray(out[:k])
+
+
+def device_signal_rows(N, r0, r1, torch, device):
+    """Rows [r0, r1) of signal[y, x] = 10 exp(-((x-N/2)^2 + (y-N/2)^2) / (2 sigma^2)); noise == 1."""
+    s = sigma(N)
+    ax = torch.arange(N, dtype=torch.float64, device=device)
+    gx = torch.exp(-((ax - N / 2.0) ** 2) / (2.0 * s * s))
+    return 10.0 * gx[r0:r1, None] * gx[None, :]
+
+
+def host_signal_rows(N, r0, r1):
+    s = sigma(N)
+    ax = np.arange(N, dtype=np.float64)
+    gx = np.exp(-((ax - N / 2.0) ** 2) / (2.0 * s * s))
+    return 10.0 * gx[r0:r1, None] * gx[None, :]
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.f = None
+        self.p = None
+
+    def start(self):
+        try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
+        self.p.terminate()
+        try:
+            self.p.wait(5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().splitlines():
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        self.f.close()
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------ CPU reference
+def reference_lloyd_callable():
+    """(callable(xy, w, nodes, max_iters) -> ..., kind).  The compiled reference when present
+    (oracle/_ref: tess/lloyd.pyx built unmodified), else the oracle's C port."""
+    from oracle import oracle as O
+    if O.ref_available():
+        try:
+            O.ref_module()
+            return (lambda xy, w, nd, mi: O.ref_lloyd(xy, w, nd, mi)), "reference"
+        except Exception:
+            pass
+    return (lambda xy, w, nd, mi: O.c_lloyd(xy, w, nd, mi)), "port"
+
+
+def cpu_slab(N, k, rows, seed=0):
+    """A centred slab of `rows` image rows of the workload as the reference's point set
+    (tess/voronoi.py:281-287) with ALL k generators."""
+    r0 = max(0, N // 2 - rows // 2)
+    r1 = min(N, r0 + rows)
+    sig = host_signal_rows(N, r0, r1)
+    w = (sig / 1.0) ** 2
+    x, y = np.meshgrid(np.arange(N, dtype=float), np.arange(r0, r1, dtype=float))
+    xy = np.column_stack((x.ravel(), y.ravel()))
+    return xy, np.ascontiguousarray(w.ravel()), gauss_seeds(N, k, seed), (r0, r1)
+
+
+def time_reference(N, k, rows, iters):
+    """Seconds per reference iteration on the slab (1 thread: lloyd.pyx:55 passes no `workers`)."""
+    fn, kind = reference_lloyd_callable()
+    xy, w, seeds, rr = cpu_slab(N, k, rows)
+    t0 = time.perf_counter()
+    fn(xy, w, seeds, iters - 2)                   # max_iters = t - 2 runs exactly t loop bodies
+    dt = (time.perf_counter() - t0) / iters
+    return dt, xy.shape[0], kind, rr
+
+
+def run_reference_arm(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    N, k = wl["N"], wl["k"]
+    total = args.steps + args.warmup
+    # ~1.5 Mpix/s on one core: size the slab so that the whole run takes about two minutes
+    px_budget = 1.5e6 * 120.0 / max(total, 1)
+    rows = int(min(N, max(16, px_budget // N)))
+    fn, kind = reference_lloyd_callable()
+    xy, w, seeds, rr = cpu_slab(N, k, rows)
+    for _ in range(args.warmup):
+        fn(xy, w, seeds, -1)                      # max_iters = -1: exactly one loop body
+    times = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        fn(xy, w, seeds, -1)
+        times.append(time.perf_counter() - t0)
+    ms = 1e3 * float(np.mean(times))
+    val = xy.shape[0] / (ms * 1e-3) / 1e9
+    sample = "rows %d..%d of the %dx%d map (%d px) x all %d generators, 1 Lloyd iteration per step" % (
+        rr[0], rr[1], N, N, xy.shape[0], k)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["name"], "mode": args.mode, "sample": sample, "host_cpus": os.cpu_count()},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=[None] + sorted(WORKLOADS))
+    ap.add_argument("--mode", default="cvt", choices=["cvt", "sn"],
+                    help="cvt: density map, 4 moments, 12 B/px (reference parity); sn: signal+noise maps, 6 moments, 20 B/px")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-single", action="store_true", help="N>1: skip rank 0's one-GPU run of the same map")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    wl_key = args.workload or ("c3" if max(world, args.gpus) == 1 else "c4")
+    wl = WORKLOADS[wl_key]
+    if args.impl == "reference":
+        return run_reference_arm(args, wl)
+
+    import torch
+    import torch.distributed as dist
+    from tess_b200.engine import Engine
+    from tess_b200 import _capi
+    from tess_b200.sharded import ShardedLloyd, shard_rows
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    N, k, mode = wl["N"], wl["k"], args.mode
+    r0, r1 = shard_rows(N, world)[rank]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maps(r0, r1):
+        sig = device_signal_rows(N, r0, r1, torch, device)
+        if mode == "cvt":
+            return dict(density=(sig / 1.0) ** 2)
+        return dict(signal=sig, noise=torch.ones_like(sig))
+
+    seeds_h = gauss_seeds(N, k)
+    seeds = torch.from_numpy(seeds_h).to(device)
+    eng = Engine(local)
+    drv = ShardedLloyd(eng) if world > 1 else None
+
+    def setup(e, r0, r1):
+        m = maps(r0, r1)
+        e.set_image(y0=float(r0), **m)
+        e.set_generators(seeds)
+
+    def step(n=1):
+        if drv is not None:
+            drv.step(n)
+        else:
+            eng.step(n)
+
+    setup(eng, r0, r1)
+    launches0 = eng.api.launch_count()
+    step(args.warmup)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = eng.api.launch_count()
+    ev0.record()
+    step(args.steps)
+    ev1.record()
+    barrier()
+    gpu_launches = eng.api.launch_count() - l0
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = (float(N) * N) / (ms_step * 1e-3) / 1e9
+    conv, _ = eng.status()
+
+    # ---- dominant kernel, timed live with CUDA events on its own stream (second pass)
+    eng.set_option(_capi.OPT_KERNEL_TIMING, 1)
+    eng.kernel_timing()
+    step(min(args.steps, 64))
+    torch.cuda.synchronize()
+    k_ms, k_n = eng.kernel_timing()
+    eng.set_option(_capi.OPT_KERNEL_TIMING, 0)
+    peak, peak_src = measured_peaks()
+    roof = None
+    if k_n > 0:
+        k_ms_avg = k_ms / k_n
+        alg_bytes = BYTES_PER_PX[mode] * float(r1 - r0) * N          # per launch (this rank's rows)
+        ach = alg_bytes / (k_ms_avg * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "kernel": "k_image_main", "kernel_ms": k_ms_avg, "kernel_share_of_step": k_ms_avg / ms_step,
+                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                "step_frac_of_roofline": (BYTES_PER_PX[mode] * float(N) * N / world / (ms_step * 1e-3) / 1e9) / peak}
+        tf = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes per launch from the ncu --set full capture
+        if os.path.exists(tf):
+            try:
+                roof["traffic"] = json.load(open(tf)).get("%s_%s" % (wl_key, mode))
+            except Exception:
+                pass
+
+    # ---- end to end through the public API with pinned host buffers
+    e2e = None
+    if not args.no_e2e:
+        m = maps(r0, r1)
+        host_in = {kk: v.cpu().pin_memory() for kk, v in m.items()}
+        del m
+        seeds_pin = torch.from_numpy(seeds_h).pin_memory()
+        lab_pin = torch.empty((r1 - r0, N), dtype=torch.int32).pin_memory()
+        node_pin = torch.empty((k, 2), dtype=torch.float64).pin_memory()
+        e2 = Engine(local)
+        d2 = ShardedLloyd(e2) if world > 1 else None
+
+        def e2e_step():
+            e2.set_image(y0=float(r0), **host_in)          # H2D of this step's maps (pinned -> device)
+            e2.set_generators(seeds_pin)                    # H2D of the generator table
+            (d2.step(1) if d2 is not None else e2.step(1))
+            lab_pin.copy_(e2.labels(), non_blocking=True)   # D2H of the results
+            node_pin.copy_(e2.generators(), non_blocking=True)
+            torch.cuda.synchronize()
+
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        n_e2e = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / n_e2e
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        h2d = sum(v.numel() * 8 for v in host_in.values()) + seeds_pin.numel() * 8
+        d2h = lab_pin.numel() * 4 + node_pin.numel() * 8
+        e2e = {"value": (float(N) * N) / dt / 1e9, "unit": UNIT, "ms_per_step": dt * 1e3,
+               "h2d_bytes_per_step": int(h2d * world), "d2h_bytes_per_step": int(d2h * world),
+               "call": "Engine.set_image(pinned host maps) + set_generators + step(1) + labels()/generators() to pinned host"}
+        e2.close()
+        del host_in, lab_pin
+
+    # ---- N > 1: the same map on ONE GPU (rank 0), so the speed-up is apples to apples
+    single = None
+    if world > 1 and not args.no_single:
+        barrier()
+        if rank == 0:
+            e1 = Engine(local)
+            setup(e1, 0, N)
+            e1.step(args.warmup)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); e1.step(args.steps); b.record(); torch.cuda.synchronize()
+            ms1 = a.elapsed_time(b) / args.steps
+            single = {"ms_per_step": ms1, "value": (float(N) * N) / (ms1 * 1e-3) / 1e9, "unit": UNIT,
+                      "speedup": ms1 / ms_step}
+            e1.close()
+        barrier()
+
+    # ---- CPU baseline: the compiled reference on a bounded slab (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rows = max(16, int(1.5e6 * 10.0 // N))            # ~20 s: two iterations over ~15 Mpix in total
+        dt, npx, kind, rr = time_reference(N, k, min(rows, N), 2)
+        cpu = {"value": npx / dt / 1e9, "unit": UNIT, "cores": 1, "kind": kind, "s_per_iter_sample": dt,
+               "s_per_iter_full_map_extrapolated": dt * (float(N) * N / npx), "host_cpus": os.cpu_count(),
+               "sample": "rows %d..%d of the %dx%d map (%d px) x all %d generators, lloyd(max_iters=0) = 2 iterations"
+                         % (rr[0], rr[1], N, N, npx, k)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": wl["name"], "pixels": N * N, "generators": k, "mode": mode,
+                           "bytes_per_px": BYTES_PER_PX[mode], "parallelism": "rows x%d + allreduce(moments)" % world if world > 1 else "1 GPU",
+                           "l2": "inputs (%.0f MB per GPU) larger than L2 (126 MB); no flush needed" % (
+                               (BYTES_PER_PX[mode] - 4) * (r1 - r0) * N / 1e6),
+                           "converged_during_run": bool(conv)},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roof, "cpu_baseline": cpu}
+        if single is not None:
+            line["single_gpu_same_workload"] = single
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -14,8 +14,9 @@
  * maintainer would add.
  *
  * Conventions
- *   - every function returns 0 (TESS_OK) or a negative TESS_ERR_* code; never throws;
- *     tess_last_error() gives a thread-local message for the last failure.
+ *   - every function (bar tess_version, tess_last_error, tess_launch_count) returns 0 (TESS_OK)
+ *     or a negative TESS_ERR_* code; never throws; tess_last_error() gives a thread-local
+ *     message for the last failure.
  *   - ALL data pointers are DEVICE pointers on the context's device (e.g. torch CUDA tensor
  *     data_ptr()).  Input arrays are BORROWED: they must stay alive and unchanged until they
  *     are replaced by another tess_set_* call or the context is destroyed.
@@ -71,9 +72,12 @@ enum {
                                    /* update set scale_j = sqrt(count_j / (S/N)_j) (Diehl &   */
                                    /* Statler 2006 eq. 4); needs signal/noise mode.  No        */
                                    /* reference counterpart.              */
-    TESS_OPT_UNIFORM_WEIGHT = 2    /* signal/noise mode only. 0 (default): w = fl(fl(S/N)^2)  */
+    TESS_OPT_UNIFORM_WEIGHT = 2,   /* signal/noise mode only. 0 (default): w = fl(fl(S/N)^2)  */
                                    /* (scripts/demo_iso_sn_voronoi.py:26,37). 1: w = 1         */
                                    /* (geometric centroids, WVT).                              */
+    TESS_OPT_KERNEL_TIMING = 3     /* 1: bracket the dominant kernel of tess_lloyd_accumulate  */
+                                   /* (pixel / point assignment + sums) with CUDA events on    */
+                                   /* its stream; read with tess_get_kernel_timing.            */
 };
 
 int tess_version(void);
@@ -155,6 +159,19 @@ int tess_get_scales(tess_ctx* ctx, double* out, void* stream);       /* [k]     
 int tess_get_iter_stats(tess_ctx* ctx, double* delta, long* n_changed, long* n_iters_done,
                         void* stream);
 
+/* Latch and error state: *converged = 1 once the fixed point was reached, *nonfinite = 1 if a
+ * generator became NaN/Inf (see TESS_ERR_NONFINITE).  Synchronises `stream`. */
+int tess_get_status(tess_ctx* ctx, int* converged, int* nonfinite, void* stream);
+
+/*
+ * Measurement aids (bench.py).  tess_get_kernel_timing synchronises the device and returns the
+ * summed device time (ms) and number of launches of the dominant kernel recorded since the last
+ * call (needs TESS_OPT_KERNEL_TIMING; at most 512 launches are kept between calls).
+ * tess_launch_count returns how many kernels this library has launched in this process.
+ */
+int tess_get_kernel_timing(tess_ctx* ctx, double* ms_total, long* launches);
+long tess_launch_count(void);
+
 /*
  * Assignment only -- the segmentation map of VoronoiTessellation.segmap /
  * render_voronoi_field (reference tess/voronoi.py:75-114): labels_out[r*W + c] = nearest
@@ -164,6 +181,15 @@ int tess_assign_grid(tess_ctx* ctx, double x0, double y0, long H, long W, int32_
                      void* stream);
 /* partition_points (reference tess/voronoi.py:154-173): out[i] = nearest generator of xy[i]. */
 int tess_assign_points(tess_ctx* ctx, long m, const double* xy, int32_t* out, void* stream);
+
+/*
+ * Per-bin sums over a label array -- np.bincount(segmap.ravel()) of compute_cell_areas
+ * (reference tess/voronoi.py:150) and np.bincount(idx, weights=mass) of sum_cell_point_mass
+ * (tess/voronoi.py:195): out[j] = sum of weights[i] (or of 1 when weights is NULL) over labels[i]
+ * == j.  Labels outside [0, k) are skipped (flagged / masked pixels).  out is [k].
+ */
+int tess_label_sums(tess_ctx* ctx, long n, const int32_t* labels, const double* weights, long k,
+                    double* out, void* stream);
 
 /*
  * Validation aids: exhaustive O(n*k) assignment on the GPU with the same pinned arithmetic,

@@ -19,6 +19,7 @@ TESS_ERR_NOMEM = -5
 MOM_COUNT, MOM_W, MOM_WX, MOM_WY, MOM_S, MOM_N2 = range(6)
 OPT_WVT_SCALE_UPDATE = 1
 OPT_UNIFORM_WEIGHT = 2
+OPT_KERNEL_TIMING = 3
 
 _vp = ctypes.c_void_p
 _l = ctypes.c_long
@@ -45,8 +46,12 @@ SIGNATURES = {
     "tess_get_generators": (_i, [_vp, _vp, _vp]),
     "tess_get_scales": (_i, [_vp, _vp, _vp]),
     "tess_get_iter_stats": (_i, [_vp, ctypes.POINTER(_d), ctypes.POINTER(_l), ctypes.POINTER(_l), _vp]),
+    "tess_get_status": (_i, [_vp, ctypes.POINTER(_i), ctypes.POINTER(_i), _vp]),
+    "tess_get_kernel_timing": (_i, [_vp, ctypes.POINTER(_d), ctypes.POINTER(_l)]),
+    "tess_launch_count": (_l, []),
     "tess_assign_grid": (_i, [_vp, _d, _d, _l, _l, _vp, _vp]),
     "tess_assign_points": (_i, [_vp, _l, _vp, _vp, _vp]),
+    "tess_label_sums": (_i, [_vp, _l, _vp, _vp, _l, _vp, _vp]),
     "tess_assign_grid_exhaustive": (_i, [_vp, _d, _d, _l, _l, _vp, _vp]),
     "tess_assign_points_exhaustive": (_i, [_vp, _l, _vp, _vp, _vp]),
 }
@@ -115,3 +120,16 @@ class CApi(object):
         delta, nch, nit = _d(0), _l(0), _l(0)
         self.call("tess_get_iter_stats", ctx, ctypes.byref(delta), ctypes.byref(nch), ctypes.byref(nit), stream)
         return delta.value, nch.value, nit.value
+
+    def status(self, ctx, stream):
+        conv, bad = _i(0), _i(0)
+        self.call("tess_get_status", ctx, ctypes.byref(conv), ctypes.byref(bad), stream)
+        return bool(conv.value), bool(bad.value)
+
+    def kernel_timing(self, ctx):
+        ms, n = _d(0), _l(0)
+        self.call("tess_get_kernel_timing", ctx, ctypes.byref(ms), ctypes.byref(n))
+        return ms.value, n.value
+
+    def launch_count(self):
+        return int(self.dll.tess_launch_count())

@@ -84,6 +84,11 @@ struct tess_ctx {
     long mom_cap;
     double* prev_count;
     double* scratch;   // 8 doubles (bounding-box reduction)
+    int timing;        // TESS_OPT_KERNEL_TIMING
+#ifndef TESS_EMU
+    cudaEvent_t ev[2 * 512];
+    int n_ev_alloc, n_ev_used;
+#endif
     TessState* h_st;   // pinned mirror
 };
 
@@ -139,6 +144,9 @@ extern "C" int tess_ctx_destroy(tess_ctx* c) {
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (c->h_st) cudaFreeHost(c->h_st);
+#ifndef TESS_EMU
+    for (int i = 0; i < c->n_ev_alloc; ++i) cudaEventDestroy(c->ev[i]);
+#endif
     delete c;
     return TESS_OK;
 }
@@ -148,6 +156,7 @@ extern "C" int tess_set_option(tess_ctx* c, int option, long value) {
     switch (option) {
         case TESS_OPT_WVT_SCALE_UPDATE: c->wvt_update = value ? 1 : 0; return TESS_OK;
         case TESS_OPT_UNIFORM_WEIGHT: c->uniform_weight = value ? 1 : 0; return TESS_OK;
+        case TESS_OPT_KERNEL_TIMING: c->timing = value ? 1 : 0; return TESS_OK;
         default: return tess_fail(TESS_ERR_ARG, "tess_set_option: unknown option %d", option);
     }
 }
@@ -488,6 +497,43 @@ static int run_points(tess_ctx* c, const Geometry& q, int mode, int honor, long 
     return TESS_OK;
 }
 
+// event bracket around the dominant kernel (TESS_OPT_KERNEL_TIMING)
+static void timing_mark(tess_ctx* c, cudaStream_t s, int end) {
+#ifndef TESS_EMU
+    if (!c->timing) return;
+    if (!end && c->n_ev_used + 2 > 2 * 512) return;
+    if (end && (c->n_ev_used & 1) == 0) return;
+    while (c->n_ev_alloc <= c->n_ev_used) {
+        if (cudaEventCreate(&c->ev[c->n_ev_alloc]) != cudaSuccess) return;
+        ++c->n_ev_alloc;
+    }
+    cudaEventRecord(c->ev[c->n_ev_used++], s);
+#else
+    (void)c; (void)s; (void)end;
+#endif
+}
+
+extern "C" int tess_get_kernel_timing(tess_ctx* c, double* ms_total, long* launches) {
+    TRY(bind(c));
+    double tot = 0.0;
+    long n = 0;
+#ifndef TESS_EMU
+    CU_TRY(cudaDeviceSynchronize());
+    for (int i = 0; i + 1 < c->n_ev_used; i += 2) {
+        float ms = 0.f;
+        CU_TRY(cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]));
+        tot += ms;
+        ++n;
+    }
+    c->n_ev_used = 0;
+#endif
+    if (ms_total) *ms_total = tot;
+    if (launches) *launches = n;
+    return TESS_OK;
+}
+
+extern "C" long tess_launch_count(void) { return g_tess_launches; }
+
 static int check_ready(tess_ctx* c, const char* who) {
     TRY(bind(c));
     if (c->source == SRC_NONE) return tess_fail(TESS_ERR_STATE, "%s: call tess_set_image or tess_set_points first", who);
@@ -507,12 +553,16 @@ extern "C" int tess_lloyd_accumulate(tess_ctx* c, void* stream) {
         Geometry q = window_geometry(c->x0, c->y0, c->H, c->W);
         TRY(build_index(c, q, 1, c->mom, n_mom, s));
         TRY(build_lists(c, q, 1, s));
+        timing_mark(c, s, 0);
         TRY(run_image(c, q, c->img_mode, 1, nullptr, s));
+        timing_mark(c, s, 1);
         n = c->H * c->W;
     } else {
         Geometry q = box_geometry(c->pb, c->k);
         TRY(build_index(c, q, 1, c->mom, n_mom, s));
+        timing_mark(c, s, 0);
         TRY(run_points(c, q, 1, 1, c->n_pts, c->pts_xy, c->pts_w, nullptr, s));
+        timing_mark(c, s, 1);
         n = c->n_pts;
     }
     const int nb = (c->k + 255) / 256;
@@ -655,6 +705,14 @@ extern "C" int tess_get_iter_stats(tess_ctx* c, double* delta, long* n_changed, 
     return TESS_OK;
 }
 
+extern "C" int tess_get_status(tess_ctx* c, int* converged, int* nonfinite, void* stream) {
+    TRY(bind(c));
+    TRY(fetch_state(c, S(stream)));
+    if (converged) *converged = c->h_st->converged;
+    if (nonfinite) *nonfinite = (c->h_st->flags & TESS_FLAG_NONFINITE) ? 1 : 0;
+    return TESS_OK;
+}
+
 // ------------------------------------------------------------------------------------ assignment only
 extern "C" int tess_assign_grid(tess_ctx* c, double x0, double y0, long H, long W, int32_t* labels_out, void* stream) {
     TRY(bind(c));
@@ -678,6 +736,20 @@ extern "C" int tess_assign_points(tess_ctx* c, long m, const double* xy, int32_t
     Geometry q = box_geometry(box, c->k);
     TRY(build_index(c, q, 0, nullptr, 0, s));
     TRY(run_points(c, q, 0, 0, m, xy, nullptr, out, s));
+    return TESS_OK;
+}
+
+extern "C" int tess_label_sums(tess_ctx* c, long n, const int32_t* labels, const double* weights, long k, double* out,
+                               void* stream) {
+    TRY(bind(c));
+    if (n < 0 || k <= 0 || !out || (n > 0 && !labels)) return tess_fail(TESS_ERR_ARG, "tess_label_sums: bad arguments");
+    cudaStream_t s = S(stream);
+    CU_TRY(cudaMemsetAsync(out, 0, sizeof(double) * (size_t)k, s));
+    if (n > 0) {
+        const long threads = (n + TESS_RUN - 1) / TESS_RUN;
+        TESS_LAUNCH((k_label_sums), (int)((threads + 255) / 256), 256, s, labels, weights, n, k, out);
+        CU_TRY(cudaGetLastError());
+    }
     return TESS_OK;
 }
 

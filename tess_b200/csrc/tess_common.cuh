@@ -13,11 +13,13 @@
 #include <stdint.h>
 #include <math.h>
 
+static long g_tess_launches = 0;   // kernels launched by the library (host-side count)
+
 #ifdef TESS_EMU
-#define TESS_LAUNCH(kern, grid, block, stream, ...) emu::launch(kern, dim3(grid), dim3(block), __VA_ARGS__)
+#define TESS_LAUNCH(kern, grid, block, stream, ...) (++g_tess_launches, emu::launch(kern, dim3(grid), dim3(block), __VA_ARGS__))
 #else
 #include <cuda_runtime.h>
-#define TESS_LAUNCH(kern, grid, block, stream, ...) kern<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#define TESS_LAUNCH(kern, grid, block, stream, ...) (++g_tess_launches, kern<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__))
 #endif
 
 #define TESS_TS 64            // super-tile edge, px
@@ -61,6 +63,8 @@ struct TessState {
     unsigned list_cursor;            // bump allocator of the candidate-list arena
     unsigned ticket;                 // "last block done" counters of the fused tail kernels
     unsigned ticket2;
+    int last_parity;                 // label buffer (0/1) written by the most recent accumulate
+    int pad_;
 };
 #define TESS_FLAG_NONFINITE 1
 // iteration kernels are no-ops once the latch closed or an error flag is up (unless forced)

@@ -57,14 +57,16 @@ k_cell_scan(TessState* st, int honor, const int* cell_cnt, int* cell_start, int 
     }
     if (t == nt - 1) cell_start[n_cells] = s_part[t];
     if (t == 0) {
-        st->delta = 0.0;
-        st->n_changed = 0ull;
-        st->count_changed = 0;
-        st->counted = 0;
+        if (honor) {   // part of a Lloyd iteration (not a stand-alone assignment query)
+            st->delta = 0.0;
+            st->n_changed = 0ull;
+            st->count_changed = 0;
+            st->counted = 0;
+            st->min_inv_next = 0x7ff0000000000000ull;   // +inf
+        }
         st->list_cursor = 0u;
         st->tile_counter = 0;
         st->n_brute = 0;
-        st->min_inv_next = 0x7ff0000000000000ull;   // +inf
     }
 }
 

@@ -73,6 +73,7 @@ k_compare_labels(TessState* st, int honor, int32_t* lab0, int32_t* lab1, long n,
         st->counted = need ? 1 : 0;
         mom_tail[TESS_TAIL_CHANGED] = changed ? 1.0 : 0.0;
         mom_tail[TESS_TAIL_SPARE] = 0.0;
+        st->last_parity = (int)(st->iters_done & 1);
         st->ticket = 0u;
     }
 }
@@ -185,8 +186,32 @@ k_export_moments(const double* mom, int M, int k, double* out) {
 // widen / copy labels of the iteration that ran last (buffer parity lives on the device)
 __global__ void __launch_bounds__(256)
 k_export_labels(const TessState* st, const int32_t* lab0, const int32_t* lab1, long n, int32_t* out) {
-    const int32_t* cur = ((st->iters_done - 1) & 1) ? lab1 : lab0;
+    const int32_t* cur = st->last_parity ? lab1 : lab0;
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long stride = (long)gridDim.x * blockDim.x;
     for (; i < n; i += stride) out[i] = cur[i];
+}
+
+// Per-bin sums over a label array (np.bincount of tess/voronoi.py:150,195).  Each thread walks
+// TESS_RUN consecutive elements and flushes one reduction per same-label run: segmentation maps
+// are spatially coherent, so most threads issue a single atomic.
+#define TESS_RUN 16
+__global__ void __launch_bounds__(256)
+k_label_sums(const int32_t* labels, const double* w, long n, long k, double* out) {
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long b = t * TESS_RUN;
+    if (b >= n) return;
+    const long e = (b + TESS_RUN < n) ? b + TESS_RUN : n;
+    int cur = -1;
+    double acc = 0.0;
+    for (long i = b; i < e; ++i) {
+        const int l = labels[i];
+        if (l != cur) {
+            if (cur >= 0 && cur < k) atomicAdd(out + cur, acc);
+            cur = l;
+            acc = 0.0;
+        }
+        acc = __dadd_rn(acc, w ? w[i] : 1.0);
+    }
+    if (cur >= 0 && cur < k) atomicAdd(out + cur, acc);
 }

@@ -1,0 +1,113 @@
+"""
+tess_b200.sharded -- the Lloyd / WVT iteration over pixel rows sharded across GPUs.
+
+One process per GPU (torch.distributed, NCCL over NVLink).  Rank r owns a contiguous block of
+image rows (its slice of the density / signal / noise maps and of the label map); the generator
+table is replicated and every rank rebuilds the same index.  Per iteration exactly one collective
+runs: an all-reduce (sum, fp64) of the packed per-bin moment vector [k*M | changed-flag], which is
+the only data that couples pixels across GPUs.  All ranks then hold bit-identical
+sums, so they take the same node update and the same convergence decision without a broadcast.
+
+The reference has no distributed path; the single-process semantics being reproduced are those of
+tess/lloyd.pyx:47-90.
+"""
+from ._capi import TessNonFinite
+
+
+def shard_rows(H, world, align=64):
+    """Row ranges [(r0, r1), ...] of `world` contiguous shards of an H-row image.  Boundaries fall
+    on multiples of `align` (the kernels' 64-row super-tiles) where H allows it; a rank may get an
+    empty range only if H < world."""
+    blocks = (H + align - 1) // align
+    if blocks >= world:
+        cuts = [min(H, ((blocks * r) // world) * align) for r in range(world + 1)]
+    else:
+        cuts = [(H * r) // world for r in range(world + 1)]
+    cuts[-1] = H
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+class ShardedLloyd(object):
+    """Drives one `Engine` per rank; `dist` is torch.distributed (already initialised)."""
+
+    def __init__(self, engine, group=None):
+        import torch
+        import torch.distributed as dist
+        self.eng = engine
+        self.dist = dist
+        self.torch = torch
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self._view = None
+
+    # ------------------------------------------------------------------ inputs
+    def set_image_rows(self, density=None, signal=None, noise=None, row0=0, x0=0.0, y0=0.0):
+        """This rank's rows of the maps; `row0` is the global index of its first row."""
+        self.eng.set_image(density=density, signal=signal, noise=noise, x0=x0, y0=float(y0) + float(row0))
+        self._view = None
+
+    def set_generators(self, node_xy, scale=None):
+        """Same table on every rank (replicated)."""
+        self.eng.set_generators(node_xy, scale)
+        self._view = None
+
+    # ------------------------------------------------------------------ iteration
+    def _moments(self):
+        if self._view is None:
+            v, _ = self.eng.moments_view()
+            if not isinstance(v, self.torch.Tensor):          # NumPy-memory engine (CPU tests, gloo)
+                v = self.torch.from_numpy(v)
+            self._view = v
+        return self._view
+
+    def step(self, n=1):
+        """n iterations: local accumulate -> all-reduce of the moment vector -> update."""
+        for _ in range(int(n)):
+            self.eng.accumulate()
+            self.dist.all_reduce(self._moments(), op=self.dist.ReduceOp.SUM, group=self.group)
+            self.eng.update()
+
+    def run(self, max_iters, check_every=4):
+        """Reference stop rule (tess/lloyd.pyx:85-90) on the sharded problem.
+        Returns (converged, n_iters); identical on every rank."""
+        budget = max(int(max_iters) + 2, 1)
+        start = self.eng.stats()[2]
+        done, conv = 0, False
+        while not conv and done < budget:
+            chunk = min(int(check_every), budget - done)
+            self.step(chunk)
+            done = self.eng.stats()[2] - start
+            conv, bad = self.eng.status()
+            if bad:
+                if done < budget:
+                    raise TessNonFinite(-4, "a bin with pixels has zero total weight: generator became "
+                                            "NaN/Inf after iteration %d" % done)
+                return False, done
+        return conv, done
+
+    # ------------------------------------------------------------------ results
+    def generators(self):
+        return self.eng.generators()
+
+    def local_labels(self):
+        """Labels of this rank's rows (they never leave the GPU unless asked for)."""
+        return self.eng.labels()
+
+    def moments(self):
+        """Global per-bin moments [k, 6] (identical on all ranks after a step)."""
+        return self.eng.moments()
+
+    def gather_labels(self, dst=0):
+        """Full label map on rank `dst` (None elsewhere); rows are concatenated in rank order."""
+        lab = self.local_labels()
+        if not isinstance(lab, self.torch.Tensor):
+            lab = self.torch.from_numpy(lab)
+        sizes = [None] * self.world
+        self.dist.all_gather_object(sizes, tuple(lab.shape), group=self.group)
+        if self.rank == dst:
+            parts = [self.torch.empty(s, dtype=lab.dtype, device=lab.device) for s in sizes]
+        else:
+            parts = None
+        self.dist.gather(lab.contiguous(), parts, dst=dst, group=self.group)
+        return self.torch.cat(parts, dim=0) if self.rank == dst else None

@@ -29,98 +29,58 @@ def build(force=False):
     return OUT
 
 
-def _p(a):
-    return None if a is None else a.ctypes.data
+import ctypes
+import sys
+
+sys.path.insert(0, ROOT)
+from tess_b200._capi import CApi          # noqa: E402
+from tess_b200.engine import Engine       # noqa: E402
+
+_API = None
 
 
-class EmuEngine(object):
-    """NumPy-memory twin of tess_b200.engine.Engine (same call sequence, same C ABI)."""
+def emu_api():
+    global _API
+    if _API is None:
+        _API = CApi(build())
+    return _API
 
-    def __init__(self):
-        import sys
-        sys.path.insert(0, ROOT)
-        from tess_b200._capi import CApi
-        self.api = CApi(build())
+
+class EmuEngine(Engine):
+    """tess_b200.engine.Engine with NumPy memory and the emulator build of the library: the same
+    host logic and the same C ABI calls as on the GPU, runnable on the GPU-less build box."""
+
+    def __init__(self, device=None):
+        self.api = emu_api()
+        self.device = "emu"
         self.ctx = self.api.ctx_create(0)
-        self.keep = {}
-        self.n = 0
-        self.k = 0
+        self._init_common()
 
-    def close(self):
-        if self.ctx is not None:
-            self.api.call("tess_ctx_destroy", self.ctx)
-            self.ctx = None
+    def _to_dev(self, a, dtype="float64"):
+        return np.ascontiguousarray(a, dtype=dtype)
 
-    def set_option(self, opt, val):
-        self.api.call("tess_set_option", self.ctx, opt, val)
+    def _empty(self, shape, dtype="float64"):
+        return np.empty(shape, dtype=dtype)
 
-    def set_image(self, density=None, signal=None, noise=None, x0=0.0, y0=0.0):
-        arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (density, signal, noise)]
-        ref = next(a for a in arrs if a is not None)
-        H, W = ref.shape
-        self.keep["img"] = arrs
-        self.n = H * W
-        self.shape = (H, W)
-        self.api.call("tess_set_image", self.ctx, H, W, float(x0), float(y0), _p(arrs[0]), _p(arrs[1]), _p(arrs[2]), None)
+    def _ptr(self, t):
+        return None if t is None else t.ctypes.data
 
-    def set_points(self, xy, w):
-        xy = np.ascontiguousarray(xy, dtype=np.float64)
-        w = np.ascontiguousarray(w, dtype=np.float64)
-        self.keep["pts"] = (xy, w)
-        self.n = xy.shape[0]
-        self.shape = (self.n,)
-        self.api.call("tess_set_points", self.ctx, self.n, _p(xy), _p(w), None)
+    def _stream(self):
+        return None
 
-    def set_generators(self, node, scale=None):
-        node = np.ascontiguousarray(node, dtype=np.float64)
-        sc = None if scale is None else np.ascontiguousarray(scale, dtype=np.float64)
-        self.k = node.shape[0]
-        self.api.call("tess_set_generators", self.ctx, self.k, _p(node), _p(sc), None)
+    def _view(self, ptr, n):
+        return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_double)), shape=(n,))
 
-    def step(self, n=1):
-        self.api.call("tess_lloyd_step", self.ctx, n, None)
+    def _to_host(self, t):
+        return t
 
-    def accumulate(self):
-        self.api.call("tess_lloyd_accumulate", self.ctx, None)
+    def _finite_mask(self, t):
+        return np.isfinite(t)
 
-    def update(self):
-        self.api.call("tess_lloyd_update", self.ctx, None)
+    def _masked_fill(self, t, mask, value):
+        t = t.copy()
+        t[mask] = value
+        return t
 
-    def run(self, max_iters):
-        return self.api.lloyd_run(self.ctx, max_iters, None)
-
-    def labels(self):
-        out = np.empty(self.n, dtype=np.int32)
-        self.api.call("tess_get_labels", self.ctx, _p(out), None)
-        return out.reshape(self.shape)
-
-    def moments(self):
-        out = np.empty((self.k, 6), dtype=np.float64)
-        self.api.call("tess_get_moments", self.ctx, _p(out), None)
-        return out
-
-    def generators(self):
-        out = np.empty((self.k, 2), dtype=np.float64)
-        self.api.call("tess_get_generators", self.ctx, _p(out), None)
-        return out
-
-    def scales(self):
-        out = np.empty(self.k, dtype=np.float64)
-        self.api.call("tess_get_scales", self.ctx, _p(out), None)
-        return out
-
-    def stats(self):
-        return self.api.iter_stats(self.ctx, None)
-
-    def assign_grid(self, x0, y0, H, W, exhaustive=False):
-        out = np.empty((H, W), dtype=np.int32)
-        name = "tess_assign_grid_exhaustive" if exhaustive else "tess_assign_grid"
-        self.api.call(name, self.ctx, float(x0), float(y0), H, W, _p(out), None)
-        return out
-
-    def assign_points(self, xy, exhaustive=False):
-        xy = np.ascontiguousarray(xy, dtype=np.float64)
-        out = np.empty(xy.shape[0], dtype=np.int32)
-        name = "tess_assign_points_exhaustive" if exhaustive else "tess_assign_points"
-        self.api.call(name, self.ctx, xy.shape[0], _p(xy), _p(out), None)
-        return out
+    def _amax(self, t):
+        return int(t.max()) if t.size else -1

@@ -1,0 +1,158 @@
+"""
+Kernel LOGIC on the CPU: tess_b200/csrc compiled against the SIMT emulator (tests/emu) and driven
+through the product's own host code (tess_b200.engine / lloyd / voronoi) with NumPy memory.
+This is not a product path (the product has no CPU build); it catches indexing, warp-choreography
+and latch errors on the GPU-less build box.  The same checks run on the real GPU in
+tests/test_gpu_parity.py.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden, gaussian_image, sampled_seeds
+from oracle import oracle as O
+
+sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+from harness import EmuEngine  # noqa: E402
+
+
+@pytest.fixture()
+def eng():
+    e = EmuEngine()
+    yield e
+    e.close()
+
+
+def test_img64_trajectory_matches_reference(eng):
+    g = golden("lloyd_img64.npz")
+    eng.set_image(density=g["density"])
+    eng.set_generators(g["seeds"])
+    T = int(g["n_iters"])
+    for t in range(T):
+        eng.step(1)
+        assert np.array_equal(eng.labels().ravel(), g["labels"][t].astype(np.int32)), t
+        assert np.abs(eng.generators() - g["nodes"][t]).max() < 1e-9, t
+        delta, nch, it = eng.stats()
+        assert it == t + 1
+        assert abs(delta - float(g["deltas_txt"][t])) <= 6e-3 * max(delta, 1e-300) or delta == 0.0
+    assert eng.stats()[0] == 0.0 and eng.status() == (True, False)
+    eng.step(3)                                   # latch closed: further steps are no-ops
+    assert eng.stats()[2] == T
+
+
+def test_stop_rule(eng):
+    g = golden("lloyd_img64.npz")
+    eng.set_image(density=g["density"])
+    for max_iters, want in ((300, (True, int(g["n_iters"]))), (3, (False, 5)), (0, (False, 2)), (-5, (False, 1))):
+        eng.set_generators(g["seeds"])
+        assert eng.run(max_iters) == want
+
+
+def test_moments_and_sn_mode(eng):
+    rng = np.random.default_rng(5)
+    sig = gaussian_image(80) + 1.0
+    noise = np.sqrt(sig + 1.0)
+    sig[3, 7] = np.nan
+    noise[40, 41] = np.inf
+    w = (sig / noise) ** 2
+    seeds = sampled_seeds(np.nan_to_num(w, posinf=0.0), 14, seed=8)
+    eng.set_image(signal=sig, noise=noise)
+    eng.set_generators(seeds)
+    eng.accumulate()
+    lab = eng.labels()
+    assert np.array_equal(lab, O.c_assign_grid(80, 80, seeds))        # masked pixels still get a label
+    good = np.isfinite(w) & np.isfinite(sig) & np.isfinite(noise)
+    x, y = np.meshgrid(np.arange(80.0), np.arange(80.0))
+    xy = np.column_stack((x.ravel(), y.ravel()))
+    idx = np.where(good.ravel(), lab.ravel(), -1).astype(np.int64)
+    ref = O.np_moments(xy, np.nan_to_num(w.ravel(), posinf=0.0), idx, 14, signal=np.nan_to_num(sig.ravel()),
+                       noise=np.nan_to_num(noise.ravel(), posinf=0.0))
+    np.testing.assert_allclose(eng.moments(), ref, rtol=1e-12, atol=0)
+    eng.update()
+    new, _ = O.np_update_nodes(ref, seeds)
+    np.testing.assert_allclose(eng.generators(), new, rtol=0, atol=1e-9)
+
+
+def test_wvt_scaled_assignment(eng):
+    rng = np.random.default_rng(6)
+    node = rng.uniform(0, 100, (60, 2))
+    scale = rng.uniform(0.5, 3.0, 60)
+    eng.set_generators(node, scale)
+    lab = eng.assign_grid(-3.0, 2.0, 70, 90)
+    assert np.array_equal(lab, O.c_assign_grid(70, 90, node, x0=-3.0, y0=2.0, scale=scale))
+    assert np.array_equal(lab, eng.assign_grid(-3.0, 2.0, 70, 90, exhaustive=True))
+    pts = rng.uniform(-20, 120, (700, 2))
+    assert np.array_equal(eng.assign_points(pts), O.c_assign_points(pts, node, scale))
+
+
+def test_ties_go_to_lowest_index(eng):
+    # generators on half-integers: thousands of exact ties on an integer pixel grid
+    gx, gy = np.meshgrid(np.arange(0.5, 40, 4.0), np.arange(0.5, 40, 4.0))
+    node = np.column_stack((gx.ravel(), gy.ravel()))
+    node = node[np.random.default_rng(1).permutation(node.shape[0])]
+    eng.set_generators(node)
+    assert np.array_equal(eng.assign_grid(0, 0, 40, 40), O.c_assign_grid(40, 40, node))
+
+
+def test_far_generators_and_odd_shapes(eng):
+    # all generators in one corner, odd width (scalar path), window offset from the generators
+    rng = np.random.default_rng(9)
+    node = rng.uniform(0, 6, (25, 2))
+    eng.set_generators(node)
+    for (x0, y0, H, W) in ((0, 0, 130, 67), (50.5, -20.25, 65, 129), (-300, 400, 3, 5)):
+        assert np.array_equal(eng.assign_grid(x0, y0, H, W), O.c_assign_grid(H, W, node, x0=x0, y0=y0)), (x0, y0)
+    # a single generator; more generators than the per-tile list can hold (exhaustive-scan fallback)
+    eng.set_generators(node[:1])
+    assert (eng.assign_grid(0, 0, 70, 70) == 0).all()
+    dense = rng.uniform(0, 40, (1300, 2))
+    eng.set_generators(dense)
+    assert np.array_equal(eng.assign_grid(0, 0, 40, 40), O.c_assign_grid(40, 40, dense))
+
+
+def test_voronoi_api_matches_reference_fixture():
+    from tess_b200.voronoi import VoronoiTessellation
+    g = golden("segmap.npz")
+    vt = VoronoiTessellation(g["gens"], engine=EmuEngine())
+    vt.set_pixel_grid(tuple(g["xlim"]), tuple(g["ylim"]))
+    assert np.array_equal(vt.segmap, g["segmap"]) and vt.segmap.dtype == np.int64
+    assert np.array_equal(vt.render_voronoi_field(g["values"]), g["field"])
+    assert np.array_equal(vt.partition_points(g["points"]), g["partition"])
+    np.testing.assert_allclose(vt.sum_cell_point_mass(g["points"], mass=g["mass"]), g["cell_mass"], rtol=1e-13)
+    assert np.array_equal(vt.compute_cell_areas(), np.bincount(g["segmap"].ravel()))
+    flag = np.zeros(g["segmap"].shape); flag[:10] = 1
+    assert np.array_equal(vt.compute_cell_areas(flag)[:5], np.bincount(g["segmap"][10:].ravel(), minlength=40)[:5])
+
+
+def test_from_image_with_nan_matches_reference_fixture():
+    from tess_b200.voronoi import CVTessellation
+    g = golden("from_image_nan.npz")
+    cv = CVTessellation.from_image(g["density"], g["seeds"], engine=EmuEngine())
+    assert np.abs(cv.nodes - g["nodes"]).max() < 1e-6
+    assert np.array_equal(cv.membership, g["membership"])
+    np.testing.assert_allclose(cv.node_weights, g["node_weights"], rtol=1e-12)
+    assert np.array_equal(cv.segmap, g["segmap"])
+    assert (cv.xlim, cv.ylim) == ((0, 96), (0, 96))
+
+
+def test_lloyd_points_small(eng):
+    from tess_b200.lloyd import lloyd
+    rng = np.random.default_rng(12)
+    xy = np.column_stack((rng.normal(250, 100, 1500), rng.normal(250, 50, 1500)))
+    w = rng.uniform(0.1, 1.0, 1500)
+    seeds = xy[rng.choice(1500, 40, replace=False)] + rng.uniform(-0.1, 0.1, (40, 2))
+    n, i, c = lloyd(xy, w, seeds, 6, engine=eng)
+    rn, ri, rc, nit, _, _ = O.c_lloyd(xy, w, seeds, 6)
+    assert c == rc and np.array_equal(i, ri) and i.dtype == np.int64
+    np.testing.assert_allclose(n, rn, rtol=0, atol=1e-9)
+    with pytest.raises(ValueError):
+        lloyd(xy.astype(np.float32), w, seeds, 3, engine=eng)       # reference: Buffer dtype mismatch
+
+
+def test_zero_weight_bin_raises_like_the_reference(eng):
+    from tess_b200.lloyd import lloyd
+    xy = np.array([[0.0, 0.0], [1.0, 0.0], [10.0, 0.0], [11.0, 0.0]])
+    w = np.array([1.0, 1.0, 1.0, -1.0])          # second bin: count 2, sum w == 0 -> NaN node
+    with pytest.raises(ValueError):
+        lloyd(xy, w, np.array([[0.4, 0.1], [10.4, 0.1]]), 10, engine=eng)

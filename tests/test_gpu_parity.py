@@ -1,0 +1,323 @@
+"""
+Parity of the CUDA path (through the C ABI, via tess_b200.engine / lloyd / voronoi) with
+ (i) the golden fixtures generated from the reference itself (tests/golden/make_golden.py),
+ (ii) the CPU oracle on seeded inputs at sizes it finishes in seconds, and
+ (iii) size-independent properties at BASELINE.json's full sizes.
+Bars: labels bit-exact; per-bin moments <= 1e-12 relative; converged nodes <= 1e-6 px.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden, gaussian_image, sampled_seeds
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def eng(engine_cls):
+    e = engine_cls(0)
+    yield e
+    e.close()
+
+
+def h(t):
+    return t.cpu().numpy()
+
+
+# ---------------------------------------------------------------- golden fixtures (reference outputs)
+def test_img64_trajectory_matches_reference(eng):
+    g = golden("lloyd_img64.npz")
+    eng.set_image(density=g["density"])
+    eng.set_generators(g["seeds"])
+    T = int(g["n_iters"])
+    for t in range(T):
+        eng.step(1)
+        assert np.array_equal(h(eng.labels()).ravel(), g["labels"][t].astype(np.int32)), t
+        assert np.abs(h(eng.generators()) - g["nodes"][t]).max() < 1e-9, t
+        delta = eng.stats()[0]
+        assert abs(delta - float(g["deltas_txt"][t])) <= 6e-3 * max(delta, 1e-300) or delta == 0.0
+    assert eng.status() == (True, False)
+    eng.step(3)
+    assert eng.stats()[2] == T
+    for max_iters, want in ((300, (True, T)), (3, (False, 5)), (0, (False, 2))):
+        eng.set_generators(g["seeds"])
+        assert eng.run(max_iters) == want
+
+
+def test_config_c1_demo256(engine_cls):
+    """C1: scripts/demo_iso_sn_voronoi.py inputs, EqualSNAccretor seeds, Lloyd to convergence."""
+    from tess_b200.voronoi import CVTessellation
+    g = golden("lloyd_demo256.npz")
+    dens = gaussian_image(256) ** 2.0
+    cv = CVTessellation.from_image(dens, g["seeds"])
+    assert np.abs(cv.nodes - g["nodes"]).max() < 1e-6
+    assert np.array_equal(cv.membership, g["membership"]) and cv.membership.dtype == np.int64
+    assert np.array_equal(cv.segmap, g["segmap"])
+    assert cv._engine.stats()[2] == int(g["n_iters"])
+
+
+def test_config_c2_shape_points_fixture():
+    from tess_b200.lloyd import lloyd
+    from tess_b200.voronoi import CVTessellation
+    g = golden("lloyd_points.npz")
+    n, i, c = lloyd(g["xy"], g["w"], g["seeds"], int(g["max_iters"]))
+    assert not c and np.array_equal(i, g["membership"]) and i.dtype == np.int64
+    assert np.abs(n - g["nodes"]).max() < 1e-6
+    cv = CVTessellation(g["xy"], g["w"], node_xy=g["seeds"], max_iters=int(g["max_iters"]))
+    np.testing.assert_allclose(cv.node_weights, g["node_weights"], rtol=1e-12)
+    assert np.array_equal(cv.membership, g["membership"])
+
+
+def test_voronoi_api_fixture():
+    from tess_b200.voronoi import VoronoiTessellation
+    g = golden("segmap.npz")
+    vt = VoronoiTessellation(g["gens"])
+    vt.set_pixel_grid(tuple(g["xlim"]), tuple(g["ylim"]))
+    assert np.array_equal(vt.segmap, g["segmap"]) and vt.segmap.dtype == np.int64
+    assert np.array_equal(vt.render_voronoi_field(g["values"]), g["field"])
+    assert np.array_equal(vt.partition_points(g["points"]), g["partition"])
+    np.testing.assert_allclose(vt.sum_cell_point_mass(g["points"], mass=g["mass"]), g["cell_mass"], rtol=1e-13)
+    assert np.array_equal(vt.compute_cell_areas(), np.bincount(g["segmap"].ravel()))
+    dens = vt.cell_point_density(g["points"], mass=g["mass"])
+    np.testing.assert_allclose(dens, g["cell_mass"] / np.bincount(g["segmap"].ravel()), rtol=1e-13)
+
+
+def test_from_image_nan_fixture():
+    from tess_b200.voronoi import CVTessellation
+    g = golden("from_image_nan.npz")
+    cv = CVTessellation.from_image(g["density"], g["seeds"])
+    assert np.abs(cv.nodes - g["nodes"]).max() < 1e-6
+    assert np.array_equal(cv.membership, g["membership"])
+    np.testing.assert_allclose(cv.node_weights, g["node_weights"], rtol=1e-12)
+    assert np.array_equal(cv.segmap, g["segmap"])
+
+
+def test_torch_in_torch_out():
+    import torch
+    from tess_b200.lloyd import lloyd
+    g = golden("lloyd_points.npz")
+    xy = torch.from_numpy(g["xy"]).cuda(); w = torch.from_numpy(g["w"]).cuda(); s = torch.from_numpy(g["seeds"]).cuda()
+    n, i, c = lloyd(xy, w, s, 5)
+    rn, ri, rc, _, _, _ = O.c_lloyd(g["xy"], g["w"], g["seeds"], 5)
+    assert n.is_cuda and i.is_cuda and i.dtype == torch.int64 and c == rc
+    assert np.array_equal(h(i), ri) and np.abs(h(n) - rn).max() < 1e-9
+    assert torch.equal(s, torch.from_numpy(g["seeds"]).cuda())          # inputs are not modified
+    with pytest.raises(ValueError):
+        lloyd(xy.float(), w, s, 3)
+
+
+# ---------------------------------------------------------------- oracle on seeded inputs
+def test_1024_map_teacher_forced_iterations(eng):
+    """1024^2 x 1563 tie-free: labels bit-exact, moments 1e-12, next nodes 1e-9."""
+    N, k = 1024, 1563
+    w = gaussian_image(N) ** 2.0
+    seeds = sampled_seeds(w, k, seed=0)
+    x, y = np.meshgrid(np.arange(N, dtype=float), np.arange(N, dtype=float))
+    xy = np.column_stack((x.ravel(), y.ravel()))
+    eng.set_image(density=w)
+    node = seeds
+    for it in range(3):
+        eng.set_generators(node)          # teacher forcing: the oracle's node table goes in
+        eng.accumulate()
+        lab = h(eng.labels())
+        ref = O.c_assign_grid(N, N, node)
+        assert np.array_equal(lab, ref), it
+        mom = h(eng.moments())
+        rm = O.np_moments(xy, w.ravel(), ref.ravel(), k)
+        np.testing.assert_allclose(mom[:, :4], rm[:, :4], rtol=1e-12, atol=0)
+        eng.update()
+        node, _ = O.np_update_nodes(rm, node)
+        assert np.abs(h(eng.generators()) - node).max() < 1e-9
+
+
+def test_sn_mode_moments_and_mask(eng):
+    sig = gaussian_image(300) + 1.0
+    noise = np.sqrt(sig + 1.0)
+    bad = np.random.default_rng(2).choice(300 * 300, 90, replace=False)
+    sig.ravel()[bad[:45]] = np.nan
+    noise.ravel()[bad[45:]] = np.inf
+    w = (sig / noise) ** 2
+    seeds = sampled_seeds(np.nan_to_num(w, posinf=0.0), 120, seed=8)
+    eng.set_image(signal=sig, noise=noise)
+    eng.set_generators(seeds)
+    eng.accumulate()
+    lab = h(eng.labels())
+    assert np.array_equal(lab, O.c_assign_grid(300, 300, seeds))
+    good = np.isfinite(w) & np.isfinite(sig) & np.isfinite(noise)
+    x, y = np.meshgrid(np.arange(300.0), np.arange(300.0))
+    xy = np.column_stack((x.ravel(), y.ravel()))
+    idx = np.where(good.ravel(), lab.ravel(), -1).astype(np.int64)
+    ref = O.np_moments(xy, np.nan_to_num(w.ravel(), posinf=0.0), idx, 120, signal=np.nan_to_num(sig.ravel()),
+                       noise=np.nan_to_num(noise.ravel(), posinf=0.0))
+    mom = h(eng.moments())
+    np.testing.assert_allclose(mom, ref, rtol=1e-12, atol=0)
+    np.testing.assert_allclose(mom[:, 4] / np.sqrt(mom[:, 5]), O.bin_sn(ref), rtol=1e-12)
+
+
+def test_wvt_scales_ties_far_generators_odd_shapes(eng):
+    rng = np.random.default_rng(6)
+    node = rng.uniform(0, 400, (900, 2))
+    scale = rng.uniform(0.5, 3.0, 900)
+    eng.set_generators(node, scale)
+    lab = h(eng.assign_grid(-3.0, 2.0, 301, 417))
+    assert np.array_equal(lab, O.c_assign_grid(301, 417, node, x0=-3.0, y0=2.0, scale=scale))
+    pts = rng.uniform(-50, 450, (20000, 2))
+    assert np.array_equal(h(eng.assign_points(pts)), O.c_assign_points(pts, node, scale))
+    # exact ties -> lowest index
+    gx, gy = np.meshgrid(np.arange(0.5, 200, 4.0), np.arange(0.5, 200, 4.0))
+    tn = np.column_stack((gx.ravel(), gy.ravel()))
+    tn = tn[np.random.default_rng(1).permutation(tn.shape[0])]
+    eng.set_generators(tn)
+    assert np.array_equal(h(eng.assign_grid(0, 0, 200, 200)), O.c_assign_grid(200, 200, tn))
+    # all generators in one corner; windows away from them; odd widths (scalar load/store path)
+    cn = rng.uniform(0, 6, (25, 2))
+    eng.set_generators(cn)
+    for (x0, y0, H, W) in ((0, 0, 530, 267), (50.5, -20.25, 65, 129), (-3000, 4000, 3, 5)):
+        assert np.array_equal(h(eng.assign_grid(x0, y0, H, W)), O.c_assign_grid(H, W, cn, x0=x0, y0=y0))
+    # more generators than a tile list can hold -> exhaustive-scan fallback inside the kernel
+    dense = rng.uniform(0, 64, (3000, 2))
+    eng.set_generators(dense)
+    assert np.array_equal(h(eng.assign_grid(0, 0, 64, 64)), O.c_assign_grid(64, 64, dense))
+    # every point its own generator (CVTessellation default, voronoi.py:298-299)
+    from tess_b200.lloyd import lloyd
+    pts = rng.uniform(0, 30, (500, 2))
+    n, i, c = lloyd(pts, np.ones(500), pts.copy(), 10)
+    assert c and np.array_equal(i, np.arange(500)) and np.abs(n - pts).max() < 1e-12
+
+
+def test_empty_bins_and_zero_weight_bin(eng):
+    from tess_b200.lloyd import lloyd
+    xy = np.array([[5.0, 5.0], [6.0, 5.0], [5.0, 6.0], [7.0, 7.5]])
+    n, i, c = lloyd(xy, np.ones(4), np.array([[5.2, 5.1], [100.0, 100.0]]), 0)
+    rn, ri, rc, _, _, _ = O.c_lloyd(xy, np.ones(4), np.array([[5.2, 5.1], [100.0, 100.0]]), 0)
+    assert np.array_equal(i, ri) and np.allclose(n, rn, atol=1e-12) and c == rc      # empty -> (0,0)
+    xy = np.array([[0.0, 0.0], [1.0, 0.0], [10.0, 0.0], [11.0, 0.0]])
+    with pytest.raises(ValueError):
+        lloyd(xy, np.array([1.0, 1.0, 1.0, -1.0]), np.array([[0.4, 0.1], [10.4, 0.1]]), 10)
+    with pytest.raises(ValueError):
+        eng.set_generators(np.array([[np.nan, 1.0]]))
+
+
+def test_fake_sharding_equals_single_engine(engine_cls):
+    """Two contexts on one GPU, each with half of the rows; their moment vectors are summed as the
+    all-reduce would (tess_b200/sharded.py) -- labels and nodes must equal the unsharded run."""
+    N, k = 512, 400
+    w = gaussian_image(N) ** 2.0
+    seeds = sampled_seeds(w, k, seed=3)
+    one, a, b = engine_cls(0), engine_cls(0), engine_cls(0)
+    one.set_image(density=w); one.set_generators(seeds)
+    a.set_image(density=w[:256], y0=0.0); a.set_generators(seeds)
+    b.set_image(density=w[256:], y0=256.0); b.set_generators(seeds)
+    for it in range(4):
+        one.step(1)
+        a.accumulate(); b.accumulate()
+        va, _ = a.moments_view(); vb, _ = b.moments_view()
+        tot = va + vb
+        va.copy_(tot); vb.copy_(tot)
+        a.update(); b.update()
+        lab = np.vstack((h(a.labels()), h(b.labels())))
+        assert np.array_equal(lab, h(one.labels())), it
+        np.testing.assert_allclose(h(a.generators()), h(one.generators()), rtol=0, atol=1e-9)
+        assert np.array_equal(h(a.generators()), h(b.generators()))
+    for e in (one, a, b):
+        e.close()
+
+
+# ---------------------------------------------------------------- full-size properties
+def _device_gaussian(N, torch):
+    s = 50.0 * N / 256.0
+    ax = torch.arange(N, dtype=torch.float64, device="cuda")
+    gx = torch.exp(-((ax - N / 2.0) ** 2) / (2.0 * s * s))
+    return (10.0 * gx[:, None] * gx[None, :]) ** 2
+
+
+def _gauss_seeds(N, k, seed):
+    rng = np.random.default_rng(seed)
+    s = 50.0 * N / 256.0 / np.sqrt(2.0)
+    out = np.empty((0, 2))
+    while out.shape[0] < k:
+        c = rng.normal(N / 2.0, s, (2 * k, 2))
+        c = c[(c[:, 0] > 0) & (c[:, 0] < N - 1) & (c[:, 1] > 0) & (c[:, 1] < N - 1)]
+        out = np.vstack((out, c))
+    return out[:k]
+
+
+def test_config_c3_full_size_properties(eng):
+    """8192^2 x 1e5 (headline): conservation, Lloyd-path == segmap-path, tiled == exhaustive on a
+    window, determinism of labels, label-change latch."""
+    import torch
+    N, k = 8192, 100000
+    dens = _device_gaussian(N, torch)
+    seeds = _gauss_seeds(N, k, 0)
+    eng.set_image(density=dens)
+    eng.set_generators(seeds)
+    eng.accumulate()
+    lab = eng.labels()
+    mom = eng.moments()
+    assert float(mom[:, 0].sum().item()) == float(N) * N                       # every pixel counted once
+    tot = dens.sum().item()
+    assert abs(mom[:, 1].sum().item() - tot) <= 1e-11 * tot                    # weight conserved
+    ax = torch.arange(N, dtype=torch.float64, device="cuda")
+    wx = (dens * ax[None, :]).sum().item(); wy = (dens * ax[:, None]).sum().item()
+    assert abs(mom[:, 2].sum().item() - wx) <= 1e-11 * wx and abs(mom[:, 3].sum().item() - wy) <= 1e-11 * wy
+    assert int(lab.min().item()) >= 0 and int(lab.max().item()) < k
+    # per-bin count == bincount of the label map (a checksum of checksums)
+    assert torch.equal(torch.bincount(lab.reshape(-1).long(), minlength=k).double(), mom[:, 0])
+    # the segmap path (tess_assign_grid) and the Lloyd path agree everywhere
+    assert torch.equal(eng.assign_grid(0.0, 0.0, N, N), lab)
+    # tiled == exhaustive O(n k) on a window through the dense centre and on a far corner
+    for (x0, y0, H, W) in ((3584, 3840, 512, 768), (0, 0, 256, 384)):
+        ex = eng.assign_grid(float(x0), float(y0), H, W, exhaustive=True)
+        assert torch.equal(ex, lab[y0:y0 + H, x0:x0 + W])
+    # same generators again: labels identical, and the moment sums agree to 1e-12
+    eng.set_generators(seeds)
+    eng.accumulate()
+    assert torch.equal(eng.labels(), lab)
+    assert torch.allclose(eng.moments(), mom, rtol=1e-12, atol=0)
+    # oracle on a 64-row strip
+    strip = O.c_assign_grid(8, 512, seeds, x0=3840.0, y0=4096.0)
+    assert np.array_equal(h(lab[4096:4104, 3840:4352]), strip)
+    # a few free-running iterations: delta decreases overall, node table stays finite
+    eng.step(3)
+    d, _, it = eng.stats()
+    assert it == 3 and np.isfinite(d) and d > 0
+
+
+def test_config_c2_full_size_points(eng):
+    """1e6 points x 1e4 generators (C2): tiled == exhaustive, oracle on a subset, conservation."""
+    import torch
+    rng = np.random.default_rng(1)
+    n, k = 1000000, 10000
+    xy = np.column_stack((np.clip(rng.normal(250, 100, n), 0, 500), np.clip(rng.normal(250, 50, n), 0, 500)))
+    w = rng.uniform(0.1, 1.0, n)
+    seeds = xy[rng.choice(n, k, replace=False)] + rng.uniform(-1e-3, 1e-3, (k, 2))
+    eng.set_points(xy, w)
+    eng.set_generators(seeds)
+    eng.accumulate()
+    lab = eng.labels()
+    assert torch.equal(lab, eng.assign_points(xy, exhaustive=True))
+    sub = rng.choice(n, 20000, replace=False)
+    assert np.array_equal(h(lab)[sub], O.c_assign_points(xy[sub], seeds))
+    mom = h(eng.moments())
+    assert mom[:, 0].sum() == n and abs(mom[:, 1].sum() - w.sum()) <= 1e-11 * w.sum()
+    rm = O.np_moments(xy, w, h(lab).astype(np.int64), k)
+    np.testing.assert_allclose(mom[:, :4], rm[:, :4], rtol=1e-12, atol=0)
+    conv, nit = eng.run(48)
+    assert nit == 50 or conv
+
+
+def test_config_c5_segmap_large(eng):
+    """Segmentation-map rasterisation at a large size (C5 shape scaled to fit the test budget:
+    16384^2 x 2.5e5 generators): tiled == exhaustive on windows, all labels valid."""
+    import torch
+    N, k = 16384, 250000
+    seeds = _gauss_seeds(N, k, 5)
+    eng.set_generators(seeds)
+    seg = eng.assign_grid(0.0, 0.0, N, N)
+    assert int(seg.min().item()) >= 0 and int(seg.max().item()) < k
+    for (x0, y0, H, W) in ((8000, 8100, 256, 512), (16000, 100, 128, 384)):
+        ex = eng.assign_grid(float(x0), float(y0), H, W, exhaustive=True)
+        assert torch.equal(ex, seg[y0:y0 + H, x0:x0 + W])
+    # idempotence: the same call returns the same map
+    assert torch.equal(eng.assign_grid(0.0, 0.0, N, N), seg)
