@@ -25,10 +25,11 @@ static long g_tess_launches = 0;   // kernels launched by the library (host-side
 #define TESS_TS 64            // super-tile edge, px
 #define TESS_WT_W 32          // warp-tile width, px
 #define TESS_WT_H 8           // warp-tile height, px
-#define TESS_CAP 1024         // candidates of one tile staged in shared memory
-#define TESS_LEAF_CAP 32      // candidates of one 8x8 leaf
+#define TESS_CAP 512           // candidates of one tile staged in shared memory
+#define TESS_LEAF_CAP 16      // candidates of one 8x8 leaf
 #define TESS_MAIN_THREADS 128 // image main kernel: 4 warps
 #define TESS_FULL 0xffffffffu
+#define TESS_NAN (__longlong_as_double(0x7ff8000000000000LL))
 #define TESS_BRUTE (-1)       // list_cnt marker: list did not fit, scan every generator
 
 // relative slack on bound comparisons, 1 + 2^-39
@@ -93,8 +94,10 @@ __host__ __device__ __forceinline__ int tess_cell_coord(double g, double o, doub
 
 #ifndef TESS_EMU
 #define TESS_DEVFN __device__ __forceinline__
+#define TESS_NOINLINE __device__ __noinline__
 #else
 #define TESS_DEVFN inline
+#define TESS_NOINLINE static __attribute__((noinline))
 #endif
 
 TESS_DEVFN double tess_warp_min(double v) {

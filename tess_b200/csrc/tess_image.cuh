@@ -5,20 +5,30 @@
 // CVTessellation.from_image builds (tess/voronoi.py:281-287); in MODE 0 it is the nearest-
 // generator rasterisation behind VoronoiTessellation.segmap (tess/voronoi.py:75-114).
 //
-// One persistent CTA (4 warps) pulls 64x64 super-tiles from a dynamic counter.  Per super-tile
-// the candidate list (k_build_lists) is staged in shared memory; each warp walks four 32x8
-// warp tiles, narrowing the list twice (warp tile, then 8x8 leaf) with the exact
-// mind2 <= min maxd2 test, evaluates the surviving candidates with the pinned fp64 formula,
-// writes int32 labels (one coalesced 128-byte line per row) and folds the pixel's moments into
-// a two-entry most-recently-used cache held in registers.  A cache entry is flushed to the
-// global moment table with fire-and-forget fp64 reductions when a third label shows up in the
-// lane's pixel strip; at the end of every super-tile the lanes of a warp that hold the same bin
-// are merged with shuffles and one reduction per (warp, bin) is issued.
+// One persistent CTA (4 warps) pulls 64x64 super-tiles from a dynamic counter.  Per super-tile the
+// candidate list (k_build_lists, sorted by generator index) is staged in shared memory.  Each warp
+// owns a 32x32 quadrant: it narrows the list once for the quadrant and then, for each of its four
+// 32x8 warp tiles, once more per 8x8 leaf (8 lanes per leaf) with a centre + radius test
+//     keep g  iff  u(c,g) <= min_h u(c,h) + 2 rho / s_min        (u = distance / scale)
+// which can never drop the true nearest generator of any pixel of the leaf.  The survivors are
+// evaluated with the pinned fp64 formula; lists are in ascending generator index, so a strict '<'
+// implements the lowest-index tie rule.  Labels leave as one coalesced 128-byte line per row.
+//
+// Moments ("segmented reduction"): every lane owns a 2-column x 4-row pixel patch per warp tile and
+// keeps ONE running same-label accumulator in registers across the warp tiles of a quadrant
+// (labels are spatially coherent, so most patches extend the current run).  When a run ends, the
+// lanes of the warp that retire the same bin are merged with shuffles (warp-level aggregation) and
+// one lane adds the result to the CTA's shared-memory table of per-candidate accumulators; only at
+// the end of the super-tile does the table go to the global moment vector, one fp64 reduction per
+// (tile, bin, moment).
 //
 // Algorithmic HBM traffic per pixel: MODE 1: 8 B (density) + 4 B (label) = 12 B;
 // MODE 2: 8 + 8 B (signal, noise) + 4 B = 20 B; MODE 0: 4 B.  Pixel coordinates are implicit.
 #pragma once
 #include "tess_common.cuh"
+
+#define TESS_QCAP 256       // quadrant list capacity (else the staged list is used as is)
+#define TESS_ACC_CAP 256    // shared accumulator slots per super-tile (slots beyond go to global)
 
 struct TessImgArgs {
     const double* dens;    // MODE 1: [H][W] weights
@@ -42,367 +52,558 @@ struct TessImgArgs {
     int honor;             // honour the convergence latch (iteration kernels) or not (segmap)
 };
 
-// Two-entry MRU cache of per-bin partial moments, in registers.
+// A run of same-label pixels being summed by one lane (registers).
+// v = sum w, sum w*x, sum w*y [, sum S, sum N^2]
 template <int NV>
-struct TessEntry {
-    int id;      // generator index, -1 = empty
-    int n;       // pixel count
-    double v[NV];  // sum w, sum w*x, sum w*y [, sum S, sum N^2]
+struct TessRun {
+    int slot;   // index into the staged candidate list; -1 = none yet
+    int n;      // pixel count
+    double v[NV];
 };
 
+// Finished runs wait in a small per-warp shared-memory stage (two entries per lane) until the end
+// of the warp tile, where the warp merges equal bins and adds them to the CTA table.
+#define TESS_STAGE_DEPTH 2
 template <int NV>
-TESS_DEVFN void tess_entry_clear(TessEntry<NV>& e) {
-    e.id = -1;
-    e.n = 0;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) e.v[i] = 0.0;
+struct TessStage {
+    int2 key[TESS_STAGE_DEPTH][32];          // (slot, n)
+    double v[TESS_STAGE_DEPTH][NV][32];
+};
+
+// fp64 add to a shared-memory word (no native instruction: compare-and-swap loop on the 32-bit
+// shared address, so that no generic-address dispatch is generated)
+TESS_DEVFN void tess_smem_add(double* p, double v) {
+#ifndef TESS_EMU
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(p);
+    unsigned long long old, assumed;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(old) : "r"(addr));
+    do {
+        assumed = old;
+        const unsigned long long upd = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)assumed), v));
+        asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(addr), "l"(assumed), "l"(upd) : "memory");
+    } while (old != assumed);
+#else
+    atomicAdd(p, v);
+#endif
+}
+TESS_DEVFN void tess_gmem_add(double* p, double v) {
+#ifndef TESS_EMU
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+#else
+    atomicAdd(p, v);
+#endif
 }
 
-// fire-and-forget fp64 reductions into the global table (REDG.E.ADD.F64 on sm_100a)
+// one lane adds a finished run to the CTA table (or, beyond its capacity, to the global vector).
+// Out of line and with scalar arguments so that the callers' accumulators stay in registers.
 template <int NV>
-TESS_DEVFN void tess_entry_flush(const TessEntry<NV>& e, double* mom) {
-    if (e.n > 0) {
-        double* m = mom + (long)e.id * (NV + 1);
-        atomicAdd(m, (double)e.n);
-#pragma unroll
-        for (int i = 0; i < NV; ++i) atomicAdd(m + 1 + i, e.v[i]);
-    }
-}
-
-// End-of-kernel flush: lanes holding the same bin are summed with shuffles first, so a bin that
-// spans many warps receives one reduction per warp instead of one per lane.
-template <int NV>
-TESS_DEVFN void tess_entry_flush_warp(const TessEntry<NV>& e, double* mom, int lane) {
-    int id = (e.n > 0) ? e.id : -1;
-    unsigned todo = __ballot_sync(TESS_FULL, id >= 0);
-    while (todo) {
-        int leader = __ffs((int)todo) - 1;
-        int lid = __shfl_sync(TESS_FULL, id, leader);
-        bool mine = (id == lid);
-        unsigned grp = __ballot_sync(TESS_FULL, mine);
-        double cnt = tess_warp_sum(mine ? (double)e.n : 0.0);
-        double s[NV];
-#pragma unroll
-        for (int i = 0; i < NV; ++i) s[i] = tess_warp_sum(mine ? e.v[i] : 0.0);
-        if (lane == leader) {
-            double* m = mom + (long)lid * (NV + 1);
-            atomicAdd(m, cnt);
-#pragma unroll
-            for (int i = 0; i < NV; ++i) atomicAdd(m + 1 + i, s[i]);
+TESS_NOINLINE void tess_table_add(double* s_acc, const int* s_gid, double* mom, int slot, int n, double v0, double v1,
+                                  double v2, double v3, double v4) {
+    if (slot < TESS_ACC_CAP) {
+        double* t = s_acc + slot * (NV + 1);
+        tess_smem_add(t, (double)n);
+        tess_smem_add(t + 1, v0);
+        tess_smem_add(t + 2, v1);
+        tess_smem_add(t + 3, v2);
+        if (NV > 3) {
+            tess_smem_add(t + 4, v3);
+            tess_smem_add(t + 5, v4);
         }
-        todo &= ~grp;
-    }
-}
-
-// Fold one pixel into the cache.  A is the most recently used entry.
-template <int NV>
-TESS_DEVFN void tess_cache_add(TessEntry<NV>& A, TessEntry<NV>& B, double* mom, int id, const double (&val)[NV]) {
-    if (id != A.id) {
-        if (id == B.id) {
-            TessEntry<NV> t = A;
-            A = B;
-            B = t;
-        } else {
-            tess_entry_flush<NV>(B, mom);
-            B = A;
-            tess_entry_clear<NV>(A);
-            A.id = id;
+    } else {
+        double* t = mom + (long)s_gid[slot] * (NV + 1);
+        tess_gmem_add(t, (double)n);
+        tess_gmem_add(t + 1, v0);
+        tess_gmem_add(t + 2, v1);
+        tess_gmem_add(t + 3, v2);
+        if (NV > 3) {
+            tess_gmem_add(t + 4, v3);
+            tess_gmem_add(t + 5, v4);
         }
     }
-    A.n += 1;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) A.v[i] = __dadd_rn(A.v[i], val[i]);
 }
 
-// bits of a full-warp ballot that belong to leaf `leaf` (lanes 4*leaf..4*leaf+3 and +16),
-// packed in `sub` order (sub = (lane&3) | ((lane>>4)<<2))
-TESS_DEVFN unsigned tess_leaf_bits(unsigned b, int leaf) {
-    return ((b >> (4 * leaf)) & 0xFu) | (((b >> (16 + 4 * leaf)) & 0xFu) << 4);
+// The lane's current run ends: park it in the stage (or, if both of its entries are taken -- three
+// or more bin changes inside one 2x4 patch -- add it to the table directly).  Returns the new entry
+// count.  Out of line: it is reached from eight places of the unrolled pixel loop.
+template <int NV>
+TESS_NOINLINE int tess_run_stash(TessStage<NV>* stg, int nst, double* s_acc, const int* s_gid, double* mom, int lane,
+                                 int slot, int n, double v0, double v1, double v2, double v3, double v4) {
+    if (nst < TESS_STAGE_DEPTH) {
+        stg->key[nst][lane] = make_int2(slot, n);
+        stg->v[nst][0][lane] = v0;
+        stg->v[nst][1][lane] = v1;
+        stg->v[nst][2][lane] = v2;
+        if (NV > 3) {
+            stg->v[nst][NV - 2][lane] = v3;
+            stg->v[nst][NV - 1][lane] = v4;
+        }
+        return nst + 1;
+    }
+    tess_table_add<NV>(s_acc, s_gid, mom, slot, n, v0, v1, v2, v3, v4);
+    return nst;
+}
+
+template <int NV>
+TESS_DEVFN void tess_run_switch(TessRun<NV>& cur, int& nst, TessStage<NV>* stg, double* s_acc, const int* s_gid,
+                                double* mom, int lane, int slot) {
+    if (cur.n > 0)
+        nst = tess_run_stash<NV>(stg, nst, s_acc, s_gid, mom, lane, cur.slot, cur.n, cur.v[0], cur.v[1], cur.v[2],
+                                 NV > 3 ? cur.v[NV - 2] : 0.0, NV > 3 ? cur.v[NV - 1] : 0.0);
+    cur.slot = slot;
+    cur.n = 0;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) cur.v[i] = 0.0;
+}
+
+// Warp-level aggregation of the staged runs: lanes whose entries carry the same bin form a group
+// (match.any); the lowest lane of each group sums the group's entries straight from shared memory
+// and adds the result to the CTA table.  All 32 lanes must call; nst is the lane's entry count.
+template <int NV>
+TESS_NOINLINE void tess_warp_retire(TessStage<NV>* stg, int nst, double* s_acc, const int* s_gid, double* mom, int lane) {
+    __syncwarp();
+    for (int e = 0; e < TESS_STAGE_DEPTH; ++e) {
+        const bool has = nst > e;
+        if (!__any_sync(TESS_FULL, has)) break;
+        const int key = has ? stg->key[e][lane].x : -1 - lane;       // unique negative key: a group of one
+        unsigned grp = __match_any_sync(TESS_FULL, key);
+        if (has && lane == __ffs((int)grp) - 1) {
+            int n = 0;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;
+            while (grp) {
+                const int m = __ffs((int)grp) - 1;
+                grp &= grp - 1;
+                n += stg->key[e][m].y;
+                s0 = __dadd_rn(s0, stg->v[e][0][m]);
+                s1 = __dadd_rn(s1, stg->v[e][1][m]);
+                s2 = __dadd_rn(s2, stg->v[e][2][m]);
+                if (NV > 3) {
+                    s3 = __dadd_rn(s3, stg->v[e][NV - 2][m]);
+                    s4 = __dadd_rn(s4, stg->v[e][NV - 1][m]);
+                }
+            }
+            tess_table_add<NV>(s_acc, s_gid, mom, key, n, s0, s1, s2, s3, s4);
+        }
+    }
+    __syncwarp();
+}
+
+// upper bound of sqrt(x) for x >= 0 from the fp32 unit (exact value is not needed, only >=)
+TESS_DEVFN double tess_sqrt_up(double x) {
+    return (double)sqrtf((float)x) * 1.000001 + 1e-18;
+}
+
+// squared threshold of the centre + radius test: (sqrt(umin) + c)^2 with slack, c = 2 rho / s_min
+TESS_DEVFN double tess_center_thr(double umin, double c) {
+    return (umin + 2.0 * c * tess_sqrt_up(umin) + c * c) * TESS_SLACK;
+}
+
+// Exhaustive fallback for a super-tile whose candidate list did not fit (more than TESS_CAP
+// generators can win inside 64x64 pixels, e.g. "every point is its own generator"): the CTA scans
+// the whole generator table for each pixel and sends the moments straight to the global vector.
+// Correct but slow; kept out of line so that it does not bloat the hot loop.
+template <int MODE, bool HAS_SCALE>
+TESS_NOINLINE void tess_tile_brute(const TessImgArgs& a, int32_t* labels, int tx, int ty, double2* s_g, double* s_inv) {
+    constexpr int NV = (MODE == 2) ? 5 : 3;
+    const int tid = threadIdx.x;
+    const long bx = (long)tx * TESS_TS, by = (long)ty * TESS_TS;
+    for (int half = 0; half < TESS_TS * TESS_TS; half += 8 * TESS_MAIN_THREADS) {
+        // each thread owns 8 pixels of this slice: p = half + j*THREADS + tid
+        double bd[8];
+        int bi[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { bd[j] = INFINITY; bi[j] = 0; }
+        for (int g0 = 0; g0 < a.k; g0 += TESS_CAP) {
+            const int cnt = min(TESS_CAP, a.k - g0);
+            __syncthreads();
+            for (int i = tid; i < cnt; i += TESS_MAIN_THREADS) {
+                s_g[i] = make_double2(a.node[2 * (long)(g0 + i)], a.node[2 * (long)(g0 + i) + 1]);
+                if (HAS_SCALE) s_inv[i] = a.inv_s2[g0 + i];
+            }
+            __syncthreads();
+            for (int i = 0; i < cnt; ++i) {
+                const double2 g = s_g[i];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int p = half + j * TESS_MAIN_THREADS + tid;
+                    const double X = a.x0 + (double)(bx + (p & (TESS_TS - 1))), Y = a.y0 + (double)(by + (p >> 6));
+                    double d = tess_d2_pinned(X, Y, g.x, g.y);
+                    if (HAS_SCALE) d = __dmul_rn(d, s_inv[i]);
+                    if (d < bd[j]) { bd[j] = d; bi[j] = g0 + i; }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int p = half + j * TESS_MAIN_THREADS + tid;
+            const long c = bx + (p & (TESS_TS - 1)), r = by + (p >> 6);
+            if (c >= a.W || r >= a.H) continue;
+            const long idx = r * a.W + c;
+            labels[idx] = bi[j];
+            if (MODE != 0) {
+                const double X = a.x0 + (double)c, Y = a.y0 + (double)r;
+                double val[NV];
+                bool ok;
+                if (MODE == 1) {
+                    const double w = a.dens[idx];
+                    ok = isfinite(w);
+                    val[0] = w; val[1] = __dmul_rn(w, X); val[2] = __dmul_rn(w, Y);
+                } else {
+                    const double S = a.sig[idx], N = a.noise[idx];
+                    double w = 1.0;
+                    if (!a.uniform_weight) { const double q = __ddiv_rn(S, N); w = __dmul_rn(q, q); }
+                    ok = isfinite(w) && isfinite(S) && isfinite(N);
+                    val[0] = w; val[1] = __dmul_rn(w, X); val[2] = __dmul_rn(w, Y);
+                    val[NV - 2] = S; val[NV - 1] = __dmul_rn(N, N);
+                }
+                if (ok) {
+                    double* m = a.mom + (long)bi[j] * (NV + 1);
+                    tess_gmem_add(m, 1.0);
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) tess_gmem_add(m + 1 + i, val[i]);
+                }
+            }
+        }
+    }
+    __syncthreads();
 }
 
 // MODE 0: labels only; 1: density map (4 moments); 2: signal + noise maps (6 moments)
 template <int MODE, bool HAS_SCALE, bool VEC>
-__global__ void __launch_bounds__(TESS_MAIN_THREADS)
+__global__ void __launch_bounds__(TESS_MAIN_THREADS, (MODE == 2) ? 4 : 5)
 k_image_main(TessImgArgs a) {
     constexpr int NV = (MODE == 2) ? 5 : 3;
+    constexpr int NW = TESS_MAIN_THREADS / 32;
     if (TESS_STOPPED(a.st, a.honor)) return;
     int32_t* const labels = a.labels_ext ? a.labels_ext : ((a.st->iters_done & 1) ? a.lab1 : a.lab0);
 
-    __shared__ __align__(16) double2 s_g[TESS_CAP];    // generator (x, y) of each list slot
-    __shared__ int s_gid[TESS_CAP];                    // its global index
-    __shared__ double s_inv[HAS_SCALE ? TESS_CAP : 1]; // 1/scale^2
-    __shared__ unsigned short s_wl[TESS_MAIN_THREADS / 32][TESS_CAP];               // warp-tile lists
-    __shared__ unsigned short s_ll[TESS_MAIN_THREADS / 32][4][TESS_LEAF_CAP];       // leaf lists
-    __shared__ int s_tile;
+    __shared__ __align__(16) double2 s_g[TESS_CAP];     // generator (x, y) of each list slot
+    __shared__ int s_gid[TESS_CAP];                     // its global index
+    __shared__ double s_inv[HAS_SCALE ? TESS_CAP : 1];  // 1/scale^2
+    __shared__ unsigned short s_ql[NW][TESS_QCAP];      // quadrant lists (slots)
+    __shared__ __align__(16) double2 s_lg[NW][4][TESS_LEAF_CAP];   // leaf lists: coordinates ...
+    __shared__ double s_li[HAS_SCALE ? NW : 1][4][HAS_SCALE ? TESS_LEAF_CAP : 1];   // ... 1/scale^2 ...
+    __shared__ unsigned short s_ls[NW][4][TESS_LEAF_CAP];          // ... and slot
+    __shared__ double s_acc[(MODE != 0) ? TESS_ACC_CAP * (NV + 1) : 1];   // per-slot accumulators
+    __shared__ int s_tile[2];
 
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     const int cx = lane & 15, ry = lane >> 4;          // patch: cols 2cx,2cx+1; rows 4ry..4ry+3
     const int leaf = cx >> 2;                          // 8-px-wide leaf of the warp tile
     const int sub = (lane & 3) | (ry << 2);            // rank inside the leaf's 8 lanes
-    unsigned short* wl = s_wl[wib];
-    unsigned short* ll = s_ll[wib][leaf];
+    unsigned short* const ql = s_ql[wib];
     const int n_tiles = a.tiles_x * a.tiles_y;
 
-    TessEntry<NV> A, B;
-    tess_entry_clear<NV>(A);
-    tess_entry_clear<NV>(B);
+    __shared__ TessStage<NV> s_stage[(MODE != 0) ? NW : 1];
+    TessStage<NV>* const stg = &s_stage[(MODE != 0) ? wib : 0];
+    TessRun<NV> cur;                 // the lane's running same-label sum (registers)
+    cur.slot = -1;
+    cur.n = 0;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) cur.v[i] = 0.0;
+    int nst = 0;                     // entries of this lane in the stage
 
-    for (;;) {
-        if (tid == 0) s_tile = atomicAdd(&a.st->tile_counter, 1);
-        __syncthreads();
-        const int tile = s_tile;
-        if (tile >= n_tiles) break;
+    if (tid == 0) s_tile[0] = atomicAdd(&a.st->tile_counter, 1);
+    __syncthreads();
+    int tile = s_tile[0];
+
+    for (int it = 0; tile < n_tiles; ++it) {
+        if (tid == 0) s_tile[(it + 1) & 1] = atomicAdd(&a.st->tile_counter, 1);   // prefetch the next tile
         const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
-        const int cnt_raw = a.list_cnt[tile];
-        const bool brute = (cnt_raw == TESS_BRUTE);
-        const int n_chunks = brute ? (a.k + TESS_CAP - 1) / TESS_CAP : 1;
+        const int cnt = a.list_cnt[tile];
+        if (cnt == TESS_BRUTE) {       // CTA-uniform
+            tess_tile_brute<MODE, HAS_SCALE>(a, labels, tx, ty, s_g, s_inv);
+            tile = s_tile[(it + 1) & 1];
+            continue;
+        }
+        // quadrant of this warp, clipped to the image
+        const long qx0 = (long)tx * TESS_TS + 32 * (wib & 1);
+        const long qy0 = (long)ty * TESS_TS + 32 * (wib >> 1);
+        const bool q_in = (qx0 < a.W) && (qy0 < a.H);
+        const long qx1 = min(qx0 + 31, a.W - 1), qy1 = min(qy0 + 31, a.H - 1);
+        const long px = qx0 + 2 * cx;                    // first column of this lane
+        const double X0 = a.x0 + (double)px, X1 = a.x0 + (double)(px + 1);
 
-        // warp-tile origin inside the super-tile: x half = wib&1, 32-row half = wib>>1, 4 steps down
-        const long wx0 = (long)tx * TESS_TS + 32 * (wib & 1);
-        const long wyb = (long)ty * TESS_TS + 32 * (wib >> 1);
-
-        if (!brute) {
-            const int off = a.list_off[tile];
-            for (int i = tid; i < cnt_raw; i += TESS_MAIN_THREADS) {
-                int gid = a.list_items[off + i];
-                s_gid[i] = gid;
-                s_g[i] = make_double2(a.node[2 * (long)gid], a.node[2 * (long)gid + 1]);
-                if (HAS_SCALE) s_inv[i] = a.inv_s2[gid];
+        {
+            // ---- stage the candidate list
+            {
+                const int off = a.list_off[tile];
+                for (int i = tid; i < cnt; i += TESS_MAIN_THREADS) {
+                    const int gid = a.list_items[off + i];
+                    s_gid[i] = gid;
+                    s_g[i] = make_double2(a.node[2 * (long)gid], a.node[2 * (long)gid + 1]);
+                    if (HAS_SCALE) s_inv[i] = a.inv_s2[gid];
+                }
+            }
+            if (MODE != 0) {
+                const int na = min(cnt, TESS_ACC_CAP) * (NV + 1);
+                for (int i = tid; i < na; i += TESS_MAIN_THREADS) s_acc[i] = 0.0;
             }
             __syncthreads();
-        }
 
-        for (int step = 0; step < 4; ++step) {
-            const long wy0 = wyb + 8 * step;
-            const bool wt_in = (wx0 < a.W) && (wy0 < a.H);   // warp-uniform
-            const long px = wx0 + 2 * cx;                    // first column of this lane
-            const long py = wy0 + 4 * ry;                    // first row of this lane
-            const double X0 = a.x0 + (double)px, X1 = a.x0 + (double)(px + 1);
-
-            // ---- issue the pixel loads early; they are consumed after the candidate evaluation
-            double w_[4][2], s_[4][2], n_[4][2];
-            if (MODE != 0) {
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const bool rin = wt_in && (py + r < a.H);
-                    const long base = (py + r) * a.W + px;
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) { w_[r][c] = 0.0; s_[r][c] = 0.0; n_[r][c] = 0.0; }
-                    if (VEC) {
-                        if (rin && px < a.W) {
-                            if (MODE == 1) {
-                                double2 v = *reinterpret_cast<const double2*>(a.dens + base);
-                                w_[r][0] = v.x; w_[r][1] = v.y;
-                            } else {
-                                double2 v = *reinterpret_cast<const double2*>(a.sig + base);
-                                double2 u = *reinterpret_cast<const double2*>(a.noise + base);
-                                s_[r][0] = v.x; s_[r][1] = v.y; n_[r][0] = u.x; n_[r][1] = u.y;
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 2; ++c)
-                            if (rin && px + c < a.W) {
-                                if (MODE == 1) w_[r][c] = a.dens[base + c];
-                                else { s_[r][c] = a.sig[base + c]; n_[r][c] = a.noise[base + c]; }
-                            }
-                    }
+            // ---- quadrant list: staged list -> slots that can win somewhere in the 32x32 quadrant
+            int c_q = cnt;
+            bool q_ident = true;       // true: the quadrant list is the staged list itself
+            if (q_in && cnt > 1) {
+                const double ccx = a.x0 + 0.5 * (double)(qx0 + qx1), ccy = a.y0 + 0.5 * (double)(qy0 + qy1);
+                const double hx = 0.5 * (double)(qx1 - qx0), hy = 0.5 * (double)(qy1 - qy0);
+                const double rho = sqrt(hx * hx + hy * hy) * 1.0000001;
+                double umin = INFINITY, imax = 1.0;
+                for (int i = lane; i < cnt; i += 32) {
+                    const double2 g = s_g[i];
+                    const double dx = ccx - g.x, dy = ccy - g.y;
+                    double d = dx * dx + dy * dy;
+                    if (HAS_SCALE) { const double iv = s_inv[i]; d *= iv; imax = fmax(imax, iv); }
+                    umin = fmin(umin, d);
                 }
+                umin = tess_warp_min(umin);
+                double c = 2.0 * rho;
+                if (HAS_SCALE) {
+                    imax = -tess_warp_min(-imax);
+                    c *= tess_sqrt_up(imax);
+                }
+                const double thr = tess_center_thr(umin, c);
+                int n = 0;
+                for (int b0 = 0; b0 < cnt; b0 += 32) {
+                    const int i = b0 + lane;
+                    bool keep = false;
+                    if (i < cnt) {
+                        const double2 g = s_g[i];
+                        const double dx = ccx - g.x, dy = ccy - g.y;
+                        double d = dx * dx + dy * dy;
+                        if (HAS_SCALE) d *= s_inv[i];
+                        keep = d <= thr;
+                    }
+                    const unsigned b = __ballot_sync(TESS_FULL, keep);
+                    const int pos = n + __popc(b & tess_lanemask_lt(lane));
+                    if (keep && pos < TESS_QCAP) ql[pos] = (unsigned short)i;
+                    n += __popc(b);
+                }
+                if (n <= TESS_QCAP) { c_q = n; q_ident = false; }
+                __syncwarp();
             }
 
-            // ---- best (distance, index) per pixel
-            double bd[4][2];
-            int bi[4][2];
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-                for (int c = 0; c < 2; ++c) { bd[r][c] = INFINITY; bi[r][c] = 0x7fffffff; }
+            for (int step = 0; step < 4 && q_in; ++step) {
+                const long wy0 = qy0 + 8 * step;
+                if (wy0 >= a.H) break;                         // warp-uniform
+                const long py = wy0 + 4 * ry;                  // first row of this lane
 
-            for (int chunk = 0; chunk < n_chunks; ++chunk) {
-                int cnt = cnt_raw;
-                if (brute) {   // exhaustive fallback: stage generators [chunk*CAP, ...) ; CTA-uniform
-                    __syncthreads();
-                    const int g0 = chunk * TESS_CAP;
-                    cnt = min(TESS_CAP, a.k - g0);
-                    for (int i = tid; i < cnt; i += TESS_MAIN_THREADS) {
-                        s_gid[i] = g0 + i;
-                        s_g[i] = make_double2(a.node[2 * (long)(g0 + i)], a.node[2 * (long)(g0 + i) + 1]);
-                        if (HAS_SCALE) s_inv[i] = a.inv_s2[g0 + i];
-                    }
-                    __syncthreads();
-                }
-
-                // ---- level 1: super-tile list -> warp-tile list (wl, slots into s_g)
-                int c_w;
-                bool wl_identity;   // true: the warp list is the staged list itself (slots 0..cnt-1)
-                if (cnt == 1 || brute || !wt_in) {
-                    c_w = cnt;
-                    wl_identity = true;
-                } else {
-                    TessRect wr;
-                    wr.x0 = a.x0 + (double)wx0;
-                    wr.x1 = a.x0 + (double)min(wx0 + TESS_WT_W - 1, a.W - 1);
-                    wr.y0 = a.y0 + (double)wy0;
-                    wr.y1 = a.y0 + (double)min(wy0 + TESS_WT_H - 1, a.H - 1);
-                    double rmin = INFINITY;
-                    for (int i = lane; i < cnt; i += 32) {
-                        double d = tess_maxd2(wr, s_g[i].x, s_g[i].y);
-                        if (HAS_SCALE) d *= s_inv[i];
-                        rmin = fmin(rmin, d);
-                    }
-                    rmin = tess_warp_min(rmin);
-                    const double thr = rmin * TESS_SLACK;
-                    c_w = 0;
-                    for (int b0 = 0; b0 < cnt; b0 += 32) {
-                        int i = b0 + lane;
-                        bool keep = false;
-                        if (i < cnt) {
-                            double d = tess_mind2(wr, s_g[i].x, s_g[i].y);
-                            if (HAS_SCALE) d *= s_inv[i];
-                            keep = d <= thr;
-                        }
-                        unsigned b = __ballot_sync(TESS_FULL, keep);
-                        if (keep) wl[c_w + __popc(b & tess_lanemask_lt(lane))] = (unsigned short)i;
-                        c_w += __popc(b);
-                    }
-                    wl_identity = false;
-                    __syncwarp();
-                }
-
-                // ---- level 2: warp-tile list -> leaf list (ll), per 8-lane group
-                const unsigned short* lst = wl;
-                int len = c_w;
-                bool identity = wl_identity;
-                if (!wl_identity && c_w > 1) {
-                    TessRect lr;
-                    const long lx0 = wx0 + 8 * leaf;
-                    lr.x0 = a.x0 + (double)lx0;
-                    lr.x1 = a.x0 + (double)min(lx0 + 7, a.W - 1);
-                    lr.y0 = a.y0 + (double)wy0;
-                    lr.y1 = a.y0 + (double)min(wy0 + TESS_WT_H - 1, a.H - 1);
-                    double rmin = INFINITY;
-                    for (int i = sub; i < c_w; i += 8) {
-                        int sl = wl[i];
-                        double d = tess_maxd2(lr, s_g[sl].x, s_g[sl].y);
-                        if (HAS_SCALE) d *= s_inv[sl];
-                        rmin = fmin(rmin, d);
-                    }
-                    rmin = fmin(rmin, __shfl_xor_sync(TESS_FULL, rmin, 1));
-                    rmin = fmin(rmin, __shfl_xor_sync(TESS_FULL, rmin, 2));
-                    rmin = fmin(rmin, __shfl_xor_sync(TESS_FULL, rmin, 16));
-                    const double thr = rmin * TESS_SLACK;
-                    int c_l = 0;
-                    for (int b0 = 0; b0 < c_w; b0 += 8) {
-                        int i = b0 + sub;
-                        bool keep = false;
-                        int sl = 0;
-                        if (i < c_w) {
-                            sl = wl[i];
-                            double d = tess_mind2(lr, s_g[sl].x, s_g[sl].y);
-                            if (HAS_SCALE) d *= s_inv[sl];
-                            keep = d <= thr;
-                        }
-                        unsigned gb = tess_leaf_bits(__ballot_sync(TESS_FULL, keep), leaf);
-                        int pos = c_l + __popc(gb & ((1u << sub) - 1u));
-                        if (keep && pos < TESS_LEAF_CAP) ll[pos] = (unsigned short)sl;
-                        c_l += __popc(gb);
-                    }
-                    __syncwarp();
-                    if (c_l <= TESS_LEAF_CAP) { lst = ll; len = c_l; }
-                }
-
-                // ---- evaluate the surviving candidates with the pinned formula
-                if (wt_in) {
-                    if (len == 1 && !brute) {
-                        const int sl = identity ? 0 : lst[0];
-                        const int gid = s_gid[sl];
+                // ---- issue the pixel loads early; they are consumed after the candidate evaluation
+                double w_[4][2], s_[4][2], n_[4][2];
+                if (MODE != 0) {
 #pragma unroll
-                        for (int r = 0; r < 4; ++r) { bi[r][0] = gid; bi[r][1] = gid; }
-                    } else {
-                        for (int j = 0; j < len; ++j) {
-                            const int sl = identity ? j : lst[j];
-                            const double2 g = s_g[sl];
-                            const int gid = s_gid[sl];
-                            double inv = 1.0;
-                            if (HAS_SCALE) inv = s_inv[sl];
-                            const double dx0 = __dsub_rn(X0, g.x), dx1 = __dsub_rn(X1, g.x);
-                            const double dxx0 = __dmul_rn(dx0, dx0), dxx1 = __dmul_rn(dx1, dx1);
+                    for (int r = 0; r < 4; ++r) {
+                        const bool rin = (py + r < a.H);
+                        const long base = (py + r) * a.W + px;
 #pragma unroll
-                            for (int r = 0; r < 4; ++r) {
-                                const double Y = a.y0 + (double)(py + r);
-                                const double dy = __dsub_rn(Y, g.y);
-                                const double dyy = __dmul_rn(dy, dy);
-                                double d0 = __dadd_rn(dxx0, dyy), d1 = __dadd_rn(dxx1, dyy);
-                                if (HAS_SCALE) { d0 = __dmul_rn(d0, inv); d1 = __dmul_rn(d1, inv); }
-                                if ((d0 < bd[r][0]) | ((d0 == bd[r][0]) & (gid < bi[r][0]))) { bd[r][0] = d0; bi[r][0] = gid; }
-                                if ((d1 < bd[r][1]) | ((d1 == bd[r][1]) & (gid < bi[r][1]))) { bd[r][1] = d1; bi[r][1] = gid; }
+                        for (int c = 0; c < 2; ++c) { w_[r][c] = TESS_NAN; s_[r][c] = TESS_NAN; n_[r][c] = TESS_NAN; }
+                        if (VEC) {
+                            if (rin && px < a.W) {
+                                if (MODE == 1) {
+                                    const double2 v = *reinterpret_cast<const double2*>(a.dens + base);
+                                    w_[r][0] = v.x; w_[r][1] = v.y;
+                                } else {
+                                    const double2 v = *reinterpret_cast<const double2*>(a.sig + base);
+                                    const double2 u = *reinterpret_cast<const double2*>(a.noise + base);
+                                    s_[r][0] = v.x; s_[r][1] = v.y; n_[r][0] = u.x; n_[r][1] = u.y;
+                                }
                             }
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 2; ++c)
+                                if (rin && px + c < a.W) {
+                                    if (MODE == 1) w_[r][c] = a.dens[base + c];
+                                    else { s_[r][c] = a.sig[base + c]; n_[r][c] = a.noise[base + c]; }
+                                }
                         }
                     }
                 }
-            }   // chunks
 
-            // ---- labels out: 16 lanes x 8 B = one 128-byte line per row
-            if (wt_in) {
+                // ---- best (distance, slot) per pixel
+                double bd[4][2];
+                int bs[4][2];
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) { bd[r][c] = INFINITY; bs[r][c] = 0; }
+
+                if (c_q == 1) {
+                    const int sl = q_ident ? 0 : (int)ql[0];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) { bs[r][0] = sl; bs[r][1] = sl; }
+                } else {
+                    // ---- leaf list: quadrant list -> candidates of this lane's 8x8 leaf
+                    const long lx0 = qx0 + 8 * leaf;
+                    const long lx1 = min(lx0 + 7, a.W - 1), ly1 = min(wy0 + 7, a.H - 1);
+                    const bool l_in = lx0 < a.W;
+                    const double lcx = a.x0 + 0.5 * (double)(lx0 + lx1), lcy = a.y0 + 0.5 * (double)(wy0 + ly1);
+                    const double hx = 0.5 * (double)(lx1 - lx0), hy = 0.5 * (double)(ly1 - wy0);
+                    double2* const lg = s_lg[wib][leaf];
+                    unsigned short* const ls = s_ls[wib][leaf];
+                    double* const li = HAS_SCALE ? s_li[wib][leaf] : nullptr;
+                    int len = 0;
+                    bool use_leaf = false;
+                    if (c_q > 2) {
+                        const double rho = sqrt(hx * hx + hy * hy) * 1.0000001;
+                        double umin = INFINITY, imax = 1.0;
+                        for (int i = sub; i < c_q; i += 8) {
+                            const int sl = q_ident ? i : (int)ql[i];
+                            const double2 g = s_g[sl];
+                            const double dx = lcx - g.x, dy = lcy - g.y;
+                            double d = dx * dx + dy * dy;
+                            if (HAS_SCALE) { const double iv = s_inv[sl]; d *= iv; imax = fmax(imax, iv); }
+                            umin = fmin(umin, d);
+                        }
+                        umin = fmin(umin, __shfl_xor_sync(TESS_FULL, umin, 1));
+                        umin = fmin(umin, __shfl_xor_sync(TESS_FULL, umin, 2));
+                        umin = fmin(umin, __shfl_xor_sync(TESS_FULL, umin, 16));
+                        double c = 2.0 * rho;
+                        if (HAS_SCALE) {
+                            imax = fmax(imax, __shfl_xor_sync(TESS_FULL, imax, 1));
+                            imax = fmax(imax, __shfl_xor_sync(TESS_FULL, imax, 2));
+                            imax = fmax(imax, __shfl_xor_sync(TESS_FULL, imax, 16));
+                            c *= tess_sqrt_up(imax);
+                        }
+                        const double thr = tess_center_thr(umin, c);
+                        for (int b0 = 0; b0 < c_q; b0 += 8) {
+                            const int i = b0 + sub;
+                            bool keep = false;
+                            int sl = 0;
+                            double2 g = make_double2(0.0, 0.0);
+                            double iv = 1.0;
+                            if (i < c_q) {
+                                sl = q_ident ? i : (int)ql[i];
+                                g = s_g[sl];
+                                const double dx = lcx - g.x, dy = lcy - g.y;
+                                double d = dx * dx + dy * dy;
+                                if (HAS_SCALE) { iv = s_inv[sl]; d *= iv; }
+                                keep = l_in && (d <= thr);
+                            }
+                            const unsigned bb = __ballot_sync(TESS_FULL, keep);
+                            const unsigned gb = ((bb >> (4 * leaf)) & 0xFu) | (((bb >> (16 + 4 * leaf)) & 0xFu) << 4);
+                            const int pos = len + __popc(gb & ((1u << sub) - 1u));
+                            if (keep && pos < TESS_LEAF_CAP) {
+                                lg[pos] = g;
+                                ls[pos] = (unsigned short)sl;
+                                if (HAS_SCALE) li[pos] = iv;
+                            }
+                            len += __popc(gb);
+                        }
+                        use_leaf = (len <= TESS_LEAF_CAP);
+                        __syncwarp();
+                    }
+                    // ---- evaluate the surviving candidates with the pinned formula (ascending index:
+                    //      strict '<' keeps the lowest index on exact ties)
+                    const int n_ev = use_leaf ? len : c_q;
+                    for (int j = 0; j < n_ev; ++j) {
+                        double2 g;
+                        int sl;
+                        double inv = 1.0;
+                        if (use_leaf) {
+                            g = lg[j];
+                            sl = ls[j];
+                            if (HAS_SCALE) inv = li[j];
+                        } else {
+                            sl = q_ident ? j : (int)ql[j];
+                            g = s_g[sl];
+                            if (HAS_SCALE) inv = s_inv[sl];
+                        }
+                        const double dx0 = __dsub_rn(X0, g.x), dx1 = __dsub_rn(X1, g.x);
+                        const double dxx0 = __dmul_rn(dx0, dx0), dxx1 = __dmul_rn(dx1, dx1);
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            const double Y = a.y0 + (double)(py + r);
+                            const double dy = __dsub_rn(Y, g.y);
+                            const double dyy = __dmul_rn(dy, dy);
+                            double d0 = __dadd_rn(dxx0, dyy), d1 = __dadd_rn(dxx1, dyy);
+                            if (HAS_SCALE) { d0 = __dmul_rn(d0, inv); d1 = __dmul_rn(d1, inv); }
+                            if (d0 < bd[r][0]) { bd[r][0] = d0; bs[r][0] = sl; }
+                            if (d1 < bd[r][1]) { bd[r][1] = d1; bs[r][1] = sl; }
+                        }
+                    }
+                }
+
+                // ---- labels out: 16 lanes x 8 B = one 128-byte line per row
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                     if (py + r < a.H) {
                         const long base = (py + r) * a.W + px;
+                        const int g0 = s_gid[bs[r][0]], g1 = s_gid[bs[r][1]];
                         if (VEC) {
-                            if (px < a.W) *reinterpret_cast<int2*>(labels + base) = make_int2(bi[r][0], bi[r][1]);
+                            if (px < a.W) *reinterpret_cast<int2*>(labels + base) = make_int2(g0, g1);
                         } else {
-                            if (px < a.W) labels[base] = bi[r][0];
-                            if (px + 1 < a.W) labels[base + 1] = bi[r][1];
+                            if (px < a.W) labels[base] = g0;
+                            if (px + 1 < a.W) labels[base + 1] = g1;
                         }
                     }
                 }
-            }
 
-            // ---- moments: fold the lane's 8 pixels into its register cache
-            if (MODE != 0 && wt_in) {
+                // ---- moments: fold the lane's 8 pixels into its running same-label sum, column by
+                // column (the column order alternates with the step so that runs continue across warp
+                // tiles).  Pixels outside the image were loaded as NaN and drop out with the masked ones.
+                if (MODE != 0) {
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const double Y = a.y0 + (double)(py + r);
+                    for (int cc = 0; cc < 2; ++cc) {
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const bool in = (py + r < a.H) && (px + c < a.W);
-                        const double X = c ? X1 : X0;
-                        double val[NV];
-                        bool ok;
-                        if (MODE == 1) {
-                            const double w = w_[r][c];
-                            ok = in && isfinite(w);
-                            val[0] = w;
-                            val[1] = __dmul_rn(w, X);
-                            val[2] = __dmul_rn(w, Y);
-                        } else {
-                            const double S = s_[r][c], N = n_[r][c];
-                            double w = 1.0;
-                            if (!a.uniform_weight) {
-                                const double q = __ddiv_rn(S, N);
-                                w = __dmul_rn(q, q);
+                        for (int r = 0; r < 4; ++r) {
+                            const bool flip = (step & 1);
+                            const int sl = (cc == 0) ? (flip ? bs[r][1] : bs[r][0]) : (flip ? bs[r][0] : bs[r][1]);
+                            const double X = (cc == 0) ? (flip ? X1 : X0) : (flip ? X0 : X1);
+                            const double Y = a.y0 + (double)(py + r);
+                            double w, S = 0.0, N = 0.0;
+                            bool ok;
+                            if (MODE == 1) {
+                                w = (cc == 0) ? (flip ? w_[r][1] : w_[r][0]) : (flip ? w_[r][0] : w_[r][1]);
+                                ok = fabs(w) <= 1.7976931348623157e308;
+                            } else {
+                                S = (cc == 0) ? (flip ? s_[r][1] : s_[r][0]) : (flip ? s_[r][0] : s_[r][1]);
+                                N = (cc == 0) ? (flip ? n_[r][1] : n_[r][0]) : (flip ? n_[r][0] : n_[r][1]);
+                                w = 1.0;
+                                if (!a.uniform_weight) { const double q = __ddiv_rn(S, N); w = __dmul_rn(q, q); }
+                                ok = (fabs(w) <= 1.7976931348623157e308) && (fabs(S) <= 1.7976931348623157e308) &&
+                                     (fabs(N) <= 1.7976931348623157e308);
                             }
-                            ok = in && isfinite(w) && isfinite(S) && isfinite(N);
-                            val[0] = w;
-                            val[1] = __dmul_rn(w, X);
-                            val[2] = __dmul_rn(w, Y);
-                            val[3] = S;
-                            val[4] = __dmul_rn(N, N);
+                            if (ok) {
+                                if (sl != cur.slot) tess_run_switch<NV>(cur, nst, stg, s_acc, s_gid, a.mom, lane, sl);
+                                cur.n += 1;
+                                cur.v[0] = __dadd_rn(cur.v[0], w);
+                                cur.v[1] = __dadd_rn(cur.v[1], __dmul_rn(w, X));
+                                cur.v[2] = __dadd_rn(cur.v[2], __dmul_rn(w, Y));
+                                if (MODE == 2) {
+                                    cur.v[NV - 2] = __dadd_rn(cur.v[NV - 2], S);
+                                    cur.v[NV - 1] = __dadd_rn(cur.v[NV - 1], __dmul_rn(N, N));
+                                }
+                            }
                         }
-                        if (ok) tess_cache_add<NV>(A, B, a.mom, bi[r][c], val);
+                    }
+                    // ---- runs that ended in this warp tile: merge across the warp, add to the table
+                    if (__any_sync(TESS_FULL, nst > 0)) {
+                        tess_warp_retire<NV>(stg, nst, s_acc, s_gid, a.mom, lane);
+                        nst = 0;
+                    }
+                }
+            }   // steps
+
+            // ---- end of super-tile: retire the live runs, then table -> global moment vector
+            if (MODE != 0) {
+                tess_run_switch<NV>(cur, nst, stg, s_acc, s_gid, a.mom, lane, -1);
+                tess_warp_retire<NV>(stg, nst, s_acc, s_gid, a.mom, lane);
+                nst = 0;
+            }
+            __syncthreads();
+            if (MODE != 0) {
+                const int na = min(cnt, TESS_ACC_CAP);
+                for (int sl = tid; sl < na; sl += TESS_MAIN_THREADS) {
+                    const double* t = s_acc + sl * (NV + 1);
+                    if (t[0] != 0.0) {
+                        double* m = a.mom + (long)s_gid[sl] * (NV + 1);
+#pragma unroll
+                        for (int i = 0; i <= NV; ++i) tess_gmem_add(m + i, t[i]);
                     }
                 }
             }
-        }   // steps
-
-        // ---- end of super-tile: lanes holding the same bin are merged with shuffles, one
-        // reduction per (warp, bin) goes to the global table
-        if (MODE != 0) {
-            tess_entry_flush_warp<NV>(A, a.mom, lane);
-            tess_entry_flush_warp<NV>(B, a.mom, lane);
-            tess_entry_clear<NV>(A);
-            tess_entry_clear<NV>(B);
+            __syncthreads();   // the table and the staged list are rewritten by the next tile
         }
+        tile = s_tile[(it + 1) & 1];
     }       // tiles
 }
 

@@ -226,6 +226,28 @@ k_build_lists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cell
             }
         }
         __syncwarp();
+        // ---- sort by generator index (bitonic, in shared memory): every list derived from this one
+        // is an order-preserving compaction, so the evaluators implement "lowest index wins a tie"
+        // with a strict '<'
+        if (cnt > 1 && cnt <= TESS_CAP) {
+            int n2 = 2;
+            while (n2 < cnt) n2 <<= 1;
+            for (int i = cnt + lane; i < n2; i += 32) stage[i] = 0x7fffffff;
+            __syncwarp();
+            for (int k2 = 2; k2 <= n2; k2 <<= 1) {
+                for (int j = k2 >> 1; j > 0; j >>= 1) {
+                    for (int i = lane; i < n2; i += 32) {
+                        const int ixj = i ^ j;
+                        if (ixj > i) {
+                            const int va = stage[i], vb = stage[ixj];
+                            const bool up = ((i & k2) == 0);
+                            if ((va > vb) == up) { stage[i] = vb; stage[ixj] = va; }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
         // ---- publish
         unsigned off = 0;
         int ok = 1;
