@@ -43,19 +43,28 @@ def up_to_date():
     return os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in sources())
 
 
-def build(force=False, verbose=False):
-    """Build tess_b200/libtess_b200.so if it is older than its sources.  Returns its path."""
-    if not force and up_to_date():
+def build(force=False, verbose=False, out=None, defines=()):
+    """Build tess_b200/libtess_b200.so if it is older than its sources.  Returns its path.
+    `out` / `defines` build a tuning variant elsewhere (load it with TESS_B200_LIB=<path>)."""
+    if out is None and not defines and not force and up_to_date():
         return LIB
-    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB, os.path.join(CSRC, "tess_b200.cu")]
+    out = out or LIB
+    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-D" + d for d in defines] + \
+          ["-o", out, os.path.join(CSRC, "tess_b200.cu")]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), r.stdout))
     if verbose:
         print(r.stdout)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("-v", action="store_true")
+    ap.add_argument("--out", default=None)
+    ap.add_argument("-D", action="append", default=[])
+    a = ap.parse_args()
+    print(build(force=a.force, verbose=a.v, out=a.out, defines=a.D))

@@ -26,8 +26,11 @@ static long g_tess_launches = 0;   // kernels launched by the library (host-side
 #define TESS_WT_W 32          // warp-tile width, px
 #define TESS_WT_H 8           // warp-tile height, px
 #define TESS_CAP 512           // candidates of one tile staged in shared memory
-#define TESS_LEAF_CAP 16      // candidates of one 8x8 leaf
+#define TESS_LEAF_CAP 24      // candidates of one 8x8 leaf
 #define TESS_MAIN_THREADS 128 // image main kernel: 4 warps
+#ifndef TESS_MAIN_MINBLOCKS
+#define TESS_MAIN_MINBLOCKS 4 // CTAs per SM the main kernel is compiled for (<= 128 registers)
+#endif
 #define TESS_FULL 0xffffffffu
 #define TESS_NAN (__longlong_as_double(0x7ff8000000000000LL))
 #define TESS_BRUTE (-1)       // list_cnt marker: list did not fit, scan every generator

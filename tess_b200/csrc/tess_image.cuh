@@ -28,7 +28,8 @@
 #include "tess_common.cuh"
 
 #define TESS_QCAP 256       // quadrant list capacity (else the staged list is used as is)
-#define TESS_ACC_CAP 256    // shared accumulator slots per super-tile (slots beyond go to global)
+// shared accumulator slots per super-tile (runs of slots beyond it go straight to the global vector)
+#define TESS_ACC_CAP(NV) ((NV) > 3 ? 160 : 256)
 
 struct TessImgArgs {
     const double* dens;    // MODE 1: [H][W] weights
@@ -99,7 +100,7 @@ TESS_DEVFN void tess_gmem_add(double* p, double v) {
 template <int NV>
 TESS_NOINLINE void tess_table_add(double* s_acc, const int* s_gid, double* mom, int slot, int n, double v0, double v1,
                                   double v2, double v3, double v4) {
-    if (slot < TESS_ACC_CAP) {
+    if (slot < TESS_ACC_CAP(NV)) {
         double* t = s_acc + slot * (NV + 1);
         tess_smem_add(t, (double)n);
         tess_smem_add(t + 1, v0);
@@ -267,9 +268,97 @@ TESS_NOINLINE void tess_tile_brute(const TessImgArgs& a, int32_t* labels, int tx
     __syncthreads();
 }
 
+// ---- lane groups of the list filters: 32 lanes (quadrant), 16 lanes (16x16 block: the lanes of
+// eight adjacent pixel-column pairs, both row halves) or 8 lanes (8x8 leaf)
+template <int GROUP>
+TESS_DEVFN int tess_group_rank(int lane) {
+    if (GROUP == 32) return lane;
+    if (GROUP == 16) return (lane & 7) | ((lane >> 4) << 3);
+    return (lane & 3) | ((lane >> 4) << 2);
+}
+template <int GROUP>
+TESS_DEVFN unsigned tess_group_bits(unsigned bb, int lane) {
+    if (GROUP == 32) return bb;
+    if (GROUP == 16) {
+        const int h = (lane >> 3) & 1;
+        return ((bb >> (8 * h)) & 0xFFu) | (((bb >> (16 + 8 * h)) & 0xFFu) << 8);
+    }
+    const int l = (lane >> 2) & 3;
+    return ((bb >> (4 * l)) & 0xFu) | (((bb >> (16 + 4 * l)) & 0xFu) << 4);
+}
+template <int GROUP>
+TESS_DEVFN double tess_group_min(double v) {
+    v = fmin(v, __shfl_xor_sync(TESS_FULL, v, 1));
+    v = fmin(v, __shfl_xor_sync(TESS_FULL, v, 2));
+    if (GROUP >= 16) v = fmin(v, __shfl_xor_sync(TESS_FULL, v, 4));
+    if (GROUP == 32) v = fmin(v, __shfl_xor_sync(TESS_FULL, v, 8));
+    v = fmin(v, __shfl_xor_sync(TESS_FULL, v, 16));
+    return v;
+}
+
+// Centre + radius filter of a slot list (`pl`, or the identity 0..plen-1 when pident) for the
+// rectangle with centre (ccx, ccy) and half-diagonal rho, done by a group of GROUP lanes:
+//   keep g  iff  u(c,g) <= min_h u(c,h) + 2 rho / s_min      (u = distance / scale)
+// Order preserving.  If LEAF, the survivors' coordinates go to (lg, ls, li), else their slots to `out`.
+// Returns the number of survivors (which may exceed `cap`: the caller then keeps using the parent).
+// plen may differ between groups of a warp; plen_max is its maximum over the warp.
+template <int GROUP, bool HAS_SCALE, bool LEAF>
+TESS_DEVFN int tess_filter(const double2* s_g, const double* s_inv, const unsigned short* pl, bool pident, int plen,
+                           int plen_max, double ccx, double ccy, double rho, bool active, int lane, unsigned short* out, double2* lg,
+                           double* li, int cap) {
+    const int rank = tess_group_rank<GROUP>(lane);
+    double umin = INFINITY, imax = 1.0;
+    for (int i = rank; i < plen; i += GROUP) {
+        const int sl = pident ? i : (int)pl[i];
+        const double2 g = s_g[sl];
+        const double dx = ccx - g.x, dy = ccy - g.y;
+        double d = dx * dx + dy * dy;
+        if (HAS_SCALE) { const double iv = s_inv[sl]; d *= iv; imax = fmax(imax, iv); }
+        umin = fmin(umin, d);
+    }
+    umin = tess_group_min<GROUP>(umin);
+    double c = 2.0 * rho;
+    if (HAS_SCALE) {
+        imax = -tess_group_min<GROUP>(-imax);
+        c *= tess_sqrt_up(imax);
+    }
+    const double thr = tess_center_thr(umin, c);
+    int n = 0;
+    for (int b0 = 0; b0 < plen_max; b0 += GROUP) {     // plen_max: warp-uniform bound (ballots inside)
+        const int i = b0 + rank;
+        bool keep = false;
+        int sl = 0;
+        double2 g = make_double2(0.0, 0.0);
+        double iv = 1.0;
+        if (i < plen) {
+            sl = pident ? i : (int)pl[i];
+            g = s_g[sl];
+            const double dx = ccx - g.x, dy = ccy - g.y;
+            double d = dx * dx + dy * dy;
+            if (HAS_SCALE) { iv = s_inv[sl]; d *= iv; }
+            keep = active && (d <= thr);
+        }
+        const unsigned gb = tess_group_bits<GROUP>(__ballot_sync(TESS_FULL, keep), lane);
+        const int pos = n + __popc(gb & ((1u << rank) - 1u));
+        if (keep && pos < cap) {
+            out[pos] = (unsigned short)sl;
+            if (LEAF) {
+                lg[pos] = g;
+                if (HAS_SCALE) li[pos] = iv;
+            }
+        }
+        n += __popc(gb);
+    }
+    __syncwarp();
+    return n;
+}
+
+#define TESS_BCAP 64        // 16x16 block list capacity
+#define TESS_BLOCK_MIN 20   // quadrant lists longer than this get the intermediate 16x16 level
+
 // MODE 0: labels only; 1: density map (4 moments); 2: signal + noise maps (6 moments)
 template <int MODE, bool HAS_SCALE, bool VEC>
-__global__ void __launch_bounds__(TESS_MAIN_THREADS, (MODE == 2) ? 4 : 5)
+__global__ void __launch_bounds__(TESS_MAIN_THREADS, TESS_MAIN_MINBLOCKS)
 k_image_main(TessImgArgs a) {
     constexpr int NV = (MODE == 2) ? 5 : 3;
     constexpr int NW = TESS_MAIN_THREADS / 32;
@@ -280,21 +369,22 @@ k_image_main(TessImgArgs a) {
     __shared__ int s_gid[TESS_CAP];                     // its global index
     __shared__ double s_inv[HAS_SCALE ? TESS_CAP : 1];  // 1/scale^2
     __shared__ unsigned short s_ql[NW][TESS_QCAP];      // quadrant lists (slots)
+    __shared__ unsigned short s_bl[NW][2][TESS_BCAP];   // 16x16 block lists (slots)
     __shared__ __align__(16) double2 s_lg[NW][4][TESS_LEAF_CAP];   // leaf lists: coordinates ...
     __shared__ double s_li[HAS_SCALE ? NW : 1][4][HAS_SCALE ? TESS_LEAF_CAP : 1];   // ... 1/scale^2 ...
     __shared__ unsigned short s_ls[NW][4][TESS_LEAF_CAP];          // ... and slot
-    __shared__ double s_acc[(MODE != 0) ? TESS_ACC_CAP * (NV + 1) : 1];   // per-slot accumulators
+    __shared__ double s_acc[(MODE != 0) ? TESS_ACC_CAP(NV) * (NV + 1) : 1];   // per-slot accumulators
+    __shared__ TessStage<NV> s_stage[(MODE != 0) ? NW : 1];
     __shared__ int s_tile[2];
 
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     const int cx = lane & 15, ry = lane >> 4;          // patch: cols 2cx,2cx+1; rows 4ry..4ry+3
     const int leaf = cx >> 2;                          // 8-px-wide leaf of the warp tile
-    const int sub = (lane & 3) | (ry << 2);            // rank inside the leaf's 8 lanes
+    const int blk = cx >> 3;                           // 16-px-wide block
     unsigned short* const ql = s_ql[wib];
     const int n_tiles = a.tiles_x * a.tiles_y;
-
-    __shared__ TessStage<NV> s_stage[(MODE != 0) ? NW : 1];
     TessStage<NV>* const stg = &s_stage[(MODE != 0) ? wib : 0];
+
     TessRun<NV> cur;                 // the lane's running same-label sum (registers)
     cur.slot = -1;
     cur.n = 0;
@@ -323,286 +413,243 @@ k_image_main(TessImgArgs a) {
         const long px = qx0 + 2 * cx;                    // first column of this lane
         const double X0 = a.x0 + (double)px, X1 = a.x0 + (double)(px + 1);
 
+        // ---- stage the candidate list, clear the accumulator table
         {
-            // ---- stage the candidate list
-            {
-                const int off = a.list_off[tile];
-                for (int i = tid; i < cnt; i += TESS_MAIN_THREADS) {
-                    const int gid = a.list_items[off + i];
-                    s_gid[i] = gid;
-                    s_g[i] = make_double2(a.node[2 * (long)gid], a.node[2 * (long)gid + 1]);
-                    if (HAS_SCALE) s_inv[i] = a.inv_s2[gid];
-                }
+            const int off = a.list_off[tile];
+            for (int i = tid; i < cnt; i += TESS_MAIN_THREADS) {
+                const int gid = a.list_items[off + i];
+                s_gid[i] = gid;
+                s_g[i] = make_double2(a.node[2 * (long)gid], a.node[2 * (long)gid + 1]);
+                if (HAS_SCALE) s_inv[i] = a.inv_s2[gid];
             }
             if (MODE != 0) {
-                const int na = min(cnt, TESS_ACC_CAP) * (NV + 1);
+                const int na = min(cnt, TESS_ACC_CAP(NV)) * (NV + 1);
                 for (int i = tid; i < na; i += TESS_MAIN_THREADS) s_acc[i] = 0.0;
             }
-            __syncthreads();
+        }
+        __syncthreads();
 
-            // ---- quadrant list: staged list -> slots that can win somewhere in the 32x32 quadrant
-            int c_q = cnt;
-            bool q_ident = true;       // true: the quadrant list is the staged list itself
-            if (q_in && cnt > 1) {
-                const double ccx = a.x0 + 0.5 * (double)(qx0 + qx1), ccy = a.y0 + 0.5 * (double)(qy0 + qy1);
-                const double hx = 0.5 * (double)(qx1 - qx0), hy = 0.5 * (double)(qy1 - qy0);
-                const double rho = sqrt(hx * hx + hy * hy) * 1.0000001;
-                double umin = INFINITY, imax = 1.0;
-                for (int i = lane; i < cnt; i += 32) {
-                    const double2 g = s_g[i];
-                    const double dx = ccx - g.x, dy = ccy - g.y;
-                    double d = dx * dx + dy * dy;
-                    if (HAS_SCALE) { const double iv = s_inv[i]; d *= iv; imax = fmax(imax, iv); }
-                    umin = fmin(umin, d);
-                }
-                umin = tess_warp_min(umin);
-                double c = 2.0 * rho;
-                if (HAS_SCALE) {
-                    imax = -tess_warp_min(-imax);
-                    c *= tess_sqrt_up(imax);
-                }
-                const double thr = tess_center_thr(umin, c);
-                int n = 0;
-                for (int b0 = 0; b0 < cnt; b0 += 32) {
-                    const int i = b0 + lane;
-                    bool keep = false;
-                    if (i < cnt) {
-                        const double2 g = s_g[i];
-                        const double dx = ccx - g.x, dy = ccy - g.y;
-                        double d = dx * dx + dy * dy;
-                        if (HAS_SCALE) d *= s_inv[i];
-                        keep = d <= thr;
+        // ---- quadrant list: staged list -> slots that can win somewhere in the 32x32 quadrant
+        int c_q = cnt;
+        bool q_ident = true;       // true: the quadrant list is the staged list itself
+        if (q_in && cnt > 1) {
+            const double hx = 0.5 * (double)(qx1 - qx0), hy = 0.5 * (double)(qy1 - qy0);
+            const int n = tess_filter<32, HAS_SCALE, false>(s_g, s_inv, nullptr, true, cnt, cnt, a.x0 + 0.5 * (double)(qx0 + qx1),
+                                                            a.y0 + 0.5 * (double)(qy0 + qy1),
+                                                            sqrt(hx * hx + hy * hy) * 1.0000001, true, lane, ql, nullptr,
+                                                            nullptr, TESS_QCAP);
+            if (n <= TESS_QCAP) { c_q = n; q_ident = false; }
+        }
+
+        const unsigned short* pl = ql;     // parent list of the leaf filter
+        bool p_ident = q_ident;
+        int p_len = c_q;
+
+        for (int step = 0; step < 4 && q_in; ++step) {
+            const long wy0 = qy0 + 8 * step;
+            if (wy0 >= a.H) break;                         // warp-uniform
+            const long py = wy0 + 4 * ry;                  // first row of this lane
+
+            // ---- issue the pixel loads early; they are consumed after the candidate evaluation.
+            //      Pixels outside the image read as NaN and drop out with the masked ones.
+            double w_[4][2], n_[4][2];                     // MODE 1: weight; MODE 2: signal, noise
+            if (MODE != 0) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const bool rin = (py + r < a.H);
+                    const long base = (py + r) * a.W + px;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) { w_[r][c] = TESS_NAN; n_[r][c] = TESS_NAN; }
+                    const double* src = (MODE == 1) ? a.dens : a.sig;
+                    if (VEC) {
+                        if (rin && px < a.W) {
+                            const double2 v = *reinterpret_cast<const double2*>(src + base);
+                            w_[r][0] = v.x; w_[r][1] = v.y;
+                            if (MODE == 2) {
+                                const double2 u = *reinterpret_cast<const double2*>(a.noise + base);
+                                n_[r][0] = u.x; n_[r][1] = u.y;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 2; ++c)
+                            if (rin && px + c < a.W) {
+                                w_[r][c] = src[base + c];
+                                if (MODE == 2) n_[r][c] = a.noise[base + c];
+                            }
                     }
-                    const unsigned b = __ballot_sync(TESS_FULL, keep);
-                    const int pos = n + __popc(b & tess_lanemask_lt(lane));
-                    if (keep && pos < TESS_QCAP) ql[pos] = (unsigned short)i;
-                    n += __popc(b);
                 }
-                if (n <= TESS_QCAP) { c_q = n; q_ident = false; }
-                __syncwarp();
             }
 
-            for (int step = 0; step < 4 && q_in; ++step) {
-                const long wy0 = qy0 + 8 * step;
-                if (wy0 >= a.H) break;                         // warp-uniform
-                const long py = wy0 + 4 * ry;                  // first row of this lane
+            // ---- 16x16 block lists (every other step), only where the quadrant list is long
+            if ((step & 1) == 0) {
+                pl = ql; p_ident = q_ident; p_len = c_q;
+                if (c_q > TESS_BLOCK_MIN) {
+                    const long bx0 = qx0 + 16 * blk, bx1 = min(bx0 + 15, a.W - 1), by1 = min(wy0 + 15, a.H - 1);
+                    const double hx = 0.5 * (double)(bx1 - bx0), hy = 0.5 * (double)(by1 - wy0);
+                    const int n = tess_filter<16, HAS_SCALE, false>(s_g, s_inv, ql, q_ident, c_q, c_q, a.x0 + 0.5 * (double)(bx0 + bx1),
+                                                                    a.y0 + 0.5 * (double)(wy0 + by1),
+                                                                    sqrt(hx * hx + hy * hy) * 1.0000001, bx0 < a.W, lane,
+                                                                    s_bl[wib][blk], nullptr, nullptr, TESS_BCAP);
+                    // both blocks must fit for the (warp-uniform) parent switch
+                    if (__all_sync(TESS_FULL, n <= TESS_BCAP)) { pl = s_bl[wib][blk]; p_ident = false; p_len = n; }
+                }
+            }
 
-                // ---- issue the pixel loads early; they are consumed after the candidate evaluation
-                double w_[4][2], s_[4][2], n_[4][2];
-                if (MODE != 0) {
+            // ---- best (distance, slot) per pixel
+            double bd[4][2];
+            int bs[4][2];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) { bd[r][c] = INFINITY; bs[r][c] = 0; }
+
+            if (c_q == 1) {
+                const int sl = q_ident ? 0 : (int)ql[0];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) { bs[r][0] = sl; bs[r][1] = sl; }
+            } else {
+                // ---- leaf list: parent list -> candidates of this lane's 8x8 leaf
+                double2* const lg = s_lg[wib][leaf];
+                unsigned short* const ls = s_ls[wib][leaf];
+                double* const li = HAS_SCALE ? s_li[wib][leaf] : nullptr;
+                int len = 0;
+                bool use_leaf = false;
+                const int p_max = __reduce_max_sync(TESS_FULL, p_len);    // the two blocks' lists differ in length
+                if (p_max > 2) {
+                    const long lx0 = qx0 + 8 * leaf;
+                    const long lx1 = min(lx0 + 7, a.W - 1), ly1 = min(wy0 + 7, a.H - 1);
+                    const double hx = 0.5 * (double)(lx1 - lx0), hy = 0.5 * (double)(ly1 - wy0);
+                    len = tess_filter<8, HAS_SCALE, true>(s_g, s_inv, pl, p_ident, p_len, p_max, a.x0 + 0.5 * (double)(lx0 + lx1),
+                                                          a.y0 + 0.5 * (double)(wy0 + ly1),
+                                                          sqrt(hx * hx + hy * hy) * 1.0000001, lx0 < a.W, lane, ls, lg, li,
+                                                          TESS_LEAF_CAP);
+                    use_leaf = (len <= TESS_LEAF_CAP);
+                }
+                // ---- evaluate the surviving candidates with the pinned formula (ascending index:
+                //      strict '<' keeps the lowest index on exact ties)
+                const int n_ev = use_leaf ? len : p_len;
+                for (int j = 0; j < n_ev; ++j) {
+                    double2 g;
+                    int sl;
+                    double inv = 1.0;
+                    if (use_leaf) {
+                        g = lg[j];
+                        sl = ls[j];
+                        if (HAS_SCALE) inv = li[j];
+                    } else {
+                        sl = p_ident ? j : (int)pl[j];
+                        g = s_g[sl];
+                        if (HAS_SCALE) inv = s_inv[sl];
+                    }
+                    const double dx0 = __dsub_rn(X0, g.x), dx1 = __dsub_rn(X1, g.x);
+                    const double dxx0 = __dmul_rn(dx0, dx0), dxx1 = __dmul_rn(dx1, dx1);
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
-                        const bool rin = (py + r < a.H);
-                        const long base = (py + r) * a.W + px;
-#pragma unroll
-                        for (int c = 0; c < 2; ++c) { w_[r][c] = TESS_NAN; s_[r][c] = TESS_NAN; n_[r][c] = TESS_NAN; }
-                        if (VEC) {
-                            if (rin && px < a.W) {
-                                if (MODE == 1) {
-                                    const double2 v = *reinterpret_cast<const double2*>(a.dens + base);
-                                    w_[r][0] = v.x; w_[r][1] = v.y;
-                                } else {
-                                    const double2 v = *reinterpret_cast<const double2*>(a.sig + base);
-                                    const double2 u = *reinterpret_cast<const double2*>(a.noise + base);
-                                    s_[r][0] = v.x; s_[r][1] = v.y; n_[r][0] = u.x; n_[r][1] = u.y;
-                                }
-                            }
-                        } else {
-#pragma unroll
-                            for (int c = 0; c < 2; ++c)
-                                if (rin && px + c < a.W) {
-                                    if (MODE == 1) w_[r][c] = a.dens[base + c];
-                                    else { s_[r][c] = a.sig[base + c]; n_[r][c] = a.noise[base + c]; }
-                                }
-                        }
+                        const double Y = a.y0 + (double)(py + r);
+                        const double dy = __dsub_rn(Y, g.y);
+                        const double dyy = __dmul_rn(dy, dy);
+                        double d0 = __dadd_rn(dxx0, dyy), d1 = __dadd_rn(dxx1, dyy);
+                        if (HAS_SCALE) { d0 = __dmul_rn(d0, inv); d1 = __dmul_rn(d1, inv); }
+                        if (d0 < bd[r][0]) { bd[r][0] = d0; bs[r][0] = sl; }
+                        if (d1 < bd[r][1]) { bd[r][1] = d1; bs[r][1] = sl; }
                     }
                 }
+            }
 
-                // ---- best (distance, slot) per pixel
-                double bd[4][2];
-                int bs[4][2];
+            // ---- labels out: 16 lanes x 8 B = one 128-byte line per row
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (py + r < a.H) {
+                    const long base = (py + r) * a.W + px;
+                    const int g0 = s_gid[bs[r][0]], g1 = s_gid[bs[r][1]];
+                    if (VEC) {
+                        if (px < a.W) *reinterpret_cast<int2*>(labels + base) = make_int2(g0, g1);
+                    } else {
+                        if (px < a.W) labels[base] = g0;
+                        if (px + 1 < a.W) labels[base + 1] = g1;
+                    }
+                }
+            }
+
+            // ---- moments
+            if (MODE != 0) {
+                // weights; masked pixels (non-finite weight, signal or noise; outside the image) are
+                // marked consumed (slot -2) so that the passes below skip them
+                double wv[4][2];
 #pragma unroll
                 for (int r = 0; r < 4; ++r)
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) { bd[r][c] = INFINITY; bs[r][c] = 0; }
-
-                if (c_q == 1) {
-                    const int sl = q_ident ? 0 : (int)ql[0];
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) { bs[r][0] = sl; bs[r][1] = sl; }
-                } else {
-                    // ---- leaf list: quadrant list -> candidates of this lane's 8x8 leaf
-                    const long lx0 = qx0 + 8 * leaf;
-                    const long lx1 = min(lx0 + 7, a.W - 1), ly1 = min(wy0 + 7, a.H - 1);
-                    const bool l_in = lx0 < a.W;
-                    const double lcx = a.x0 + 0.5 * (double)(lx0 + lx1), lcy = a.y0 + 0.5 * (double)(wy0 + ly1);
-                    const double hx = 0.5 * (double)(lx1 - lx0), hy = 0.5 * (double)(ly1 - wy0);
-                    double2* const lg = s_lg[wib][leaf];
-                    unsigned short* const ls = s_ls[wib][leaf];
-                    double* const li = HAS_SCALE ? s_li[wib][leaf] : nullptr;
-                    int len = 0;
-                    bool use_leaf = false;
-                    if (c_q > 2) {
-                        const double rho = sqrt(hx * hx + hy * hy) * 1.0000001;
-                        double umin = INFINITY, imax = 1.0;
-                        for (int i = sub; i < c_q; i += 8) {
-                            const int sl = q_ident ? i : (int)ql[i];
-                            const double2 g = s_g[sl];
-                            const double dx = lcx - g.x, dy = lcy - g.y;
-                            double d = dx * dx + dy * dy;
-                            if (HAS_SCALE) { const double iv = s_inv[sl]; d *= iv; imax = fmax(imax, iv); }
-                            umin = fmin(umin, d);
-                        }
-                        umin = fmin(umin, __shfl_xor_sync(TESS_FULL, umin, 1));
-                        umin = fmin(umin, __shfl_xor_sync(TESS_FULL, umin, 2));
-                        umin = fmin(umin, __shfl_xor_sync(TESS_FULL, umin, 16));
-                        double c = 2.0 * rho;
-                        if (HAS_SCALE) {
-                            imax = fmax(imax, __shfl_xor_sync(TESS_FULL, imax, 1));
-                            imax = fmax(imax, __shfl_xor_sync(TESS_FULL, imax, 2));
-                            imax = fmax(imax, __shfl_xor_sync(TESS_FULL, imax, 16));
-                            c *= tess_sqrt_up(imax);
-                        }
-                        const double thr = tess_center_thr(umin, c);
-                        for (int b0 = 0; b0 < c_q; b0 += 8) {
-                            const int i = b0 + sub;
-                            bool keep = false;
-                            int sl = 0;
-                            double2 g = make_double2(0.0, 0.0);
-                            double iv = 1.0;
-                            if (i < c_q) {
-                                sl = q_ident ? i : (int)ql[i];
-                                g = s_g[sl];
-                                const double dx = lcx - g.x, dy = lcy - g.y;
-                                double d = dx * dx + dy * dy;
-                                if (HAS_SCALE) { iv = s_inv[sl]; d *= iv; }
-                                keep = l_in && (d <= thr);
-                            }
-                            const unsigned bb = __ballot_sync(TESS_FULL, keep);
-                            const unsigned gb = ((bb >> (4 * leaf)) & 0xFu) | (((bb >> (16 + 4 * leaf)) & 0xFu) << 4);
-                            const int pos = len + __popc(gb & ((1u << sub) - 1u));
-                            if (keep && pos < TESS_LEAF_CAP) {
-                                lg[pos] = g;
-                                ls[pos] = (unsigned short)sl;
-                                if (HAS_SCALE) li[pos] = iv;
-                            }
-                            len += __popc(gb);
-                        }
-                        use_leaf = (len <= TESS_LEAF_CAP);
-                        __syncwarp();
-                    }
-                    // ---- evaluate the surviving candidates with the pinned formula (ascending index:
-                    //      strict '<' keeps the lowest index on exact ties)
-                    const int n_ev = use_leaf ? len : c_q;
-                    for (int j = 0; j < n_ev; ++j) {
-                        double2 g;
-                        int sl;
-                        double inv = 1.0;
-                        if (use_leaf) {
-                            g = lg[j];
-                            sl = ls[j];
-                            if (HAS_SCALE) inv = li[j];
+                    for (int c = 0; c < 2; ++c) {
+                        double w = w_[r][c];
+                        bool ok;
+                        if (MODE == 2) {
+                            const double S = w_[r][c], N = n_[r][c];
+                            w = 1.0;
+                            if (!a.uniform_weight) { const double q = __ddiv_rn(S, N); w = __dmul_rn(q, q); }
+                            ok = (fabs(w) <= 1.7976931348623157e308) && (fabs(S) <= 1.7976931348623157e308) &&
+                                 (fabs(N) <= 1.7976931348623157e308);
                         } else {
-                            sl = q_ident ? j : (int)ql[j];
-                            g = s_g[sl];
-                            if (HAS_SCALE) inv = s_inv[sl];
+                            ok = fabs(w) <= 1.7976931348623157e308;
                         }
-                        const double dx0 = __dsub_rn(X0, g.x), dx1 = __dsub_rn(X1, g.x);
-                        const double dxx0 = __dmul_rn(dx0, dx0), dxx1 = __dmul_rn(dx1, dx1);
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) {
-                            const double Y = a.y0 + (double)(py + r);
-                            const double dy = __dsub_rn(Y, g.y);
-                            const double dyy = __dmul_rn(dy, dy);
-                            double d0 = __dadd_rn(dxx0, dyy), d1 = __dadd_rn(dxx1, dyy);
-                            if (HAS_SCALE) { d0 = __dmul_rn(d0, inv); d1 = __dmul_rn(d1, inv); }
-                            if (d0 < bd[r][0]) { bd[r][0] = d0; bs[r][0] = sl; }
-                            if (d1 < bd[r][1]) { bd[r][1] = d1; bs[r][1] = sl; }
-                        }
+                        wv[r][c] = w;
+                        if (!ok) bs[r][c] = -2;
                     }
-                }
-
-                // ---- labels out: 16 lanes x 8 B = one 128-byte line per row
+                // Each pass folds every not yet consumed pixel of the current run's bin into the
+                // lane's registers; lanes with pixels left then park the run in the stage (ONE code
+                // location for the whole warp) and start the run of one of the remaining bins.
+                for (;;) {
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    if (py + r < a.H) {
-                        const long base = (py + r) * a.W + px;
-                        const int g0 = s_gid[bs[r][0]], g1 = s_gid[bs[r][1]];
-                        if (VEC) {
-                            if (px < a.W) *reinterpret_cast<int2*>(labels + base) = make_int2(g0, g1);
-                        } else {
-                            if (px < a.W) labels[base] = g0;
-                            if (px + 1 < a.W) labels[base + 1] = g1;
-                        }
-                    }
-                }
-
-                // ---- moments: fold the lane's 8 pixels into its running same-label sum, column by
-                // column (the column order alternates with the step so that runs continue across warp
-                // tiles).  Pixels outside the image were loaded as NaN and drop out with the masked ones.
-                if (MODE != 0) {
+                    for (int r = 0; r < 4; ++r) {
+                        const double Y = a.y0 + (double)(py + r);
 #pragma unroll
-                    for (int cc = 0; cc < 2; ++cc) {
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) {
-                            const bool flip = (step & 1);
-                            const int sl = (cc == 0) ? (flip ? bs[r][1] : bs[r][0]) : (flip ? bs[r][0] : bs[r][1]);
-                            const double X = (cc == 0) ? (flip ? X1 : X0) : (flip ? X0 : X1);
-                            const double Y = a.y0 + (double)(py + r);
-                            double w, S = 0.0, N = 0.0;
-                            bool ok;
-                            if (MODE == 1) {
-                                w = (cc == 0) ? (flip ? w_[r][1] : w_[r][0]) : (flip ? w_[r][0] : w_[r][1]);
-                                ok = fabs(w) <= 1.7976931348623157e308;
-                            } else {
-                                S = (cc == 0) ? (flip ? s_[r][1] : s_[r][0]) : (flip ? s_[r][0] : s_[r][1]);
-                                N = (cc == 0) ? (flip ? n_[r][1] : n_[r][0]) : (flip ? n_[r][0] : n_[r][1]);
-                                w = 1.0;
-                                if (!a.uniform_weight) { const double q = __ddiv_rn(S, N); w = __dmul_rn(q, q); }
-                                ok = (fabs(w) <= 1.7976931348623157e308) && (fabs(S) <= 1.7976931348623157e308) &&
-                                     (fabs(N) <= 1.7976931348623157e308);
-                            }
-                            if (ok) {
-                                if (sl != cur.slot) tess_run_switch<NV>(cur, nst, stg, s_acc, s_gid, a.mom, lane, sl);
+                        for (int c = 0; c < 2; ++c) {
+                            if (bs[r][c] == cur.slot) {
+                                const double w = wv[r][c];
                                 cur.n += 1;
                                 cur.v[0] = __dadd_rn(cur.v[0], w);
-                                cur.v[1] = __dadd_rn(cur.v[1], __dmul_rn(w, X));
+                                cur.v[1] = __dadd_rn(cur.v[1], __dmul_rn(w, c ? X1 : X0));
                                 cur.v[2] = __dadd_rn(cur.v[2], __dmul_rn(w, Y));
                                 if (MODE == 2) {
-                                    cur.v[NV - 2] = __dadd_rn(cur.v[NV - 2], S);
-                                    cur.v[NV - 1] = __dadd_rn(cur.v[NV - 1], __dmul_rn(N, N));
+                                    cur.v[NV - 2] = __dadd_rn(cur.v[NV - 2], w_[r][c]);
+                                    cur.v[NV - 1] = __dadd_rn(cur.v[NV - 1], __dmul_rn(n_[r][c], n_[r][c]));
                                 }
+                                bs[r][c] = -2;
                             }
                         }
                     }
-                    // ---- runs that ended in this warp tile: merge across the warp, add to the table
-                    if (__any_sync(TESS_FULL, nst > 0)) {
-                        tess_warp_retire<NV>(stg, nst, s_acc, s_gid, a.mom, lane);
-                        nst = 0;
-                    }
+                    int rest = max(max(max(bs[0][0], bs[0][1]), max(bs[1][0], bs[1][1])),
+                                   max(max(bs[2][0], bs[2][1]), max(bs[3][0], bs[3][1])));
+                    if (!__any_sync(TESS_FULL, rest >= 0)) break;
+                    if (rest >= 0) tess_run_switch<NV>(cur, nst, stg, s_acc, s_gid, a.mom, lane, rest);
                 }
-            }   // steps
+                // ---- runs that ended in this warp tile: merge across the warp, add to the table
+                if (__any_sync(TESS_FULL, nst > 0)) {
+                    tess_warp_retire<NV>(stg, nst, s_acc, s_gid, a.mom, lane);
+                    nst = 0;
+                }
+            }
+        }   // steps
 
-            // ---- end of super-tile: retire the live runs, then table -> global moment vector
-            if (MODE != 0) {
-                tess_run_switch<NV>(cur, nst, stg, s_acc, s_gid, a.mom, lane, -1);
-                tess_warp_retire<NV>(stg, nst, s_acc, s_gid, a.mom, lane);
-                nst = 0;
-            }
-            __syncthreads();
-            if (MODE != 0) {
-                const int na = min(cnt, TESS_ACC_CAP);
-                for (int sl = tid; sl < na; sl += TESS_MAIN_THREADS) {
-                    const double* t = s_acc + sl * (NV + 1);
-                    if (t[0] != 0.0) {
-                        double* m = a.mom + (long)s_gid[sl] * (NV + 1);
+        // ---- end of super-tile: retire the live runs, then table -> global moment vector
+        if (MODE != 0) {
+            tess_run_switch<NV>(cur, nst, stg, s_acc, s_gid, a.mom, lane, -1);
+            tess_warp_retire<NV>(stg, nst, s_acc, s_gid, a.mom, lane);
+            nst = 0;
+        }
+        __syncthreads();
+        if (MODE != 0) {
+            const int na = min(cnt, TESS_ACC_CAP(NV));
+            for (int sl = tid; sl < na; sl += TESS_MAIN_THREADS) {
+                const double* t = s_acc + sl * (NV + 1);
+                if (t[0] != 0.0) {
+                    double* m = a.mom + (long)s_gid[sl] * (NV + 1);
 #pragma unroll
-                        for (int i = 0; i <= NV; ++i) tess_gmem_add(m + i, t[i]);
-                    }
+                    for (int i = 0; i <= NV; ++i) tess_gmem_add(m + i, t[i]);
                 }
             }
-            __syncthreads();   // the table and the staged list are rewritten by the next tile
         }
+        __syncthreads();   // the table and the staged list are rewritten by the next tile
         tile = s_tile[(it + 1) & 1];
     }       // tiles
 }

@@ -113,6 +113,16 @@ static inline unsigned __ballot_sync(unsigned mask, int pred) {
     c.warp_bar->arrive_and_wait();
     return r;
 }
+static inline int __reduce_max_sync(unsigned mask, int v) {
+    assert(mask == 0xffffffffu);
+    auto& c = emu::tctx;
+    c.xchg[c.lane] = (uint64_t)(int64_t)v;
+    c.warp_bar->arrive_and_wait();
+    int r = (int)(int64_t)c.xchg[0];
+    for (int i = 1; i < 32; ++i) { int x = (int)(int64_t)c.xchg[i]; if (x > r) r = x; }
+    c.warp_bar->arrive_and_wait();
+    return r;
+}
 static inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) == 0xffffffffu; }
 static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0u; }
 template <class T>
