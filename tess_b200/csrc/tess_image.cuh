@@ -62,15 +62,6 @@ struct TessRun {
     double v[NV];
 };
 
-// Finished runs wait in a small per-warp shared-memory stage (two entries per lane) until the end
-// of the warp tile, where the warp merges equal bins and adds them to the CTA table.
-#define TESS_STAGE_DEPTH 2
-template <int NV>
-struct TessStage {
-    int2 key[TESS_STAGE_DEPTH][32];          // (slot, n)
-    double v[TESS_STAGE_DEPTH][NV][32];
-};
-
 // fp64 add to a shared-memory word (no native instruction: compare-and-swap loop on the 32-bit
 // shared address, so that no generic-address dispatch is generated)
 TESS_DEVFN void tess_smem_add(double* p, double v) {
@@ -123,69 +114,52 @@ TESS_NOINLINE void tess_table_add(double* s_acc, const int* s_gid, double* mom, 
     }
 }
 
-// The lane's current run ends: park it in the stage (or, if both of its entries are taken -- three
-// or more bin changes inside one 2x4 patch -- add it to the table directly).  Returns the new entry
-// count.  Out of line: it is reached from eight places of the unrolled pixel loop.
+// The lane's current run ends: its sums go to the CTA table; a new run starts.  (One call site per
+// fold variant; the table add is out of line.)
 template <int NV>
-TESS_NOINLINE int tess_run_stash(TessStage<NV>* stg, int nst, double* s_acc, const int* s_gid, double* mom, int lane,
-                                 int slot, int n, double v0, double v1, double v2, double v3, double v4) {
-    if (nst < TESS_STAGE_DEPTH) {
-        stg->key[nst][lane] = make_int2(slot, n);
-        stg->v[nst][0][lane] = v0;
-        stg->v[nst][1][lane] = v1;
-        stg->v[nst][2][lane] = v2;
-        if (NV > 3) {
-            stg->v[nst][NV - 2][lane] = v3;
-            stg->v[nst][NV - 1][lane] = v4;
-        }
-        return nst + 1;
-    }
-    tess_table_add<NV>(s_acc, s_gid, mom, slot, n, v0, v1, v2, v3, v4);
-    return nst;
-}
-
-template <int NV>
-TESS_DEVFN void tess_run_switch(TessRun<NV>& cur, int& nst, TessStage<NV>* stg, double* s_acc, const int* s_gid,
-                                double* mom, int lane, int slot) {
+TESS_DEVFN void tess_run_switch(TessRun<NV>& cur, double* s_acc, const int* s_gid, double* mom, int slot) {
     if (cur.n > 0)
-        nst = tess_run_stash<NV>(stg, nst, s_acc, s_gid, mom, lane, cur.slot, cur.n, cur.v[0], cur.v[1], cur.v[2],
-                                 NV > 3 ? cur.v[NV - 2] : 0.0, NV > 3 ? cur.v[NV - 1] : 0.0);
+        tess_table_add<NV>(s_acc, s_gid, mom, cur.slot, cur.n, cur.v[0], cur.v[1], cur.v[2],
+                           NV > 3 ? cur.v[NV - 2] : 0.0, NV > 3 ? cur.v[NV - 1] : 0.0);
     cur.slot = slot;
     cur.n = 0;
 #pragma unroll
     for (int i = 0; i < NV; ++i) cur.v[i] = 0.0;
 }
 
-// Warp-level aggregation of the staged runs: lanes whose entries carry the same bin form a group
-// (match.any); the lowest lane of each group sums the group's entries straight from shared memory
-// and adds the result to the CTA table.  All 32 lanes must call; nst is the lane's entry count.
+// End of a super-tile: every lane retires its live run.  Lanes that hold the same bin are merged
+// with shuffles first (warp-level aggregation), so the table receives one add per (warp, bin).
 template <int NV>
-TESS_NOINLINE void tess_warp_retire(TessStage<NV>* stg, int nst, double* s_acc, const int* s_gid, double* mom, int lane) {
-    __syncwarp();
-    for (int e = 0; e < TESS_STAGE_DEPTH; ++e) {
-        const bool has = nst > e;
-        if (!__any_sync(TESS_FULL, has)) break;
-        const int key = has ? stg->key[e][lane].x : -1 - lane;       // unique negative key: a group of one
-        unsigned grp = __match_any_sync(TESS_FULL, key);
-        if (has && lane == __ffs((int)grp) - 1) {
-            int n = 0;
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;
-            while (grp) {
-                const int m = __ffs((int)grp) - 1;
-                grp &= grp - 1;
-                n += stg->key[e][m].y;
-                s0 = __dadd_rn(s0, stg->v[e][0][m]);
-                s1 = __dadd_rn(s1, stg->v[e][1][m]);
-                s2 = __dadd_rn(s2, stg->v[e][2][m]);
+TESS_DEVFN void tess_warp_retire(TessRun<NV>& cur, double* s_acc, const int* s_gid, double* mom, int lane) {
+    unsigned todo = __ballot_sync(TESS_FULL, cur.n > 0);
+    while (todo) {
+        const int leader = __ffs((int)todo) - 1;
+        const int sl = __shfl_sync(TESS_FULL, cur.slot, leader);
+        const bool mine = (cur.n > 0) && (cur.slot == sl);
+        const unsigned grp = __ballot_sync(TESS_FULL, mine);
+        int n = mine ? cur.n : 0;
+        double s0 = mine ? cur.v[0] : 0.0, s1 = mine ? cur.v[1] : 0.0, s2 = mine ? cur.v[2] : 0.0;
+        double s3 = (NV > 3 && mine) ? cur.v[NV - 2] : 0.0, s4 = (NV > 3 && mine) ? cur.v[NV - 1] : 0.0;
+        if (grp != (1u << leader)) {
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) {
+                n += __shfl_xor_sync(TESS_FULL, n, m);
+                s0 = __dadd_rn(s0, __shfl_xor_sync(TESS_FULL, s0, m));
+                s1 = __dadd_rn(s1, __shfl_xor_sync(TESS_FULL, s1, m));
+                s2 = __dadd_rn(s2, __shfl_xor_sync(TESS_FULL, s2, m));
                 if (NV > 3) {
-                    s3 = __dadd_rn(s3, stg->v[e][NV - 2][m]);
-                    s4 = __dadd_rn(s4, stg->v[e][NV - 1][m]);
+                    s3 = __dadd_rn(s3, __shfl_xor_sync(TESS_FULL, s3, m));
+                    s4 = __dadd_rn(s4, __shfl_xor_sync(TESS_FULL, s4, m));
                 }
             }
-            tess_table_add<NV>(s_acc, s_gid, mom, key, n, s0, s1, s2, s3, s4);
         }
+        if (lane == leader) tess_table_add<NV>(s_acc, s_gid, mom, sl, n, s0, s1, s2, s3, s4);
+        todo &= ~grp;
     }
-    __syncwarp();
+    cur.slot = -1;
+    cur.n = 0;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) cur.v[i] = 0.0;
 }
 
 // upper bound of sqrt(x) for x >= 0 from the fp32 unit (exact value is not needed, only >=)
@@ -355,6 +329,7 @@ TESS_DEVFN int tess_filter(const double2* s_g, const double* s_inv, const unsign
 
 #define TESS_BCAP 64        // 16x16 block list capacity
 #define TESS_BLOCK_MIN 20   // quadrant lists longer than this get the intermediate 16x16 level
+#define TESS_LEAF_MIN 3     // parent lists up to this length are evaluated without a leaf filter
 
 // MODE 0: labels only; 1: density map (4 moments); 2: signal + noise maps (6 moments)
 template <int MODE, bool HAS_SCALE, bool VEC>
@@ -374,7 +349,6 @@ k_image_main(TessImgArgs a) {
     __shared__ double s_li[HAS_SCALE ? NW : 1][4][HAS_SCALE ? TESS_LEAF_CAP : 1];   // ... 1/scale^2 ...
     __shared__ unsigned short s_ls[NW][4][TESS_LEAF_CAP];          // ... and slot
     __shared__ double s_acc[(MODE != 0) ? TESS_ACC_CAP(NV) * (NV + 1) : 1];   // per-slot accumulators
-    __shared__ TessStage<NV> s_stage[(MODE != 0) ? NW : 1];
     __shared__ int s_tile[2];
 
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
@@ -383,14 +357,13 @@ k_image_main(TessImgArgs a) {
     const int blk = cx >> 3;                           // 16-px-wide block
     unsigned short* const ql = s_ql[wib];
     const int n_tiles = a.tiles_x * a.tiles_y;
-    TessStage<NV>* const stg = &s_stage[(MODE != 0) ? wib : 0];
+    const double* const src = (MODE == 2) ? a.sig : a.dens;   // MODE 1: weight map; MODE 2: signal map
 
     TessRun<NV> cur;                 // the lane's running same-label sum (registers)
     cur.slot = -1;
     cur.n = 0;
 #pragma unroll
     for (int i = 0; i < NV; ++i) cur.v[i] = 0.0;
-    int nst = 0;                     // entries of this lane in the stage
 
     if (tid == 0) s_tile[0] = atomicAdd(&a.st->tile_counter, 1);
     __syncthreads();
@@ -410,6 +383,8 @@ k_image_main(TessImgArgs a) {
         const long qy0 = (long)ty * TESS_TS + 32 * (wib >> 1);
         const bool q_in = (qx0 < a.W) && (qy0 < a.H);
         const long qx1 = min(qx0 + 31, a.W - 1), qy1 = min(qy0 + 31, a.H - 1);
+        // interior tile: every pixel access of the tile is in bounds (and 16-byte aligned: VEC)
+        const bool interior = VEC && ((long)(tx + 1) * TESS_TS <= a.W) && ((long)(ty + 1) * TESS_TS <= a.H);
         const long px = qx0 + 2 * cx;                    // first column of this lane
         const double X0 = a.x0 + (double)px, X1 = a.x0 + (double)(px + 1);
 
@@ -449,35 +424,34 @@ k_image_main(TessImgArgs a) {
             const long wy0 = qy0 + 8 * step;
             if (wy0 >= a.H) break;                         // warp-uniform
             const long py = wy0 + 4 * ry;                  // first row of this lane
+            const long base0 = py * a.W + px;              // flat index of the patch's first pixel
+            double Y[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) Y[r] = a.y0 + (double)(py + r);
 
             // ---- issue the pixel loads early; they are consumed after the candidate evaluation.
             //      Pixels outside the image read as NaN and drop out with the masked ones.
             double w_[4][2], n_[4][2];                     // MODE 1: weight; MODE 2: signal, noise
             if (MODE != 0) {
+                if (interior) {
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const bool rin = (py + r < a.H);
-                    const long base = (py + r) * a.W + px;
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) { w_[r][c] = TESS_NAN; n_[r][c] = TESS_NAN; }
-                    const double* src = (MODE == 1) ? a.dens : a.sig;
-                    if (VEC) {
-                        if (rin && px < a.W) {
-                            const double2 v = *reinterpret_cast<const double2*>(src + base);
-                            w_[r][0] = v.x; w_[r][1] = v.y;
-                            if (MODE == 2) {
-                                const double2 u = *reinterpret_cast<const double2*>(a.noise + base);
-                                n_[r][0] = u.x; n_[r][1] = u.y;
-                            }
+                    for (int r = 0; r < 4; ++r) {
+                        const double2 v = *reinterpret_cast<const double2*>(src + base0 + r * a.W);
+                        w_[r][0] = v.x; w_[r][1] = v.y;
+                        if (MODE == 2) {
+                            const double2 u = *reinterpret_cast<const double2*>(a.noise + base0 + r * a.W);
+                            n_[r][0] = u.x; n_[r][1] = u.y;
                         }
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 2; ++c)
-                            if (rin && px + c < a.W) {
-                                w_[r][c] = src[base + c];
-                                if (MODE == 2) n_[r][c] = a.noise[base + c];
-                            }
                     }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            const bool in = (py + r < a.H) && (px + c < a.W);
+                            w_[r][c] = in ? src[base0 + r * a.W + c] : TESS_NAN;
+                            if (MODE == 2) n_[r][c] = in ? a.noise[base0 + r * a.W + c] : TESS_NAN;
+                        }
                 }
             }
 
@@ -496,27 +470,17 @@ k_image_main(TessImgArgs a) {
                 }
             }
 
-            // ---- best (distance, slot) per pixel
-            double bd[4][2];
-            int bs[4][2];
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-                for (int c = 0; c < 2; ++c) { bd[r][c] = INFINITY; bs[r][c] = 0; }
-
-            if (c_q == 1) {
-                const int sl = q_ident ? 0 : (int)ql[0];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) { bs[r][0] = sl; bs[r][1] = sl; }
-            } else {
-                // ---- leaf list: parent list -> candidates of this lane's 8x8 leaf
-                double2* const lg = s_lg[wib][leaf];
-                unsigned short* const ls = s_ls[wib][leaf];
-                double* const li = HAS_SCALE ? s_li[wib][leaf] : nullptr;
-                int len = 0;
-                bool use_leaf = false;
+            // ---- candidates of this lane's 8x8 leaf
+            double2* const lg = s_lg[wib][leaf];
+            unsigned short* const ls = s_ls[wib][leaf];
+            double* const li = HAS_SCALE ? s_li[wib][leaf] : nullptr;
+            int len = 0;
+            bool use_leaf = false;
+            bool uniform = (c_q == 1);                     // the whole warp tile belongs to one bin
+            int usl = q_ident ? 0 : (int)ql[0];
+            if (!uniform) {
                 const int p_max = __reduce_max_sync(TESS_FULL, p_len);    // the two blocks' lists differ in length
-                if (p_max > 2) {
+                if (p_max > TESS_LEAF_MIN) {
                     const long lx0 = qx0 + 8 * leaf;
                     const long lx1 = min(lx0 + 7, a.W - 1), ly1 = min(wy0 + 7, a.H - 1);
                     const double hx = 0.5 * (double)(lx1 - lx0), hy = 0.5 * (double)(ly1 - wy0);
@@ -525,9 +489,39 @@ k_image_main(TessImgArgs a) {
                                                           sqrt(hx * hx + hy * hy) * 1.0000001, lx0 < a.W, lane, ls, lg, li,
                                                           TESS_LEAF_CAP);
                     use_leaf = (len <= TESS_LEAF_CAP);
+                    // all (in-image) leaves ended with the same single candidate?
+                    const int one = (len == 1) ? (int)ls[0] : ((lx0 < a.W) ? -1 : -3);
+                    const int ref = __reduce_max_sync(TESS_FULL, one);
+                    uniform = (ref >= 0) && __all_sync(TESS_FULL, one == ref || one == -3);
+                    usl = ref;
                 }
+            }
+
+            int bs[4][2];                                  // winning slot per pixel
+            if (uniform) {
+                // ---- one bin for all 256 pixels: constant labels, patch sums in closed form
+                const int gid = s_gid[usl];
+                if (interior) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) *reinterpret_cast<int2*>(labels + base0 + r * a.W) = make_int2(gid, gid);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int c = 0; c < 2; ++c)
+                            if ((py + r < a.H) && (px + c < a.W)) labels[base0 + r * a.W + c] = gid;
+                }
+                if (MODE == 0) continue;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) { bs[r][0] = usl; bs[r][1] = usl; }
+            } else {
                 // ---- evaluate the surviving candidates with the pinned formula (ascending index:
                 //      strict '<' keeps the lowest index on exact ties)
+                double bd[4][2];
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) { bd[r][c] = INFINITY; bs[r][c] = 0; }
                 const int n_ev = use_leaf ? len : p_len;
                 for (int j = 0; j < n_ev; ++j) {
                     double2 g;
@@ -546,8 +540,7 @@ k_image_main(TessImgArgs a) {
                     const double dxx0 = __dmul_rn(dx0, dx0), dxx1 = __dmul_rn(dx1, dx1);
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
-                        const double Y = a.y0 + (double)(py + r);
-                        const double dy = __dsub_rn(Y, g.y);
+                        const double dy = __dsub_rn(Y[r], g.y);
                         const double dyy = __dmul_rn(dy, dy);
                         double d0 = __dadd_rn(dxx0, dyy), d1 = __dadd_rn(dxx1, dyy);
                         if (HAS_SCALE) { d0 = __dmul_rn(d0, inv); d1 = __dmul_rn(d1, inv); }
@@ -555,53 +548,82 @@ k_image_main(TessImgArgs a) {
                         if (d1 < bd[r][1]) { bd[r][1] = d1; bs[r][1] = sl; }
                     }
                 }
-            }
-
-            // ---- labels out: 16 lanes x 8 B = one 128-byte line per row
+                // ---- labels out: 16 lanes x 8 B = one 128-byte line per row
+                if (interior) {
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                if (py + r < a.H) {
-                    const long base = (py + r) * a.W + px;
-                    const int g0 = s_gid[bs[r][0]], g1 = s_gid[bs[r][1]];
-                    if (VEC) {
-                        if (px < a.W) *reinterpret_cast<int2*>(labels + base) = make_int2(g0, g1);
-                    } else {
-                        if (px < a.W) labels[base] = g0;
-                        if (px + 1 < a.W) labels[base + 1] = g1;
-                    }
+                    for (int r = 0; r < 4; ++r)
+                        *reinterpret_cast<int2*>(labels + base0 + r * a.W) = make_int2(s_gid[bs[r][0]], s_gid[bs[r][1]]);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int c = 0; c < 2; ++c)
+                            if ((py + r < a.H) && (px + c < a.W)) labels[base0 + r * a.W + c] = s_gid[bs[r][c]];
                 }
+                if (MODE == 0) continue;
             }
 
-            // ---- moments
-            if (MODE != 0) {
-                // weights; masked pixels (non-finite weight, signal or noise; outside the image) are
-                // marked consumed (slot -2) so that the passes below skip them
-                double wv[4][2];
+            // ---- moments.  Weights first; masked pixels (non-finite weight, signal or noise; outside
+            //      the image) are marked consumed (slot -2).
+            double wv[4][2];
+            bool clean = true;                             // no masked pixel in this patch
 #pragma unroll
-                for (int r = 0; r < 4; ++r)
+            for (int r = 0; r < 4; ++r)
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        double w = w_[r][c];
-                        bool ok;
-                        if (MODE == 2) {
-                            const double S = w_[r][c], N = n_[r][c];
-                            w = 1.0;
-                            if (!a.uniform_weight) { const double q = __ddiv_rn(S, N); w = __dmul_rn(q, q); }
-                            ok = (fabs(w) <= 1.7976931348623157e308) && (fabs(S) <= 1.7976931348623157e308) &&
-                                 (fabs(N) <= 1.7976931348623157e308);
-                        } else {
-                            ok = fabs(w) <= 1.7976931348623157e308;
-                        }
-                        wv[r][c] = w;
-                        if (!ok) bs[r][c] = -2;
+                for (int c = 0; c < 2; ++c) {
+                    double w = w_[r][c];
+                    bool ok;
+                    if (MODE == 2) {
+                        const double S = w_[r][c], N = n_[r][c];
+                        w = 1.0;
+                        if (!a.uniform_weight) { const double q = __ddiv_rn(S, N); w = __dmul_rn(q, q); }
+                        ok = (fabs(w) <= 1.7976931348623157e308) && (fabs(S) <= 1.7976931348623157e308) &&
+                             (fabs(N) <= 1.7976931348623157e308);
+                    } else {
+                        ok = fabs(w) <= 1.7976931348623157e308;
                     }
-                // Each pass folds every not yet consumed pixel of the current run's bin into the
-                // lane's registers; lanes with pixels left then park the run in the stage (ONE code
-                // location for the whole warp) and start the run of one of the remaining bins.
+                    wv[r][c] = w;
+                    clean = clean && ok;
+                    if (!ok) bs[r][c] = -2;
+                }
+            if (uniform && __all_sync(TESS_FULL, clean)) {
+                // closed form for a one-bin patch: sum w x = X0 col0 + X1 col1, sum w y = sum_r Y_r row_r
+                if (cur.slot != usl) tess_run_switch<NV>(cur, s_acc, s_gid, a.mom, usl);
+                const double c0 = __dadd_rn(__dadd_rn(wv[0][0], wv[1][0]), __dadd_rn(wv[2][0], wv[3][0]));
+                const double c1 = __dadd_rn(__dadd_rn(wv[0][1], wv[1][1]), __dadd_rn(wv[2][1], wv[3][1]));
+                double sy = 0.0;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) sy = __dadd_rn(sy, __dmul_rn(__dadd_rn(wv[r][0], wv[r][1]), Y[r]));
+                cur.n += 8;
+                cur.v[0] = __dadd_rn(cur.v[0], __dadd_rn(c0, c1));
+                cur.v[1] = __dadd_rn(cur.v[1], __dadd_rn(__dmul_rn(c0, X0), __dmul_rn(c1, X1)));
+                cur.v[2] = __dadd_rn(cur.v[2], sy);
+                if (MODE == 2) {
+                    double ss = 0.0, nn = 0.0;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            ss = __dadd_rn(ss, w_[r][c]);
+                            nn = __dadd_rn(nn, __dmul_rn(n_[r][c], n_[r][c]));
+                        }
+                    cur.v[NV - 2] = __dadd_rn(cur.v[NV - 2], ss);
+                    cur.v[NV - 1] = __dadd_rn(cur.v[NV - 1], nn);
+                }
+            } else {
+                // Rounds: a lane whose current run's bin is no longer among its unconsumed pixels ends
+                // that run (ONE code location for the whole warp) and starts the run of one of the
+                // remaining bins; then every lane folds all its pixels of its run's bin.
                 for (;;) {
+                    const int rest = max(max(max(bs[0][0], bs[0][1]), max(bs[1][0], bs[1][1])),
+                                         max(max(bs[2][0], bs[2][1]), max(bs[3][0], bs[3][1])));
+                    if (!__any_sync(TESS_FULL, rest >= 0)) break;
+                    bool present = false;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) present = present || (bs[r][0] == cur.slot) || (bs[r][1] == cur.slot);
+                    if (rest >= 0 && !present) tess_run_switch<NV>(cur, s_acc, s_gid, a.mom, rest);
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
-                        const double Y = a.y0 + (double)(py + r);
 #pragma unroll
                         for (int c = 0; c < 2; ++c) {
                             if (bs[r][c] == cur.slot) {
@@ -609,7 +631,7 @@ k_image_main(TessImgArgs a) {
                                 cur.n += 1;
                                 cur.v[0] = __dadd_rn(cur.v[0], w);
                                 cur.v[1] = __dadd_rn(cur.v[1], __dmul_rn(w, c ? X1 : X0));
-                                cur.v[2] = __dadd_rn(cur.v[2], __dmul_rn(w, Y));
+                                cur.v[2] = __dadd_rn(cur.v[2], __dmul_rn(w, Y[r]));
                                 if (MODE == 2) {
                                     cur.v[NV - 2] = __dadd_rn(cur.v[NV - 2], w_[r][c]);
                                     cur.v[NV - 1] = __dadd_rn(cur.v[NV - 1], __dmul_rn(n_[r][c], n_[r][c]));
@@ -618,25 +640,12 @@ k_image_main(TessImgArgs a) {
                             }
                         }
                     }
-                    int rest = max(max(max(bs[0][0], bs[0][1]), max(bs[1][0], bs[1][1])),
-                                   max(max(bs[2][0], bs[2][1]), max(bs[3][0], bs[3][1])));
-                    if (!__any_sync(TESS_FULL, rest >= 0)) break;
-                    if (rest >= 0) tess_run_switch<NV>(cur, nst, stg, s_acc, s_gid, a.mom, lane, rest);
-                }
-                // ---- runs that ended in this warp tile: merge across the warp, add to the table
-                if (__any_sync(TESS_FULL, nst > 0)) {
-                    tess_warp_retire<NV>(stg, nst, s_acc, s_gid, a.mom, lane);
-                    nst = 0;
                 }
             }
         }   // steps
 
-        // ---- end of super-tile: retire the live runs, then table -> global moment vector
-        if (MODE != 0) {
-            tess_run_switch<NV>(cur, nst, stg, s_acc, s_gid, a.mom, lane, -1);
-            tess_warp_retire<NV>(stg, nst, s_acc, s_gid, a.mom, lane);
-            nst = 0;
-        }
+        // ---- end of super-tile: retire the live runs (merged across the warp), then table -> global
+        if (MODE != 0) tess_warp_retire<NV>(cur, s_acc, s_gid, a.mom, lane);
         __syncthreads();
         if (MODE != 0) {
             const int na = min(cnt, TESS_ACC_CAP(NV));
