@@ -7,29 +7,34 @@
 //
 // One persistent CTA (4 warps) pulls 64x64 super-tiles from a dynamic counter.  Per super-tile the
 // candidate list (k_build_lists, sorted by generator index) is staged in shared memory.  Each warp
-// owns a 32x32 quadrant: it narrows the list once for the quadrant and then, for each of its four
-// 32x8 warp tiles, once more per 8x8 leaf (8 lanes per leaf) with a centre + radius test
+// owns a 32x32 quadrant: it narrows the list once for the quadrant, once more per 16x16 block where
+// the list is long, and for each of its four 32x8 warp tiles once per 8x8 leaf (8 lanes per leaf),
+// always with the centre + radius test
 //     keep g  iff  u(c,g) <= min_h u(c,h) + 2 rho / s_min        (u = distance / scale)
-// which can never drop the true nearest generator of any pixel of the leaf.  The survivors are
+// which can never drop the true nearest generator of any pixel of the rectangle.  The survivors are
 // evaluated with the pinned fp64 formula; lists are in ascending generator index, so a strict '<'
 // implements the lowest-index tie rule.  Labels leave as one coalesced 128-byte line per row.
 //
 // Moments ("segmented reduction"): every lane owns a 2-column x 4-row pixel patch per warp tile and
-// keeps ONE running same-label accumulator in registers across the warp tiles of a quadrant
-// (labels are spatially coherent, so most patches extend the current run).  When a run ends, the
-// lanes of the warp that retire the same bin are merged with shuffles (warp-level aggregation) and
-// one lane adds the result to the CTA's shared-memory table of per-candidate accumulators; only at
-// the end of the super-tile does the table go to the global moment vector, one fp64 reduction per
-// (tile, bin, moment).
+// keeps ONE running same-bin sum in registers across the warp tiles of a quadrant (labels are
+// spatially coherent, so most patches extend the current run).  When a lane's run ends, its sums go
+// to the warp's shared-memory table of per-candidate accumulators; lanes that retire the same bin in
+// the same round are serialised with match.any (warp-level aggregation, no atomics: the table is
+// private to the warp).  At the end of the quadrant the live runs are merged across the warp with
+// shuffles, and the table goes to the global moment vector -- one fp64 reduction per
+// (quadrant, bin, moment).  The whole fold is written without lane-divergent branches.
 //
 // Algorithmic HBM traffic per pixel: MODE 1: 8 B (density) + 4 B (label) = 12 B;
 // MODE 2: 8 + 8 B (signal, noise) + 4 B = 20 B; MODE 0: 4 B.  Pixel coordinates are implicit.
 #pragma once
 #include "tess_common.cuh"
 
-#define TESS_QCAP 256       // quadrant list capacity (else the staged list is used as is)
-// shared accumulator slots per super-tile (runs of slots beyond it go straight to the global vector)
-#define TESS_ACC_CAP(NV) ((NV) > 3 ? 160 : 256)
+#define TESS_QCAP 128       // quadrant list capacity (else the staged list is used as is)
+#define TESS_BCAP 64        // 16x16 block list capacity
+#define TESS_BLOCK_MIN 20   // quadrant lists longer than this get the intermediate 16x16 level
+#define TESS_LEAF_MIN 3     // parent lists up to this length are evaluated without a leaf filter
+// entries of a warp's accumulator table (quadrant-list positions beyond it go straight to global)
+#define TESS_TQ(NV) ((NV) > 3 ? 96 : 128)
 
 struct TessImgArgs {
     const double* dens;    // MODE 1: [H][W] weights
@@ -53,31 +58,15 @@ struct TessImgArgs {
     int honor;             // honour the convergence latch (iteration kernels) or not (segmap)
 };
 
-// A run of same-label pixels being summed by one lane (registers).
+// A run of same-bin pixels being summed by one lane (registers).
 // v = sum w, sum w*x, sum w*y [, sum S, sum N^2]
 template <int NV>
 struct TessRun {
-    int slot;   // index into the staged candidate list; -1 = none yet
+    int key;    // position in the quadrant's candidate list; -1 = none yet
     int n;      // pixel count
     double v[NV];
 };
 
-// fp64 add to a shared-memory word (no native instruction: compare-and-swap loop on the 32-bit
-// shared address, so that no generic-address dispatch is generated)
-TESS_DEVFN void tess_smem_add(double* p, double v) {
-#ifndef TESS_EMU
-    const unsigned addr = (unsigned)__cvta_generic_to_shared(p);
-    unsigned long long old, assumed;
-    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(old) : "r"(addr));
-    do {
-        assumed = old;
-        const unsigned long long upd = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)assumed), v));
-        asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(addr), "l"(assumed), "l"(upd) : "memory");
-    } while (old != assumed);
-#else
-    atomicAdd(p, v);
-#endif
-}
 TESS_DEVFN void tess_gmem_add(double* p, double v) {
 #ifndef TESS_EMU
     asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
@@ -86,77 +75,72 @@ TESS_DEVFN void tess_gmem_add(double* p, double v) {
 #endif
 }
 
-// one lane adds a finished run to the CTA table (or, beyond its capacity, to the global vector).
-// Out of line and with scalar arguments so that the callers' accumulators stay in registers.
+// Lanes with `flush` set add their run (key, n, v) to the warp's table.  Lanes holding the same key
+// take turns (match.any elects one lane per distinct key per turn), so plain read-modify-writes are
+// enough.  Keys beyond the table go to the global vector.  All 32 lanes must call; no divergence.
 template <int NV>
-TESS_NOINLINE void tess_table_add(double* s_acc, const int* s_gid, double* mom, int slot, int n, double v0, double v1,
-                                  double v2, double v3, double v4) {
-    if (slot < TESS_ACC_CAP(NV)) {
-        double* t = s_acc + slot * (NV + 1);
-        tess_smem_add(t, (double)n);
-        tess_smem_add(t + 1, v0);
-        tess_smem_add(t + 2, v1);
-        tess_smem_add(t + 3, v2);
-        if (NV > 3) {
-            tess_smem_add(t + 4, v3);
-            tess_smem_add(t + 5, v4);
+TESS_DEVFN void tess_table_flush(bool flush, int key, int n, const double (&v)[NV], double* tab, const int* gidv,
+                                 double* mom, int lane) {
+    bool pending = flush;
+    while (__any_sync(TESS_FULL, pending)) {
+        const unsigned grp = __match_any_sync(TESS_FULL, pending ? key : -1 - lane);
+        if (pending && lane == __ffs((int)grp) - 1) {
+            if (key < TESS_TQ(NV)) {
+                double* t = tab + key * (NV + 1);
+                t[0] += (double)n;
+#pragma unroll
+                for (int i = 0; i < NV; ++i) t[1 + i] = __dadd_rn(t[1 + i], v[i]);
+            } else {
+                double* m = mom + (long)gidv[key] * (NV + 1);
+                tess_gmem_add(m, (double)n);
+#pragma unroll
+                for (int i = 0; i < NV; ++i) tess_gmem_add(m + 1 + i, v[i]);
+            }
+            pending = false;
         }
-    } else {
-        double* t = mom + (long)s_gid[slot] * (NV + 1);
-        tess_gmem_add(t, (double)n);
-        tess_gmem_add(t + 1, v0);
-        tess_gmem_add(t + 2, v1);
-        tess_gmem_add(t + 3, v2);
-        if (NV > 3) {
-            tess_gmem_add(t + 4, v3);
-            tess_gmem_add(t + 5, v4);
-        }
+        __syncwarp();
     }
 }
 
-// The lane's current run ends: its sums go to the CTA table; a new run starts.  (One call site per
-// fold variant; the table add is out of line.)
+// End of a quadrant: every lane retires its live run.  Lanes that hold the same bin are merged with
+// shuffles first, so the table receives one add per bin.
 template <int NV>
-TESS_DEVFN void tess_run_switch(TessRun<NV>& cur, double* s_acc, const int* s_gid, double* mom, int slot) {
-    if (cur.n > 0)
-        tess_table_add<NV>(s_acc, s_gid, mom, cur.slot, cur.n, cur.v[0], cur.v[1], cur.v[2],
-                           NV > 3 ? cur.v[NV - 2] : 0.0, NV > 3 ? cur.v[NV - 1] : 0.0);
-    cur.slot = slot;
-    cur.n = 0;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) cur.v[i] = 0.0;
-}
-
-// End of a super-tile: every lane retires its live run.  Lanes that hold the same bin are merged
-// with shuffles first (warp-level aggregation), so the table receives one add per (warp, bin).
-template <int NV>
-TESS_DEVFN void tess_warp_retire(TessRun<NV>& cur, double* s_acc, const int* s_gid, double* mom, int lane) {
+TESS_DEVFN void tess_warp_retire(TessRun<NV>& cur, double* tab, const int* gidv, double* mom, int lane) {
     unsigned todo = __ballot_sync(TESS_FULL, cur.n > 0);
     while (todo) {
         const int leader = __ffs((int)todo) - 1;
-        const int sl = __shfl_sync(TESS_FULL, cur.slot, leader);
-        const bool mine = (cur.n > 0) && (cur.slot == sl);
+        const int key = __shfl_sync(TESS_FULL, cur.key, leader);
+        const bool mine = (cur.n > 0) && (cur.key == key);
         const unsigned grp = __ballot_sync(TESS_FULL, mine);
         int n = mine ? cur.n : 0;
-        double s0 = mine ? cur.v[0] : 0.0, s1 = mine ? cur.v[1] : 0.0, s2 = mine ? cur.v[2] : 0.0;
-        double s3 = (NV > 3 && mine) ? cur.v[NV - 2] : 0.0, s4 = (NV > 3 && mine) ? cur.v[NV - 1] : 0.0;
+        double s[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) s[i] = mine ? cur.v[i] : 0.0;
         if (grp != (1u << leader)) {
 #pragma unroll
             for (int m = 16; m >= 1; m >>= 1) {
                 n += __shfl_xor_sync(TESS_FULL, n, m);
-                s0 = __dadd_rn(s0, __shfl_xor_sync(TESS_FULL, s0, m));
-                s1 = __dadd_rn(s1, __shfl_xor_sync(TESS_FULL, s1, m));
-                s2 = __dadd_rn(s2, __shfl_xor_sync(TESS_FULL, s2, m));
-                if (NV > 3) {
-                    s3 = __dadd_rn(s3, __shfl_xor_sync(TESS_FULL, s3, m));
-                    s4 = __dadd_rn(s4, __shfl_xor_sync(TESS_FULL, s4, m));
-                }
+#pragma unroll
+                for (int i = 0; i < NV; ++i) s[i] = __dadd_rn(s[i], __shfl_xor_sync(TESS_FULL, s[i], m));
             }
         }
-        if (lane == leader) tess_table_add<NV>(s_acc, s_gid, mom, sl, n, s0, s1, s2, s3, s4);
+        if (lane == leader) {
+            if (key < TESS_TQ(NV)) {
+                double* t = tab + key * (NV + 1);
+                t[0] += (double)n;
+#pragma unroll
+                for (int i = 0; i < NV; ++i) t[1 + i] = __dadd_rn(t[1 + i], s[i]);
+            } else {
+                double* m = mom + (long)gidv[key] * (NV + 1);
+                tess_gmem_add(m, (double)n);
+#pragma unroll
+                for (int i = 0; i < NV; ++i) tess_gmem_add(m + 1 + i, s[i]);
+            }
+        }
         todo &= ~grp;
     }
-    cur.slot = -1;
+    __syncwarp();
+    cur.key = -1;
     cur.n = 0;
 #pragma unroll
     for (int i = 0; i < NV; ++i) cur.v[i] = 0.0;
@@ -270,20 +254,24 @@ TESS_DEVFN double tess_group_min(double v) {
     return v;
 }
 
-// Centre + radius filter of a slot list (`pl`, or the identity 0..plen-1 when pident) for the
-// rectangle with centre (ccx, ccy) and half-diagonal rho, done by a group of GROUP lanes:
+// Centre + radius filter of a candidate list for the rectangle with centre (ccx, ccy) and
+// half-diagonal rho, done by a group of GROUP lanes:
 //   keep g  iff  u(c,g) <= min_h u(c,h) + 2 rho / s_min      (u = distance / scale)
-// Order preserving.  If LEAF, the survivors' coordinates go to (lg, ls, li), else their slots to `out`.
-// Returns the number of survivors (which may exceed `cap`: the caller then keeps using the parent).
+// The input list holds plen elements e_i = pident ? i : pl[i]; an element maps to a staged slot by
+// slot = q_ident ? e : ql[e].  Order preserving.  Survivors' elements go to `out` (QUAD: also their
+// generator indices to `qgid`; LEAF: also their coordinates to lg / li).  Returns the number of
+// survivors (which may exceed `cap`: the caller then keeps using the parent list).
 // plen may differ between groups of a warp; plen_max is its maximum over the warp.
-template <int GROUP, bool HAS_SCALE, bool LEAF>
-TESS_DEVFN int tess_filter(const double2* s_g, const double* s_inv, const unsigned short* pl, bool pident, int plen,
-                           int plen_max, double ccx, double ccy, double rho, bool active, int lane, unsigned short* out, double2* lg,
+template <int GROUP, bool HAS_SCALE, bool QUAD, bool LEAF>
+TESS_DEVFN int tess_filter(const double2* s_g, const double* s_inv, const int* s_gid, const unsigned short* ql,
+                           bool q_ident, const unsigned short* pl, bool pident, int plen, int plen_max, double ccx,
+                           double ccy, double rho, bool active, int lane, unsigned short* out, int* qgid, double2* lg,
                            double* li, int cap) {
     const int rank = tess_group_rank<GROUP>(lane);
     double umin = INFINITY, imax = 1.0;
     for (int i = rank; i < plen; i += GROUP) {
-        const int sl = pident ? i : (int)pl[i];
+        const int e = pident ? i : (int)pl[i];
+        const int sl = q_ident ? e : (int)ql[e];
         const double2 g = s_g[sl];
         const double dx = ccx - g.x, dy = ccy - g.y;
         double d = dx * dx + dy * dy;
@@ -301,11 +289,12 @@ TESS_DEVFN int tess_filter(const double2* s_g, const double* s_inv, const unsign
     for (int b0 = 0; b0 < plen_max; b0 += GROUP) {     // plen_max: warp-uniform bound (ballots inside)
         const int i = b0 + rank;
         bool keep = false;
-        int sl = 0;
+        int e = 0, sl = 0;
         double2 g = make_double2(0.0, 0.0);
         double iv = 1.0;
         if (i < plen) {
-            sl = pident ? i : (int)pl[i];
+            e = pident ? i : (int)pl[i];
+            sl = q_ident ? e : (int)ql[e];
             g = s_g[sl];
             const double dx = ccx - g.x, dy = ccy - g.y;
             double d = dx * dx + dy * dy;
@@ -315,7 +304,8 @@ TESS_DEVFN int tess_filter(const double2* s_g, const double* s_inv, const unsign
         const unsigned gb = tess_group_bits<GROUP>(__ballot_sync(TESS_FULL, keep), lane);
         const int pos = n + __popc(gb & ((1u << rank) - 1u));
         if (keep && pos < cap) {
-            out[pos] = (unsigned short)sl;
+            out[pos] = (unsigned short)e;
+            if (QUAD) qgid[pos] = s_gid[sl];
             if (LEAF) {
                 lg[pos] = g;
                 if (HAS_SCALE) li[pos] = iv;
@@ -327,28 +317,26 @@ TESS_DEVFN int tess_filter(const double2* s_g, const double* s_inv, const unsign
     return n;
 }
 
-#define TESS_BCAP 64        // 16x16 block list capacity
-#define TESS_BLOCK_MIN 20   // quadrant lists longer than this get the intermediate 16x16 level
-#define TESS_LEAF_MIN 3     // parent lists up to this length are evaluated without a leaf filter
-
 // MODE 0: labels only; 1: density map (4 moments); 2: signal + noise maps (6 moments)
 template <int MODE, bool HAS_SCALE, bool VEC>
 __global__ void __launch_bounds__(TESS_MAIN_THREADS, TESS_MAIN_MINBLOCKS)
 k_image_main(TessImgArgs a) {
     constexpr int NV = (MODE == 2) ? 5 : 3;
     constexpr int NW = TESS_MAIN_THREADS / 32;
+    constexpr int TQ = TESS_TQ(NV);
     if (TESS_STOPPED(a.st, a.honor)) return;
     int32_t* const labels = a.labels_ext ? a.labels_ext : ((a.st->iters_done & 1) ? a.lab1 : a.lab0);
 
-    __shared__ __align__(16) double2 s_g[TESS_CAP];     // generator (x, y) of each list slot
+    __shared__ __align__(16) double2 s_g[TESS_CAP];     // generator (x, y) of each staged slot
     __shared__ int s_gid[TESS_CAP];                     // its global index
     __shared__ double s_inv[HAS_SCALE ? TESS_CAP : 1];  // 1/scale^2
-    __shared__ unsigned short s_ql[NW][TESS_QCAP];      // quadrant lists (slots)
-    __shared__ unsigned short s_bl[NW][2][TESS_BCAP];   // 16x16 block lists (slots)
+    __shared__ unsigned short s_ql[NW][TESS_QCAP];      // quadrant lists: staged slots ...
+    __shared__ int s_qgid[NW][TESS_QCAP];               // ... and their generator indices
+    __shared__ unsigned short s_bl[NW][2][TESS_BCAP];   // 16x16 block lists (quadrant-list positions)
     __shared__ __align__(16) double2 s_lg[NW][4][TESS_LEAF_CAP];   // leaf lists: coordinates ...
     __shared__ double s_li[HAS_SCALE ? NW : 1][4][HAS_SCALE ? TESS_LEAF_CAP : 1];   // ... 1/scale^2 ...
-    __shared__ unsigned short s_ls[NW][4][TESS_LEAF_CAP];          // ... and slot
-    __shared__ double s_acc[(MODE != 0) ? TESS_ACC_CAP(NV) * (NV + 1) : 1];   // per-slot accumulators
+    __shared__ unsigned short s_ls[NW][4][TESS_LEAF_CAP];          // ... and quadrant-list position
+    __shared__ double s_tab[(MODE != 0) ? NW : 1][(MODE != 0) ? TQ * (NV + 1) : 1];   // per-warp accumulators
     __shared__ int s_tile[2];
 
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
@@ -356,11 +344,12 @@ k_image_main(TessImgArgs a) {
     const int leaf = cx >> 2;                          // 8-px-wide leaf of the warp tile
     const int blk = cx >> 3;                           // 16-px-wide block
     unsigned short* const ql = s_ql[wib];
+    double* const tab = s_tab[(MODE != 0) ? wib : 0];
     const int n_tiles = a.tiles_x * a.tiles_y;
     const double* const src = (MODE == 2) ? a.sig : a.dens;   // MODE 1: weight map; MODE 2: signal map
 
-    TessRun<NV> cur;                 // the lane's running same-label sum (registers)
-    cur.slot = -1;
+    TessRun<NV> cur;                 // the lane's running same-bin sum (registers)
+    cur.key = -1;
     cur.n = 0;
 #pragma unroll
     for (int i = 0; i < NV; ++i) cur.v[i] = 0.0;
@@ -388,7 +377,7 @@ k_image_main(TessImgArgs a) {
         const long px = qx0 + 2 * cx;                    // first column of this lane
         const double X0 = a.x0 + (double)px, X1 = a.x0 + (double)(px + 1);
 
-        // ---- stage the candidate list, clear the accumulator table
+        // ---- stage the candidate list
         {
             const int off = a.list_off[tile];
             for (int i = tid; i < cnt; i += TESS_MAIN_THREADS) {
@@ -396,10 +385,6 @@ k_image_main(TessImgArgs a) {
                 s_gid[i] = gid;
                 s_g[i] = make_double2(a.node[2 * (long)gid], a.node[2 * (long)gid + 1]);
                 if (HAS_SCALE) s_inv[i] = a.inv_s2[gid];
-            }
-            if (MODE != 0) {
-                const int na = min(cnt, TESS_ACC_CAP(NV)) * (NV + 1);
-                for (int i = tid; i < na; i += TESS_MAIN_THREADS) s_acc[i] = 0.0;
             }
         }
         __syncthreads();
@@ -409,15 +394,21 @@ k_image_main(TessImgArgs a) {
         bool q_ident = true;       // true: the quadrant list is the staged list itself
         if (q_in && cnt > 1) {
             const double hx = 0.5 * (double)(qx1 - qx0), hy = 0.5 * (double)(qy1 - qy0);
-            const int n = tess_filter<32, HAS_SCALE, false>(s_g, s_inv, nullptr, true, cnt, cnt, a.x0 + 0.5 * (double)(qx0 + qx1),
-                                                            a.y0 + 0.5 * (double)(qy0 + qy1),
-                                                            sqrt(hx * hx + hy * hy) * 1.0000001, true, lane, ql, nullptr,
-                                                            nullptr, TESS_QCAP);
+            const int n = tess_filter<32, HAS_SCALE, true, false>(
+                s_g, s_inv, s_gid, nullptr, true, nullptr, true, cnt, cnt, a.x0 + 0.5 * (double)(qx0 + qx1),
+                a.y0 + 0.5 * (double)(qy0 + qy1), sqrt(hx * hx + hy * hy) * 1.0000001, true, lane, ql, s_qgid[wib],
+                nullptr, nullptr, TESS_QCAP);
             if (n <= TESS_QCAP) { c_q = n; q_ident = false; }
         }
+        const int* const gidv = q_ident ? s_gid : s_qgid[wib];    // quadrant-list position -> generator index
+        if (MODE != 0 && q_in) {
+            const int na = min(c_q, TQ) * (NV + 1);
+            for (int i = lane; i < na; i += 32) tab[i] = 0.0;
+            __syncwarp();
+        }
 
-        const unsigned short* pl = ql;     // parent list of the leaf filter
-        bool p_ident = q_ident;
+        const unsigned short* pl = nullptr;   // parent list of the leaf filter (quadrant-list positions)
+        bool p_ident = true;
         int p_len = c_q;
 
         for (int step = 0; step < 4 && q_in; ++step) {
@@ -457,14 +448,14 @@ k_image_main(TessImgArgs a) {
 
             // ---- 16x16 block lists (every other step), only where the quadrant list is long
             if ((step & 1) == 0) {
-                pl = ql; p_ident = q_ident; p_len = c_q;
+                pl = nullptr; p_ident = true; p_len = c_q;
                 if (c_q > TESS_BLOCK_MIN) {
                     const long bx0 = qx0 + 16 * blk, bx1 = min(bx0 + 15, a.W - 1), by1 = min(wy0 + 15, a.H - 1);
                     const double hx = 0.5 * (double)(bx1 - bx0), hy = 0.5 * (double)(by1 - wy0);
-                    const int n = tess_filter<16, HAS_SCALE, false>(s_g, s_inv, ql, q_ident, c_q, c_q, a.x0 + 0.5 * (double)(bx0 + bx1),
-                                                                    a.y0 + 0.5 * (double)(wy0 + by1),
-                                                                    sqrt(hx * hx + hy * hy) * 1.0000001, bx0 < a.W, lane,
-                                                                    s_bl[wib][blk], nullptr, nullptr, TESS_BCAP);
+                    const int n = tess_filter<16, HAS_SCALE, false, false>(
+                        s_g, s_inv, s_gid, ql, q_ident, nullptr, true, c_q, c_q, a.x0 + 0.5 * (double)(bx0 + bx1),
+                        a.y0 + 0.5 * (double)(wy0 + by1), sqrt(hx * hx + hy * hy) * 1.0000001, bx0 < a.W, lane,
+                        s_bl[wib][blk], nullptr, nullptr, nullptr, TESS_BCAP);
                     // both blocks must fit for the (warp-uniform) parent switch
                     if (__all_sync(TESS_FULL, n <= TESS_BCAP)) { pl = s_bl[wib][blk]; p_ident = false; p_len = n; }
                 }
@@ -477,30 +468,30 @@ k_image_main(TessImgArgs a) {
             int len = 0;
             bool use_leaf = false;
             bool uniform = (c_q == 1);                     // the whole warp tile belongs to one bin
-            int usl = q_ident ? 0 : (int)ql[0];
+            int ukey = 0;
             if (!uniform) {
                 const int p_max = __reduce_max_sync(TESS_FULL, p_len);    // the two blocks' lists differ in length
                 if (p_max > TESS_LEAF_MIN) {
                     const long lx0 = qx0 + 8 * leaf;
                     const long lx1 = min(lx0 + 7, a.W - 1), ly1 = min(wy0 + 7, a.H - 1);
                     const double hx = 0.5 * (double)(lx1 - lx0), hy = 0.5 * (double)(ly1 - wy0);
-                    len = tess_filter<8, HAS_SCALE, true>(s_g, s_inv, pl, p_ident, p_len, p_max, a.x0 + 0.5 * (double)(lx0 + lx1),
-                                                          a.y0 + 0.5 * (double)(wy0 + ly1),
-                                                          sqrt(hx * hx + hy * hy) * 1.0000001, lx0 < a.W, lane, ls, lg, li,
-                                                          TESS_LEAF_CAP);
+                    len = tess_filter<8, HAS_SCALE, false, true>(
+                        s_g, s_inv, s_gid, ql, q_ident, pl, p_ident, p_len, p_max, a.x0 + 0.5 * (double)(lx0 + lx1),
+                        a.y0 + 0.5 * (double)(wy0 + ly1), sqrt(hx * hx + hy * hy) * 1.0000001, lx0 < a.W, lane, ls,
+                        nullptr, lg, li, TESS_LEAF_CAP);
                     use_leaf = (len <= TESS_LEAF_CAP);
                     // all (in-image) leaves ended with the same single candidate?
                     const int one = (len == 1) ? (int)ls[0] : ((lx0 < a.W) ? -1 : -3);
                     const int ref = __reduce_max_sync(TESS_FULL, one);
                     uniform = (ref >= 0) && __all_sync(TESS_FULL, one == ref || one == -3);
-                    usl = ref;
+                    ukey = ref;
                 }
             }
 
-            int bs[4][2];                                  // winning slot per pixel
+            int bs[4][2];                                  // winning quadrant-list position per pixel
             if (uniform) {
-                // ---- one bin for all 256 pixels: constant labels, patch sums in closed form
-                const int gid = s_gid[usl];
+                // ---- one bin for all 256 pixels: constant labels
+                const int gid = gidv[ukey];
                 if (interior) {
 #pragma unroll
                     for (int r = 0; r < 4; ++r) *reinterpret_cast<int2*>(labels + base0 + r * a.W) = make_int2(gid, gid);
@@ -511,9 +502,8 @@ k_image_main(TessImgArgs a) {
                         for (int c = 0; c < 2; ++c)
                             if ((py + r < a.H) && (px + c < a.W)) labels[base0 + r * a.W + c] = gid;
                 }
-                if (MODE == 0) continue;
 #pragma unroll
-                for (int r = 0; r < 4; ++r) { bs[r][0] = usl; bs[r][1] = usl; }
+                for (int r = 0; r < 4; ++r) { bs[r][0] = ukey; bs[r][1] = ukey; }
             } else {
                 // ---- evaluate the surviving candidates with the pinned formula (ascending index:
                 //      strict '<' keeps the lowest index on exact ties)
@@ -525,14 +515,15 @@ k_image_main(TessImgArgs a) {
                 const int n_ev = use_leaf ? len : p_len;
                 for (int j = 0; j < n_ev; ++j) {
                     double2 g;
-                    int sl;
+                    int e;
                     double inv = 1.0;
                     if (use_leaf) {
                         g = lg[j];
-                        sl = ls[j];
+                        e = ls[j];
                         if (HAS_SCALE) inv = li[j];
                     } else {
-                        sl = p_ident ? j : (int)pl[j];
+                        e = p_ident ? j : (int)pl[j];
+                        const int sl = q_ident ? e : (int)ql[e];
                         g = s_g[sl];
                         if (HAS_SCALE) inv = s_inv[sl];
                     }
@@ -544,27 +535,28 @@ k_image_main(TessImgArgs a) {
                         const double dyy = __dmul_rn(dy, dy);
                         double d0 = __dadd_rn(dxx0, dyy), d1 = __dadd_rn(dxx1, dyy);
                         if (HAS_SCALE) { d0 = __dmul_rn(d0, inv); d1 = __dmul_rn(d1, inv); }
-                        if (d0 < bd[r][0]) { bd[r][0] = d0; bs[r][0] = sl; }
-                        if (d1 < bd[r][1]) { bd[r][1] = d1; bs[r][1] = sl; }
+                        if (d0 < bd[r][0]) { bd[r][0] = d0; bs[r][0] = e; }
+                        if (d1 < bd[r][1]) { bd[r][1] = d1; bs[r][1] = e; }
                     }
                 }
+                __syncwarp();                              // the leaves' lists differ in length
                 // ---- labels out: 16 lanes x 8 B = one 128-byte line per row
                 if (interior) {
 #pragma unroll
                     for (int r = 0; r < 4; ++r)
-                        *reinterpret_cast<int2*>(labels + base0 + r * a.W) = make_int2(s_gid[bs[r][0]], s_gid[bs[r][1]]);
+                        *reinterpret_cast<int2*>(labels + base0 + r * a.W) = make_int2(gidv[bs[r][0]], gidv[bs[r][1]]);
                 } else {
 #pragma unroll
                     for (int r = 0; r < 4; ++r)
 #pragma unroll
                         for (int c = 0; c < 2; ++c)
-                            if ((py + r < a.H) && (px + c < a.W)) labels[base0 + r * a.W + c] = s_gid[bs[r][c]];
+                            if ((py + r < a.H) && (px + c < a.W)) labels[base0 + r * a.W + c] = gidv[bs[r][c]];
                 }
-                if (MODE == 0) continue;
             }
+            if (MODE == 0) continue;
 
             // ---- moments.  Weights first; masked pixels (non-finite weight, signal or noise; outside
-            //      the image) are marked consumed (slot -2).
+            //      the image) are marked consumed (key -2).
             double wv[4][2];
             bool clean = true;                             // no masked pixel in this patch
 #pragma unroll
@@ -584,11 +576,18 @@ k_image_main(TessImgArgs a) {
                     }
                     wv[r][c] = w;
                     clean = clean && ok;
-                    if (!ok) bs[r][c] = -2;
+                    bs[r][c] = ok ? bs[r][c] : -2;
                 }
             if (uniform && __all_sync(TESS_FULL, clean)) {
                 // closed form for a one-bin patch: sum w x = X0 col0 + X1 col1, sum w y = sum_r Y_r row_r
-                if (cur.slot != usl) tess_run_switch<NV>(cur, s_acc, s_gid, a.mom, usl);
+                const bool sw = (cur.key != ukey);
+                if (__any_sync(TESS_FULL, sw)) {
+                    tess_table_flush<NV>(sw && cur.n > 0, cur.key, cur.n, cur.v, tab, gidv, a.mom, lane);
+                    cur.key = ukey;
+                    cur.n = sw ? 0 : cur.n;
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) cur.v[i] = sw ? 0.0 : cur.v[i];
+                }
                 const double c0 = __dadd_rn(__dadd_rn(wv[0][0], wv[1][0]), __dadd_rn(wv[2][0], wv[3][0]));
                 const double c1 = __dadd_rn(__dadd_rn(wv[0][1], wv[1][1]), __dadd_rn(wv[2][1], wv[3][1]));
                 double sy = 0.0;
@@ -611,54 +610,60 @@ k_image_main(TessImgArgs a) {
                     cur.v[NV - 1] = __dadd_rn(cur.v[NV - 1], nn);
                 }
             } else {
-                // Rounds: a lane whose current run's bin is no longer among its unconsumed pixels ends
-                // that run (ONE code location for the whole warp) and starts the run of one of the
-                // remaining bins; then every lane folds all its pixels of its run's bin.
+                // Rounds (no lane-divergent branch): a lane whose run's bin is no longer among its
+                // unconsumed pixels ends the run and starts the run of one of the remaining bins;
+                // then every lane folds all its pixels of its run's bin.
                 for (;;) {
                     const int rest = max(max(max(bs[0][0], bs[0][1]), max(bs[1][0], bs[1][1])),
                                          max(max(bs[2][0], bs[2][1]), max(bs[3][0], bs[3][1])));
                     if (!__any_sync(TESS_FULL, rest >= 0)) break;
                     bool present = false;
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) present = present || (bs[r][0] == cur.slot) || (bs[r][1] == cur.slot);
-                    if (rest >= 0 && !present) tess_run_switch<NV>(cur, s_acc, s_gid, a.mom, rest);
+                    for (int r = 0; r < 4; ++r) present = present || (bs[r][0] == cur.key) || (bs[r][1] == cur.key);
+                    const bool sw = (rest >= 0) && !present;
+                    if (__any_sync(TESS_FULL, sw)) {
+                        tess_table_flush<NV>(sw && cur.n > 0, cur.key, cur.n, cur.v, tab, gidv, a.mom, lane);
+                        cur.key = sw ? rest : cur.key;
+                        cur.n = sw ? 0 : cur.n;
+#pragma unroll
+                        for (int i = 0; i < NV; ++i) cur.v[i] = sw ? 0.0 : cur.v[i];
+                    }
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
 #pragma unroll
                         for (int c = 0; c < 2; ++c) {
-                            if (bs[r][c] == cur.slot) {
-                                const double w = wv[r][c];
-                                cur.n += 1;
-                                cur.v[0] = __dadd_rn(cur.v[0], w);
-                                cur.v[1] = __dadd_rn(cur.v[1], __dmul_rn(w, c ? X1 : X0));
-                                cur.v[2] = __dadd_rn(cur.v[2], __dmul_rn(w, Y[r]));
-                                if (MODE == 2) {
-                                    cur.v[NV - 2] = __dadd_rn(cur.v[NV - 2], w_[r][c]);
-                                    cur.v[NV - 1] = __dadd_rn(cur.v[NV - 1], __dmul_rn(n_[r][c], n_[r][c]));
-                                }
-                                bs[r][c] = -2;
+                            const bool hit = (bs[r][c] == cur.key);
+                            const double w = hit ? wv[r][c] : 0.0;
+                            cur.n += hit ? 1 : 0;
+                            cur.v[0] = __dadd_rn(cur.v[0], w);
+                            cur.v[1] = __dadd_rn(cur.v[1], __dmul_rn(w, c ? X1 : X0));
+                            cur.v[2] = __dadd_rn(cur.v[2], __dmul_rn(w, Y[r]));
+                            if (MODE == 2) {
+                                cur.v[NV - 2] = __dadd_rn(cur.v[NV - 2], hit ? w_[r][c] : 0.0);
+                                const double nz = hit ? n_[r][c] : 0.0;
+                                cur.v[NV - 1] = __dadd_rn(cur.v[NV - 1], __dmul_rn(nz, nz));
                             }
+                            bs[r][c] = hit ? -2 : bs[r][c];
                         }
                     }
                 }
             }
         }   // steps
 
-        // ---- end of super-tile: retire the live runs (merged across the warp), then table -> global
-        if (MODE != 0) tess_warp_retire<NV>(cur, s_acc, s_gid, a.mom, lane);
-        __syncthreads();
-        if (MODE != 0) {
-            const int na = min(cnt, TESS_ACC_CAP(NV));
-            for (int sl = tid; sl < na; sl += TESS_MAIN_THREADS) {
-                const double* t = s_acc + sl * (NV + 1);
+        // ---- end of the quadrant: retire the live runs (merged across the warp), table -> global
+        if (MODE != 0 && q_in) {
+            tess_warp_retire<NV>(cur, tab, gidv, a.mom, lane);
+            const int na = min(c_q, TQ);
+            for (int e = lane; e < na; e += 32) {
+                const double* t = tab + e * (NV + 1);
                 if (t[0] != 0.0) {
-                    double* m = a.mom + (long)s_gid[sl] * (NV + 1);
+                    double* m = a.mom + (long)gidv[e] * (NV + 1);
 #pragma unroll
                     for (int i = 0; i <= NV; ++i) tess_gmem_add(m + i, t[i]);
                 }
             }
         }
-        __syncthreads();   // the table and the staged list are rewritten by the next tile
+        __syncthreads();   // the staged list is rewritten by the next tile
         tile = s_tile[(it + 1) & 1];
     }       // tiles
 }
