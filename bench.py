@@ -78,6 +78,8 @@ def host_signal_rows(N, r0, r1):
 
 # ------------------------------------------------------------------------------------ clocks
 class ClockSampler(object):
+    """Samples SM clock and throttle reasons of one GPU DURING the timed region: NVML in a thread
+    (every ~2 ms; the timed region is tens of milliseconds), nvidia-smi -lms as a fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -86,8 +88,48 @@ class ClockSampler(object):
         self.index = index
         self.f = None
         self.p = None
+        self.th = None
+        self.stop_flag = False
+        self.sm, self.mx, self.reasons, self.power = [], [], set(), []
+
+    def _nvml_loop(self):
+        import pynvml as nv
+        h = self.h
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = int(get_reasons(h))
+                for nm, b in bits.items():
+                    if r & b:
+                        self.reasons.add(nm)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates in PCI order; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis and all(x.strip().isdigit() for x in vis.split(",")):
+                idx = int(vis.split(",")[self.index])
+            self.h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = [float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))]
+            self.th = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.th = None
         try:
             self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
@@ -97,6 +139,13 @@ class ClockSampler(object):
             self.p = None
 
     def stop(self):
+        if self.th is not None:
+            self.stop_flag = True
+            self.th.join(1.0)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None,
+                    "sm_max_mhz": max(self.mx) if self.mx else None, "samples": len(self.sm),
+                    "power_w_max": max(self.power) if self.power else None, "reasons": sorted(self.reasons),
+                    "source": "nvml"}
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.05)
@@ -126,7 +175,7 @@ class ClockSampler(object):
         except OSError:
             pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
 def measured_peaks():

@@ -31,6 +31,9 @@ static long g_tess_launches = 0;   // kernels launched by the library (host-side
 #ifndef TESS_MAIN_MINBLOCKS
 #define TESS_MAIN_MINBLOCKS 4 // CTAs per SM the main kernel is compiled for (<= 128 registers)
 #endif
+#ifndef TESS_MAIN_MINBLOCKS_SN
+#define TESS_MAIN_MINBLOCKS_SN 3 // same for the signal/noise mode (two maps in flight: <= 168 registers)
+#endif
 #define TESS_FULL 0xffffffffu
 #define TESS_NAN (__longlong_as_double(0x7ff8000000000000LL))
 #define TESS_BRUTE (-1)       // list_cnt marker: list did not fit, scan every generator

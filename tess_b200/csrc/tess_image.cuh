@@ -317,9 +317,37 @@ TESS_DEVFN int tess_filter(const double2* s_g, const double* s_inv, const int* s
     return n;
 }
 
+// Loads the lane's 2x4 pixel patch whose first pixel is (px, py): weight (MODE 1) or signal and
+// noise (MODE 2).  Interior tiles: four 128-bit loads; else guarded scalar loads, NaN outside.
+template <int MODE, bool VEC>
+TESS_DEVFN void tess_load_patch(const TessImgArgs& a, const double* src, bool interior, long px, long py,
+                                double (&w)[4][2], double (&nz)[4][2]) {
+    const long base0 = py * a.W + px;
+    if (interior) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const double2 v = *reinterpret_cast<const double2*>(src + base0 + r * a.W);
+            w[r][0] = v.x; w[r][1] = v.y;
+            if (MODE == 2) {
+                const double2 u = *reinterpret_cast<const double2*>(a.noise + base0 + r * a.W);
+                nz[r][0] = u.x; nz[r][1] = u.y;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const bool in = (py + r < a.H) && (px + c < a.W);
+                w[r][c] = in ? src[base0 + r * a.W + c] : TESS_NAN;
+                if (MODE == 2) nz[r][c] = in ? a.noise[base0 + r * a.W + c] : TESS_NAN;
+            }
+    }
+}
+
 // MODE 0: labels only; 1: density map (4 moments); 2: signal + noise maps (6 moments)
 template <int MODE, bool HAS_SCALE, bool VEC>
-__global__ void __launch_bounds__(TESS_MAIN_THREADS, TESS_MAIN_MINBLOCKS)
+__global__ void __launch_bounds__(TESS_MAIN_THREADS, (MODE == 2) ? TESS_MAIN_MINBLOCKS_SN : TESS_MAIN_MINBLOCKS)
 k_image_main(TessImgArgs a) {
     constexpr int NV = (MODE == 2) ? 5 : 3;
     constexpr int NW = TESS_MAIN_THREADS / 32;
@@ -389,14 +417,19 @@ k_image_main(TessImgArgs a) {
         }
         __syncthreads();
 
+        // ---- request the pixels of the first warp tile (consumed after the list work below)
+        double wn_[4][2], nn_[4][2];
+        if (MODE != 0 && q_in) tess_load_patch<MODE, VEC>(a, src, interior, px, qy0 + 4 * ry, wn_, nn_);
+
         // ---- quadrant list: staged list -> slots that can win somewhere in the 32x32 quadrant
         int c_q = cnt;
         bool q_ident = true;       // true: the quadrant list is the staged list itself
         if (q_in && cnt > 1) {
             const double hx = 0.5 * (double)(qx1 - qx0), hy = 0.5 * (double)(qy1 - qy0);
+            const double rho = interior ? 21.920310216783 : sqrt(hx * hx + hy * hy) * 1.0000001;   // 15.5 sqrt 2
             const int n = tess_filter<32, HAS_SCALE, true, false>(
                 s_g, s_inv, s_gid, nullptr, true, nullptr, true, cnt, cnt, a.x0 + 0.5 * (double)(qx0 + qx1),
-                a.y0 + 0.5 * (double)(qy0 + qy1), sqrt(hx * hx + hy * hy) * 1.0000001, true, lane, ql, s_qgid[wib],
+                a.y0 + 0.5 * (double)(qy0 + qy1), rho, true, lane, ql, s_qgid[wib],
                 nullptr, nullptr, TESS_QCAP);
             if (n <= TESS_QCAP) { c_q = n; q_ident = false; }
         }
@@ -420,30 +453,16 @@ k_image_main(TessImgArgs a) {
 #pragma unroll
             for (int r = 0; r < 4; ++r) Y[r] = a.y0 + (double)(py + r);
 
-            // ---- issue the pixel loads early; they are consumed after the candidate evaluation.
+            // ---- pixel data of this warp tile was requested one warp tile ahead (software pipeline:
+            //      the loads of warp tile s+1 are in flight while warp tile s is processed).
             //      Pixels outside the image read as NaN and drop out with the masked ones.
             double w_[4][2], n_[4][2];                     // MODE 1: weight; MODE 2: signal, noise
             if (MODE != 0) {
-                if (interior) {
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const double2 v = *reinterpret_cast<const double2*>(src + base0 + r * a.W);
-                        w_[r][0] = v.x; w_[r][1] = v.y;
-                        if (MODE == 2) {
-                            const double2 u = *reinterpret_cast<const double2*>(a.noise + base0 + r * a.W);
-                            n_[r][0] = u.x; n_[r][1] = u.y;
-                        }
-                    }
-                } else {
+                for (int r = 0; r < 4; ++r)
 #pragma unroll
-                    for (int r = 0; r < 4; ++r)
-#pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            const bool in = (py + r < a.H) && (px + c < a.W);
-                            w_[r][c] = in ? src[base0 + r * a.W + c] : TESS_NAN;
-                            if (MODE == 2) n_[r][c] = in ? a.noise[base0 + r * a.W + c] : TESS_NAN;
-                        }
-                }
+                    for (int c = 0; c < 2; ++c) { w_[r][c] = wn_[r][c]; if (MODE == 2) n_[r][c] = nn_[r][c]; }
+                if (step < 3 && wy0 + 8 < a.H) tess_load_patch<MODE, VEC>(a, src, interior, px, py + 8, wn_, nn_);
             }
 
             // ---- 16x16 block lists (every other step), only where the quadrant list is long
@@ -452,9 +471,10 @@ k_image_main(TessImgArgs a) {
                 if (c_q > TESS_BLOCK_MIN) {
                     const long bx0 = qx0 + 16 * blk, bx1 = min(bx0 + 15, a.W - 1), by1 = min(wy0 + 15, a.H - 1);
                     const double hx = 0.5 * (double)(bx1 - bx0), hy = 0.5 * (double)(by1 - wy0);
+                    const double rho = interior ? 10.606602778 : sqrt(hx * hx + hy * hy) * 1.0000001;   // 7.5 sqrt 2
                     const int n = tess_filter<16, HAS_SCALE, false, false>(
                         s_g, s_inv, s_gid, ql, q_ident, nullptr, true, c_q, c_q, a.x0 + 0.5 * (double)(bx0 + bx1),
-                        a.y0 + 0.5 * (double)(wy0 + by1), sqrt(hx * hx + hy * hy) * 1.0000001, bx0 < a.W, lane,
+                        a.y0 + 0.5 * (double)(wy0 + by1), rho, bx0 < a.W, lane,
                         s_bl[wib][blk], nullptr, nullptr, nullptr, TESS_BCAP);
                     // both blocks must fit for the (warp-uniform) parent switch
                     if (__all_sync(TESS_FULL, n <= TESS_BCAP)) { pl = s_bl[wib][blk]; p_ident = false; p_len = n; }
@@ -475,9 +495,10 @@ k_image_main(TessImgArgs a) {
                     const long lx0 = qx0 + 8 * leaf;
                     const long lx1 = min(lx0 + 7, a.W - 1), ly1 = min(wy0 + 7, a.H - 1);
                     const double hx = 0.5 * (double)(lx1 - lx0), hy = 0.5 * (double)(ly1 - wy0);
+                    const double rho = interior ? 4.9497479632 : sqrt(hx * hx + hy * hy) * 1.0000001;   // 3.5 sqrt 2
                     len = tess_filter<8, HAS_SCALE, false, true>(
                         s_g, s_inv, s_gid, ql, q_ident, pl, p_ident, p_len, p_max, a.x0 + 0.5 * (double)(lx0 + lx1),
-                        a.y0 + 0.5 * (double)(wy0 + ly1), sqrt(hx * hx + hy * hy) * 1.0000001, lx0 < a.W, lane, ls,
+                        a.y0 + 0.5 * (double)(wy0 + ly1), rho, lx0 < a.W, lane, ls,
                         nullptr, lg, li, TESS_LEAF_CAP);
                     use_leaf = (len <= TESS_LEAF_CAP);
                     // all (in-image) leaves ended with the same single candidate?

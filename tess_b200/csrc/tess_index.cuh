@@ -30,33 +30,54 @@ k_cell_count(const TessState* st, int honor, TessGrid g, const double* node, int
     }
 }
 
-// Exclusive scan of cell_cnt[0..n_cells) -> cell_start[0..n_cells] (single CTA, 1024 threads).
+// Exclusive scan of cell_cnt[0..n_cells) -> cell_start[0..n_cells] (single CTA, 1024 threads):
+// 16 consecutive cells per thread in registers, warp-shuffle scans, one carry per 16384 cells.
 // Thread 0 also resets the per-iteration scalars of the state block.
+#define TESS_SCAN_ITEMS 16
 __global__ void __launch_bounds__(1024)
 k_cell_scan(TessState* st, int honor, const int* cell_cnt, int* cell_start, int n_cells) {
     if (TESS_STOPPED(st, honor)) return;
-    __shared__ int s_part[1024];
-    const int t = threadIdx.x, nt = blockDim.x;
-    const int per = (n_cells + nt - 1) / nt;
-    const int b = min(t * per, n_cells), e = min(b + per, n_cells);
-    int sum = 0;
-    for (int i = b; i < e; ++i) sum += cell_cnt[i];
-    s_part[t] = sum;
-    __syncthreads();
-    // Hillis-Steele inclusive scan over the nt partial sums
-    for (int off = 1; off < nt; off <<= 1) {
-        int v = (t >= off) ? s_part[t - off] : 0;
+    __shared__ int s_w[32];
+    __shared__ int s_tot;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    int carry = 0;
+    for (int base = 0; base < n_cells; base += 1024 * TESS_SCAN_ITEMS) {
+        const int i0 = base + t * TESS_SCAN_ITEMS;
+        int v[TESS_SCAN_ITEMS];
+#pragma unroll
+        for (int j = 0; j < TESS_SCAN_ITEMS; ++j) v[j] = (i0 + j < n_cells) ? cell_cnt[i0 + j] : 0;
+        int tot = 0;
+#pragma unroll
+        for (int j = 0; j < TESS_SCAN_ITEMS; ++j) { const int x = v[j]; v[j] = tot; tot += x; }   // local exclusive
+        int inc = tot;                                                                           // warp inclusive
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(TESS_FULL, inc, d);
+            if (lane >= d) inc += y;
+        }
+        if (lane == 31) s_w[w] = inc;
         __syncthreads();
-        s_part[t] += v;
+        if (w == 0) {
+            const int x = s_w[lane];
+            int wi = x;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int y = __shfl_up_sync(TESS_FULL, wi, d);
+                if (lane >= d) wi += y;
+            }
+            s_w[lane] = wi - x;                      // exclusive prefix of the warp totals
+            if (lane == 31) s_tot = wi;
+        }
+        __syncthreads();
+        const int off = carry + s_w[w] + (inc - tot);
+#pragma unroll
+        for (int j = 0; j < TESS_SCAN_ITEMS; ++j)
+            if (i0 + j < n_cells) cell_start[i0 + j] = off + v[j];
+        carry += s_tot;
         __syncthreads();
     }
-    int run = s_part[t] - sum;   // exclusive prefix of this thread's chunk
-    for (int i = b; i < e; ++i) {
-        cell_start[i] = run;
-        run += cell_cnt[i];
-    }
-    if (t == nt - 1) cell_start[n_cells] = s_part[t];
     if (t == 0) {
+        cell_start[n_cells] = carry;
         if (honor) {   // part of a Lloyd iteration (not a stand-alone assignment query)
             st->delta = 0.0;
             st->n_changed = 0ull;
