@@ -3,7 +3,7 @@
 //
 // One Lloyd iteration (reference tess/lloyd.pyx:47-90) is the launch sequence
 //   k_cell_count -> k_cell_scan -> k_cell_scatter        generator grid (replaces cKDTree build, :54)
-//   k_build_lists                                        per-tile candidate lists
+//   k_build_qlists                                       per-quadrant candidate lists (sorted, in an arena)
 //   k_image_main | k_points_main                         assignment (:55) fused with the sums (:58-65)
 //   k_count_prefilter -> k_compare_labels                "did any label change" (convergence, :85)
 //   [multi-GPU: the host all-reduces the moment vector here]
@@ -75,9 +75,9 @@ struct tess_ctx {
     double2* cell_xy;
     double* cell_inv;
     long cells_cap;
-    int *list_off, *list_cnt, *list_items;
-    long tiles_cap;
-    unsigned list_cap;
+    TessQLists ql;      // per-quadrant candidate lists (arena)
+    long quads_cap;
+    int arena_has_inv;
     int32_t* lab[2];
     long lab_cap;
     double* mom;
@@ -139,7 +139,7 @@ extern "C" int tess_ctx_destroy(tess_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     void* ptrs[] = {c->node, c->scale, c->inv_s2, c->st, c->cell_cnt, c->cell_start, c->cell_of, c->cell_items,
-                    c->cell_xy, c->cell_inv, c->list_off, c->list_cnt, c->list_items, c->lab[0], c->lab[1],
+                    c->cell_xy, c->cell_inv, c->ql.q_off, c->ql.q_cnt, c->ql.xy, c->ql.gid, c->ql.inv, c->lab[0], c->lab[1],
                     c->mom, c->prev_count, c->scratch};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -369,26 +369,39 @@ static int ensure_cells(tess_ctx* c, int n_cells) {
     return TESS_OK;
 }
 
-static int ensure_lists(tess_ctx* c, int n_tiles) {
-    if (n_tiles > c->tiles_cap) {
-        if (c->list_off) cudaFree(c->list_off);
-        if (c->list_cnt) cudaFree(c->list_cnt);
-        c->list_off = c->list_cnt = nullptr;
-        c->tiles_cap = 0;
-        CU_TRY(cudaMalloc((void**)&c->list_off, sizeof(int) * (size_t)n_tiles));
-        CU_TRY(cudaMalloc((void**)&c->list_cnt, sizeof(int) * (size_t)n_tiles));
-        c->tiles_cap = n_tiles;
+static int ensure_lists(tess_ctx* c, const TessTiles& T) {
+    const int nqx = 2 * T.tiles_x, nqy = 2 * T.tiles_y;
+    const long nq = (long)nqx * nqy;
+    if (nq > c->quads_cap) {
+        if (c->ql.q_off) cudaFree(c->ql.q_off);
+        if (c->ql.q_cnt) cudaFree(c->ql.q_cnt);
+        c->ql.q_off = c->ql.q_cnt = nullptr;
+        c->quads_cap = 0;
+        CU_TRY(cudaMalloc((void**)&c->ql.q_off, sizeof(int) * (size_t)nq));
+        CU_TRY(cudaMalloc((void**)&c->ql.q_cnt, sizeof(int) * (size_t)nq));
+        c->quads_cap = nq;
     }
-    // arena: a generator is listed by every tile it can win in -- its own bin plus a margin
-    double want = 128.0 * (double)n_tiles + 32.0 * (double)c->k + 65536.0;
+    // arena: a generator is listed by every quadrant it can win in -- its own bin plus a margin
+    double want = 32.0 * (double)nq + 48.0 * (double)c->k + 65536.0;
     if (want > 2.0e9) want = 2.0e9;
-    if ((unsigned)want > c->list_cap) {
-        if (c->list_items) cudaFree(c->list_items);
-        c->list_items = nullptr;
-        c->list_cap = 0;
-        CU_TRY(cudaMalloc((void**)&c->list_items, sizeof(int) * (size_t)want));
-        c->list_cap = (unsigned)want;
+    if ((unsigned)want > c->ql.capacity || (c->has_scale && !c->arena_has_inv)) {
+        if (c->ql.xy) cudaFree(c->ql.xy);
+        if (c->ql.gid) cudaFree(c->ql.gid);
+        if (c->ql.inv) cudaFree(c->ql.inv);
+        c->ql.xy = nullptr; c->ql.gid = nullptr; c->ql.inv = nullptr;
+        c->ql.capacity = 0;
+        c->arena_has_inv = 0;
+        if ((double)c->ql.capacity > want) want = (double)c->ql.capacity;
+        CU_TRY(cudaMalloc((void**)&c->ql.xy, sizeof(double2) * (size_t)want));
+        CU_TRY(cudaMalloc((void**)&c->ql.gid, sizeof(int) * (size_t)want));
+        if (c->has_scale) {
+            CU_TRY(cudaMalloc((void**)&c->ql.inv, sizeof(double) * (size_t)want));
+            c->arena_has_inv = 1;
+        }
+        c->ql.capacity = (unsigned)want;
     }
+    c->ql.nqx = nqx;
+    c->ql.nqy = nqy;
     return TESS_OK;
 }
 
@@ -421,17 +434,15 @@ static int build_index(tess_ctx* c, const Geometry& q, int honor, double* mom, l
 }
 
 static int build_lists(tess_ctx* c, const Geometry& q, int honor, cudaStream_t s) {
-    TRY(ensure_lists(c, q.T.n_tiles));
+    TRY(ensure_lists(c, q.T));
     int grid = (q.T.n_tiles + TESS_LIST_WARPS - 1) / TESS_LIST_WARPS;
-    if (grid > c->sm_count * 16) grid = c->sm_count * 16;
+    if (grid > c->sm_count * 32) grid = c->sm_count * 32;
     if (c->has_scale)
-        TESS_LAUNCH((k_build_lists<true>), grid, TESS_LIST_WARPS * 32, s, c->st, honor, q.T, q.g, c->cell_start, c->cell_items,
-                                                                c->cell_xy, c->cell_inv, c->list_off, c->list_cnt,
-                                                                c->list_items, c->list_cap);
+        TESS_LAUNCH((k_build_qlists<true>), grid, TESS_LIST_WARPS * 32, s, c->st, honor, q.T, q.g, c->cell_start,
+                    c->cell_items, c->cell_xy, c->cell_inv, c->ql);
     else
-        TESS_LAUNCH((k_build_lists<false>), grid, TESS_LIST_WARPS * 32, s, c->st, honor, q.T, q.g, c->cell_start, c->cell_items,
-                                                                 c->cell_xy, c->cell_inv, c->list_off, c->list_cnt,
-                                                                 c->list_items, c->list_cap);
+        TESS_LAUNCH((k_build_qlists<false>), grid, TESS_LIST_WARPS * 32, s, c->st, honor, q.T, q.g, c->cell_start,
+                    c->cell_items, c->cell_xy, c->cell_inv, c->ql);
     CU_TRY(cudaGetLastError());
     return TESS_OK;
 }
@@ -455,10 +466,9 @@ static int run_image(tess_ctx* c, const Geometry& q, int mode, int honor, int32_
     a.dens = c->dens; a.sig = c->sig; a.noise = c->noise;
     a.labels_ext = labels_ext; a.lab0 = c->lab[0]; a.lab1 = c->lab[1];
     a.mom = c->mom; a.node = c->node; a.inv_s2 = c->inv_s2;
-    a.list_off = c->list_off; a.list_cnt = c->list_cnt; a.list_items = c->list_items;
+    a.L = c->ql;
     a.st = c->st;
     a.H = q.T.H; a.W = q.T.W; a.x0 = q.T.x0; a.y0 = q.T.y0;
-    a.tiles_x = q.T.tiles_x; a.tiles_y = q.T.tiles_y;
     a.k = c->k;
     a.uniform_weight = c->uniform_weight;
     a.honor = honor;
@@ -466,8 +476,12 @@ static int run_image(tess_ctx* c, const Geometry& q, int mode, int honor, int32_
     if (labels_ext) vec = vec && (((uintptr_t)labels_ext & 7u) == 0);
     if (mode == 1) vec = vec && aligned16(c->dens);
     if (mode == 2) vec = vec && aligned16(c->sig) && aligned16(c->noise);
-    int grid = q.T.n_tiles;
-    if (grid > c->sm_count * 8) grid = c->sm_count * 8;
+    // one warp per quadrant, strided: enough CTAs to fill every SM at the compiled occupancy
+    const long nq = (long)c->ql.nqx * c->ql.nqy;
+    const int nw = TESS_MAIN_THREADS / 32;
+    long want = (nq + nw - 1) / nw;
+    int grid = (int)(want < (long)c->sm_count * 16 ? want : (long)c->sm_count * 16);
+    if (grid < 1) grid = 1;
     if (mode == 0) launch_image<0>(c, a, vec, grid, s);
     else if (mode == 1) launch_image<1>(c, a, vec, grid, s);
     else launch_image<2>(c, a, vec, grid, s);

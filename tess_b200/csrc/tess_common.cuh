@@ -27,12 +27,12 @@ static long g_tess_launches = 0;   // kernels launched by the library (host-side
 #define TESS_WT_H 8           // warp-tile height, px
 #define TESS_CAP 512           // candidates of one tile staged in shared memory
 #define TESS_LEAF_CAP 24      // candidates of one 8x8 leaf
-#define TESS_MAIN_THREADS 128 // image main kernel: 4 warps
+#define TESS_MAIN_THREADS 64  // image main kernel: 2 independent warps per CTA
 #ifndef TESS_MAIN_MINBLOCKS
-#define TESS_MAIN_MINBLOCKS 4 // CTAs per SM the main kernel is compiled for (<= 128 registers)
+#define TESS_MAIN_MINBLOCKS 8 // CTAs per SM the main kernel is compiled for (<= 128 registers)
 #endif
 #ifndef TESS_MAIN_MINBLOCKS_SN
-#define TESS_MAIN_MINBLOCKS_SN 3 // same for the signal/noise mode (two maps in flight: <= 168 registers)
+#define TESS_MAIN_MINBLOCKS_SN 6 // same for the signal/noise mode (two maps in flight: <= 168 registers)
 #endif
 #define TESS_FULL 0xffffffffu
 #define TESS_NAN (__longlong_as_double(0x7ff8000000000000LL))

@@ -5,36 +5,37 @@
 // CVTessellation.from_image builds (tess/voronoi.py:281-287); in MODE 0 it is the nearest-
 // generator rasterisation behind VoronoiTessellation.segmap (tess/voronoi.py:75-114).
 //
-// One persistent CTA (4 warps) pulls 64x64 super-tiles from a dynamic counter.  Per super-tile the
-// candidate list (k_build_lists, sorted by generator index) is staged in shared memory.  Each warp
-// owns a 32x32 quadrant: it narrows the list once for the quadrant, once more per 16x16 block where
-// the list is long, and for each of its four 32x8 warp tiles once per 8x8 leaf (8 lanes per leaf),
-// always with the centre + radius test
+// Work unit: one WARP per 32x32-px quadrant, warps fully independent (no CTA barrier anywhere).
+// The quadrant's candidate list (k_build_qlists: arena records in ascending generator index) is
+// copied into the warp's shared-memory buffer with cp.async one quadrant AHEAD, so list latency is
+// hidden behind the previous quadrant's arithmetic; pixel data is requested one warp tile ahead.
+// For each of its four 32x8 warp tiles the warp narrows the list per 16x16 block (long lists only)
+// and per 8x8 leaf (8 lanes per leaf) with the centre + radius test
 //     keep g  iff  u(c,g) <= min_h u(c,h) + 2 rho / s_min        (u = distance / scale)
-// which can never drop the true nearest generator of any pixel of the rectangle.  The survivors are
-// evaluated with the pinned fp64 formula; lists are in ascending generator index, so a strict '<'
-// implements the lowest-index tie rule.  Labels leave as one coalesced 128-byte line per row.
+// which can never drop the true nearest generator of any pixel of the rectangle, evaluates the
+// survivors with the pinned fp64 formula (ascending generator index + strict '<' = lowest index wins
+// an exact tie) and writes labels as one coalesced 128-byte line per row.
 //
 // Moments ("segmented reduction"): every lane owns a 2-column x 4-row pixel patch per warp tile and
-// keeps ONE running same-bin sum in registers across the warp tiles of a quadrant (labels are
+// keeps ONE running same-bin sum in registers across the warp tiles of the quadrant (labels are
 // spatially coherent, so most patches extend the current run).  When a lane's run ends, its sums go
 // to the warp's shared-memory table of per-candidate accumulators; lanes that retire the same bin in
 // the same round are serialised with match.any (warp-level aggregation, no atomics: the table is
 // private to the warp).  At the end of the quadrant the live runs are merged across the warp with
-// shuffles, and the table goes to the global moment vector -- one fp64 reduction per
-// (quadrant, bin, moment).  The whole fold is written without lane-divergent branches.
+// shuffles and the table goes to the global moment vector -- one fp64 reduction per
+// (quadrant, bin, moment).  The fold is written without lane-divergent branches.
 //
 // Algorithmic HBM traffic per pixel: MODE 1: 8 B (density) + 4 B (label) = 12 B;
 // MODE 2: 8 + 8 B (signal, noise) + 4 B = 20 B; MODE 0: 4 B.  Pixel coordinates are implicit.
 #pragma once
 #include "tess_common.cuh"
+#include "tess_index.cuh"
 
-#define TESS_QCAP 128       // quadrant list capacity (else the staged list is used as is)
 #define TESS_BCAP 64        // 16x16 block list capacity
 #define TESS_BLOCK_MIN 20   // quadrant lists longer than this get the intermediate 16x16 level
 #define TESS_LEAF_MIN 3     // parent lists up to this length are evaluated without a leaf filter
-// entries of a warp's accumulator table (quadrant-list positions beyond it go straight to global)
-#define TESS_TQ(NV) ((NV) > 3 ? 96 : 128)
+// quadrant list capacity of the fast path = entries of a warp's accumulator table
+#define TESS_QCAP(MODE) ((MODE) == 2 ? 96 : 128)
 
 struct TessImgArgs {
     const double* dens;    // MODE 1: [H][W] weights
@@ -46,13 +47,10 @@ struct TessImgArgs {
     double* mom;           // [k][M] global moment table (M = 4 or 6)
     const double* node;    // [k][2]
     const double* inv_s2;  // [k] or null
-    const int* list_off;
-    const int* list_cnt;
-    const int* list_items;
+    TessQLists L;          // per-quadrant candidate lists
     TessState* st;
     long H, W;
     double x0, y0;
-    int tiles_x, tiles_y;
     int k;
     int uniform_weight;    // MODE 2: w = 1 instead of (S/N)^2
     int honor;             // honour the convergence latch (iteration kernels) or not (segmap)
@@ -75,27 +73,47 @@ TESS_DEVFN void tess_gmem_add(double* p, double v) {
 #endif
 }
 
+// 16 / 8 / 4-byte asynchronous global -> shared copies (LDGSTS); plain copies under the emulator
+TESS_DEVFN void tess_cp_async16(void* dst, const void* src) {
+#ifndef TESS_EMU
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+#else
+    memcpy(dst, src, 16);
+#endif
+}
+TESS_DEVFN void tess_cp_async8(void* dst, const void* src) {
+#ifndef TESS_EMU
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+#else
+    memcpy(dst, src, 8);
+#endif
+}
+TESS_DEVFN void tess_cp_async4(void* dst, const void* src) {
+#ifndef TESS_EMU
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+#else
+    memcpy(dst, src, 4);
+#endif
+}
+TESS_DEVFN void tess_cp_async_wait() {
+#ifndef TESS_EMU
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+
 // Lanes with `flush` set add their run (key, n, v) to the warp's table.  Lanes holding the same key
 // take turns (match.any elects one lane per distinct key per turn), so plain read-modify-writes are
-// enough.  Keys beyond the table go to the global vector.  All 32 lanes must call; no divergence.
+// enough.  All 32 lanes must call; no divergence.
 template <int NV>
-TESS_DEVFN void tess_table_flush(bool flush, int key, int n, const double (&v)[NV], double* tab, const int* gidv,
-                                 double* mom, int lane) {
+TESS_DEVFN void tess_table_flush(bool flush, int key, int n, const double (&v)[NV], double* tab, int lane) {
     bool pending = flush;
     while (__any_sync(TESS_FULL, pending)) {
         const unsigned grp = __match_any_sync(TESS_FULL, pending ? key : -1 - lane);
         if (pending && lane == __ffs((int)grp) - 1) {
-            if (key < TESS_TQ(NV)) {
-                double* t = tab + key * (NV + 1);
-                t[0] += (double)n;
+            double* t = tab + key * (NV + 1);
+            t[0] += (double)n;
 #pragma unroll
-                for (int i = 0; i < NV; ++i) t[1 + i] = __dadd_rn(t[1 + i], v[i]);
-            } else {
-                double* m = mom + (long)gidv[key] * (NV + 1);
-                tess_gmem_add(m, (double)n);
-#pragma unroll
-                for (int i = 0; i < NV; ++i) tess_gmem_add(m + 1 + i, v[i]);
-            }
+            for (int i = 0; i < NV; ++i) t[1 + i] = __dadd_rn(t[1 + i], v[i]);
             pending = false;
         }
         __syncwarp();
@@ -105,7 +123,7 @@ TESS_DEVFN void tess_table_flush(bool flush, int key, int n, const double (&v)[N
 // End of a quadrant: every lane retires its live run.  Lanes that hold the same bin are merged with
 // shuffles first, so the table receives one add per bin.
 template <int NV>
-TESS_DEVFN void tess_warp_retire(TessRun<NV>& cur, double* tab, const int* gidv, double* mom, int lane) {
+TESS_DEVFN void tess_warp_retire(TessRun<NV>& cur, double* tab, int lane) {
     unsigned todo = __ballot_sync(TESS_FULL, cur.n > 0);
     while (todo) {
         const int leader = __ffs((int)todo) - 1;
@@ -125,17 +143,10 @@ TESS_DEVFN void tess_warp_retire(TessRun<NV>& cur, double* tab, const int* gidv,
             }
         }
         if (lane == leader) {
-            if (key < TESS_TQ(NV)) {
-                double* t = tab + key * (NV + 1);
-                t[0] += (double)n;
+            double* t = tab + key * (NV + 1);
+            t[0] += (double)n;
 #pragma unroll
-                for (int i = 0; i < NV; ++i) t[1 + i] = __dadd_rn(t[1 + i], s[i]);
-            } else {
-                double* m = mom + (long)gidv[key] * (NV + 1);
-                tess_gmem_add(m, (double)n);
-#pragma unroll
-                for (int i = 0; i < NV; ++i) tess_gmem_add(m + 1 + i, s[i]);
-            }
+            for (int i = 0; i < NV; ++i) t[1 + i] = __dadd_rn(t[1 + i], s[i]);
         }
         todo &= ~grp;
     }
@@ -156,50 +167,45 @@ TESS_DEVFN double tess_center_thr(double umin, double c) {
     return (umin + 2.0 * c * tess_sqrt_up(umin) + c * c) * TESS_SLACK;
 }
 
-// Exhaustive fallback for a super-tile whose candidate list did not fit (more than TESS_CAP
-// generators can win inside 64x64 pixels, e.g. "every point is its own generator"): the CTA scans
-// the whole generator table for each pixel and sends the moments straight to the global vector.
-// Correct but slow; kept out of line so that it does not bloat the hot loop.
+// Slow path for a quadrant whose candidate list does not fit the fast path: every pixel scans the
+// whole list (n records at gxy / gids / ginv in GLOBAL memory; gids == null: record j is generator
+// j, i.e. the complete generator table) and sends its moments straight to the global vector.
+// Correct for any density, but slow; kept out of line so that it does not bloat the hot loop.
 template <int MODE, bool HAS_SCALE>
-TESS_NOINLINE void tess_tile_brute(const TessImgArgs& a, int32_t* labels, int tx, int ty, double2* s_g, double* s_inv) {
+TESS_NOINLINE void tess_quadrant_scan(const TessImgArgs& a, int32_t* labels, long qx0, long qy0, const double2* gxy,
+                                      const int* gids, const double* ginv, int n) {
     constexpr int NV = (MODE == 2) ? 5 : 3;
-    const int tid = threadIdx.x;
-    const long bx = (long)tx * TESS_TS, by = (long)ty * TESS_TS;
-    for (int half = 0; half < TESS_TS * TESS_TS; half += 8 * TESS_MAIN_THREADS) {
-        // each thread owns 8 pixels of this slice: p = half + j*THREADS + tid
+    const int lane = threadIdx.x & 31;
+    // lane -> column qx0 + lane, all 32 rows in four passes of 8 rows
+    const long c = qx0 + lane;
+    const double X = a.x0 + (double)c;
+    for (int r0 = 0; r0 < 32; r0 += 8) {
         double bd[8];
         int bi[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) { bd[j] = INFINITY; bi[j] = 0; }
-        for (int g0 = 0; g0 < a.k; g0 += TESS_CAP) {
-            const int cnt = min(TESS_CAP, a.k - g0);
-            __syncthreads();
-            for (int i = tid; i < cnt; i += TESS_MAIN_THREADS) {
-                s_g[i] = make_double2(a.node[2 * (long)(g0 + i)], a.node[2 * (long)(g0 + i) + 1]);
-                if (HAS_SCALE) s_inv[i] = a.inv_s2[g0 + i];
-            }
-            __syncthreads();
-            for (int i = 0; i < cnt; ++i) {
-                const double2 g = s_g[i];
+        for (int i = 0; i < n; ++i) {
+            const double2 g = gxy[i];
+            const double iv = HAS_SCALE ? ginv[i] : 1.0;
+            const int gid = gids ? gids[i] : i;
+            const double dx = __dsub_rn(X, g.x);
+            const double dxx = __dmul_rn(dx, dx);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int p = half + j * TESS_MAIN_THREADS + tid;
-                    const double X = a.x0 + (double)(bx + (p & (TESS_TS - 1))), Y = a.y0 + (double)(by + (p >> 6));
-                    double d = tess_d2_pinned(X, Y, g.x, g.y);
-                    if (HAS_SCALE) d = __dmul_rn(d, s_inv[i]);
-                    if (d < bd[j]) { bd[j] = d; bi[j] = g0 + i; }
-                }
+            for (int j = 0; j < 8; ++j) {
+                const double dy = __dsub_rn(a.y0 + (double)(qy0 + r0 + j), g.y);
+                double d = __dadd_rn(dxx, __dmul_rn(dy, dy));
+                if (HAS_SCALE) d = __dmul_rn(d, iv);
+                if (d < bd[j]) { bd[j] = d; bi[j] = gid; }
             }
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int p = half + j * TESS_MAIN_THREADS + tid;
-            const long c = bx + (p & (TESS_TS - 1)), r = by + (p >> 6);
+            const long r = qy0 + r0 + j;
             if (c >= a.W || r >= a.H) continue;
             const long idx = r * a.W + c;
             labels[idx] = bi[j];
             if (MODE != 0) {
-                const double X = a.x0 + (double)c, Y = a.y0 + (double)r;
+                const double Y = a.y0 + (double)r;
                 double val[NV];
                 bool ok;
                 if (MODE == 1) {
@@ -223,20 +229,18 @@ TESS_NOINLINE void tess_tile_brute(const TessImgArgs& a, int32_t* labels, int tx
             }
         }
     }
-    __syncthreads();
+    __syncwarp();
 }
 
-// ---- lane groups of the list filters: 32 lanes (quadrant), 16 lanes (16x16 block: the lanes of
-// eight adjacent pixel-column pairs, both row halves) or 8 lanes (8x8 leaf)
+// ---- lane groups of the list filters: 16 lanes (16x16 block: the lanes of eight adjacent
+// pixel-column pairs, both row halves) or 8 lanes (8x8 leaf)
 template <int GROUP>
 TESS_DEVFN int tess_group_rank(int lane) {
-    if (GROUP == 32) return lane;
     if (GROUP == 16) return (lane & 7) | ((lane >> 4) << 3);
     return (lane & 3) | ((lane >> 4) << 2);
 }
 template <int GROUP>
 TESS_DEVFN unsigned tess_group_bits(unsigned bb, int lane) {
-    if (GROUP == 32) return bb;
     if (GROUP == 16) {
         const int h = (lane >> 3) & 1;
         return ((bb >> (8 * h)) & 0xFFu) | (((bb >> (16 + 8 * h)) & 0xFFu) << 8);
@@ -249,7 +253,6 @@ TESS_DEVFN double tess_group_min(double v) {
     v = fmin(v, __shfl_xor_sync(TESS_FULL, v, 1));
     v = fmin(v, __shfl_xor_sync(TESS_FULL, v, 2));
     if (GROUP >= 16) v = fmin(v, __shfl_xor_sync(TESS_FULL, v, 4));
-    if (GROUP == 32) v = fmin(v, __shfl_xor_sync(TESS_FULL, v, 8));
     v = fmin(v, __shfl_xor_sync(TESS_FULL, v, 16));
     return v;
 }
@@ -257,25 +260,22 @@ TESS_DEVFN double tess_group_min(double v) {
 // Centre + radius filter of a candidate list for the rectangle with centre (ccx, ccy) and
 // half-diagonal rho, done by a group of GROUP lanes:
 //   keep g  iff  u(c,g) <= min_h u(c,h) + 2 rho / s_min      (u = distance / scale)
-// The input list holds plen elements e_i = pident ? i : pl[i]; an element maps to a staged slot by
-// slot = q_ident ? e : ql[e].  Order preserving.  Survivors' elements go to `out` (QUAD: also their
-// generator indices to `qgid`; LEAF: also their coordinates to lg / li).  Returns the number of
-// survivors (which may exceed `cap`: the caller then keeps using the parent list).
-// plen may differ between groups of a warp; plen_max is its maximum over the warp.
-template <int GROUP, bool HAS_SCALE, bool QUAD, bool LEAF>
-TESS_DEVFN int tess_filter(const double2* s_g, const double* s_inv, const int* s_gid, const unsigned short* ql,
-                           bool q_ident, const unsigned short* pl, bool pident, int plen, int plen_max, double ccx,
-                           double ccy, double rho, bool active, int lane, unsigned short* out, int* qgid, double2* lg,
-                           double* li, int cap) {
+// The input list holds plen positions e_i = pident ? i : pl[i] of the quadrant list (qxy / qinv).
+// Order preserving.  Survivors' positions go to `out` (LEAF: also their coordinates to lg / li).
+// Returns the number of survivors (which may exceed `cap`: the caller then keeps using the parent
+// list).  plen may differ between groups of a warp; plen_max is its maximum over the warp.
+template <int GROUP, bool HAS_SCALE, bool LEAF>
+TESS_DEVFN int tess_filter(const double2* qxy, const double* qinv, const unsigned short* pl, bool pident, int plen,
+                           int plen_max, double ccx, double ccy, double rho, bool active, int lane, unsigned short* out,
+                           double2* lg, double* li, int cap) {
     const int rank = tess_group_rank<GROUP>(lane);
     double umin = INFINITY, imax = 1.0;
     for (int i = rank; i < plen; i += GROUP) {
         const int e = pident ? i : (int)pl[i];
-        const int sl = q_ident ? e : (int)ql[e];
-        const double2 g = s_g[sl];
+        const double2 g = qxy[e];
         const double dx = ccx - g.x, dy = ccy - g.y;
         double d = dx * dx + dy * dy;
-        if (HAS_SCALE) { const double iv = s_inv[sl]; d *= iv; imax = fmax(imax, iv); }
+        if (HAS_SCALE) { const double iv = qinv[e]; d *= iv; imax = fmax(imax, iv); }
         umin = fmin(umin, d);
     }
     umin = tess_group_min<GROUP>(umin);
@@ -289,23 +289,21 @@ TESS_DEVFN int tess_filter(const double2* s_g, const double* s_inv, const int* s
     for (int b0 = 0; b0 < plen_max; b0 += GROUP) {     // plen_max: warp-uniform bound (ballots inside)
         const int i = b0 + rank;
         bool keep = false;
-        int e = 0, sl = 0;
+        int e = 0;
         double2 g = make_double2(0.0, 0.0);
         double iv = 1.0;
         if (i < plen) {
             e = pident ? i : (int)pl[i];
-            sl = q_ident ? e : (int)ql[e];
-            g = s_g[sl];
+            g = qxy[e];
             const double dx = ccx - g.x, dy = ccy - g.y;
             double d = dx * dx + dy * dy;
-            if (HAS_SCALE) { iv = s_inv[sl]; d *= iv; }
+            if (HAS_SCALE) { iv = qinv[e]; d *= iv; }
             keep = active && (d <= thr);
         }
         const unsigned gb = tess_group_bits<GROUP>(__ballot_sync(TESS_FULL, keep), lane);
         const int pos = n + __popc(gb & ((1u << rank) - 1u));
         if (keep && pos < cap) {
             out[pos] = (unsigned short)e;
-            if (QUAD) qgid[pos] = s_gid[sl];
             if (LEAF) {
                 lg[pos] = g;
                 if (HAS_SCALE) li[pos] = iv;
@@ -318,7 +316,7 @@ TESS_DEVFN int tess_filter(const double2* s_g, const double* s_inv, const int* s
 }
 
 // Loads the lane's 2x4 pixel patch whose first pixel is (px, py): weight (MODE 1) or signal and
-// noise (MODE 2).  Interior tiles: four 128-bit loads; else guarded scalar loads, NaN outside.
+// noise (MODE 2).  Interior quadrants: four 128-bit loads; else guarded scalar loads, NaN outside.
 template <int MODE, bool VEC>
 TESS_DEVFN void tess_load_patch(const TessImgArgs& a, const double* src, bool interior, long px, long py,
                                 double (&w)[4][2], double (&nz)[4][2]) {
@@ -345,36 +343,41 @@ TESS_DEVFN void tess_load_patch(const TessImgArgs& a, const double* src, bool in
     }
 }
 
+// per-warp shared memory of the main kernel
+template <int MODE, bool HAS_SCALE>
+struct TessWarpSmem {
+    static constexpr int NV = (MODE == 2) ? 5 : 3;
+    static constexpr int QC = TESS_QCAP(MODE);
+    double2 qxy[2][QC];                                      // quadrant list (double buffered): coordinates,
+    double qinv[HAS_SCALE ? 2 : 1][HAS_SCALE ? QC : 1];     //   1/scale^2,
+    int qgid[2][QC];                                         //   generator index
+    double tab[(MODE != 0) ? QC * (NV + 1) : 1];             // accumulators per list position
+    double2 lg[4][TESS_LEAF_CAP];                            // leaf lists: coordinates,
+    double li[HAS_SCALE ? 4 : 1][HAS_SCALE ? TESS_LEAF_CAP : 1];   //   1/scale^2,
+    unsigned short ls[4][TESS_LEAF_CAP];                     //   quadrant-list position
+    unsigned short bl[2][TESS_BCAP];                         // 16x16 block lists (positions)
+};
+
 // MODE 0: labels only; 1: density map (4 moments); 2: signal + noise maps (6 moments)
 template <int MODE, bool HAS_SCALE, bool VEC>
 __global__ void __launch_bounds__(TESS_MAIN_THREADS, (MODE == 2) ? TESS_MAIN_MINBLOCKS_SN : TESS_MAIN_MINBLOCKS)
 k_image_main(TessImgArgs a) {
     constexpr int NV = (MODE == 2) ? 5 : 3;
     constexpr int NW = TESS_MAIN_THREADS / 32;
-    constexpr int TQ = TESS_TQ(NV);
+    constexpr int QC = TESS_QCAP(MODE);
     if (TESS_STOPPED(a.st, a.honor)) return;
     int32_t* const labels = a.labels_ext ? a.labels_ext : ((a.st->iters_done & 1) ? a.lab1 : a.lab0);
 
-    __shared__ __align__(16) double2 s_g[TESS_CAP];     // generator (x, y) of each staged slot
-    __shared__ int s_gid[TESS_CAP];                     // its global index
-    __shared__ double s_inv[HAS_SCALE ? TESS_CAP : 1];  // 1/scale^2
-    __shared__ unsigned short s_ql[NW][TESS_QCAP];      // quadrant lists: staged slots ...
-    __shared__ int s_qgid[NW][TESS_QCAP];               // ... and their generator indices
-    __shared__ unsigned short s_bl[NW][2][TESS_BCAP];   // 16x16 block lists (quadrant-list positions)
-    __shared__ __align__(16) double2 s_lg[NW][4][TESS_LEAF_CAP];   // leaf lists: coordinates ...
-    __shared__ double s_li[HAS_SCALE ? NW : 1][4][HAS_SCALE ? TESS_LEAF_CAP : 1];   // ... 1/scale^2 ...
-    __shared__ unsigned short s_ls[NW][4][TESS_LEAF_CAP];          // ... and quadrant-list position
-    __shared__ double s_tab[(MODE != 0) ? NW : 1][(MODE != 0) ? TQ * (NV + 1) : 1];   // per-warp accumulators
-    __shared__ int s_tile[2];
-
-    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    __shared__ __align__(16) TessWarpSmem<MODE, HAS_SCALE> s_w[NW];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    TessWarpSmem<MODE, HAS_SCALE>& sm = s_w[wib];
     const int cx = lane & 15, ry = lane >> 4;          // patch: cols 2cx,2cx+1; rows 4ry..4ry+3
     const int leaf = cx >> 2;                          // 8-px-wide leaf of the warp tile
     const int blk = cx >> 3;                           // 16-px-wide block
-    unsigned short* const ql = s_ql[wib];
-    double* const tab = s_tab[(MODE != 0) ? wib : 0];
-    const int n_tiles = a.tiles_x * a.tiles_y;
+    double* const tab = sm.tab;
     const double* const src = (MODE == 2) ? a.sig : a.dens;   // MODE 1: weight map; MODE 2: signal map
+    const long n_q = (long)a.L.nqx * a.L.nqy;
+    const long stride = (long)gridDim.x * NW;
 
     TessRun<NV> cur;                 // the lane's running same-bin sum (registers)
     cur.key = -1;
@@ -382,60 +385,61 @@ k_image_main(TessImgArgs a) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) cur.v[i] = 0.0;
 
-    if (tid == 0) s_tile[0] = atomicAdd(&a.st->tile_counter, 1);
-    __syncthreads();
-    int tile = s_tile[0];
-
-    for (int it = 0; tile < n_tiles; ++it) {
-        if (tid == 0) s_tile[(it + 1) & 1] = atomicAdd(&a.st->tile_counter, 1);   // prefetch the next tile
-        const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
-        const int cnt = a.list_cnt[tile];
-        if (cnt == TESS_BRUTE) {       // CTA-uniform
-            tess_tile_brute<MODE, HAS_SCALE>(a, labels, tx, ty, s_g, s_inv);
-            tile = s_tile[(it + 1) & 1];
-            continue;
+    // ---- software pipeline over this warp's quadrants q, q + stride, ...: the list of quadrant i+1 is
+    //      copied to shared memory (cp.async) while quadrant i is processed; (offset, count) of
+    //      quadrant i+2 are loaded at the same time.
+    long q = (long)blockIdx.x * NW + wib;
+    int cnt = (q < n_q) ? a.L.q_cnt[q] : 0, off = (q < n_q) ? a.L.q_off[q] : 0;
+    long q1 = q + stride;
+    int cnt1 = (q1 < n_q) ? a.L.q_cnt[q1] : 0, off1 = (q1 < n_q) ? a.L.q_off[q1] : 0;
+    int buf = 0;
+    auto stage = [&](int b, int o, int n) {
+        if (n > 0 && n <= QC) {
+            for (int i = lane; i < n; i += 32) {
+                tess_cp_async16(&sm.qxy[b][i], a.L.xy + o + i);
+                tess_cp_async4(&sm.qgid[b][i], a.L.gid + o + i);
+                if (HAS_SCALE) tess_cp_async8(&sm.qinv[b][i], a.L.inv + o + i);
+            }
         }
-        // quadrant of this warp, clipped to the image
-        const long qx0 = (long)tx * TESS_TS + 32 * (wib & 1);
-        const long qy0 = (long)ty * TESS_TS + 32 * (wib >> 1);
-        const bool q_in = (qx0 < a.W) && (qy0 < a.H);
-        const long qx1 = min(qx0 + 31, a.W - 1), qy1 = min(qy0 + 31, a.H - 1);
-        // interior tile: every pixel access of the tile is in bounds (and 16-byte aligned: VEC)
-        const bool interior = VEC && ((long)(tx + 1) * TESS_TS <= a.W) && ((long)(ty + 1) * TESS_TS <= a.H);
+    };
+    stage(0, off, cnt);
+
+    while (q < n_q) {
+        // (offset, count) of the quadrant after the next: in flight during this quadrant
+        const long q2 = q1 + stride;
+        int cnt2 = 0, off2 = 0;
+        if (q2 < n_q) { cnt2 = a.L.q_cnt[q2]; off2 = a.L.q_off[q2]; }
+        tess_cp_async_wait();          // this quadrant's list has landed
+        __syncwarp();
+        if (q1 < n_q) stage(buf ^ 1, off1, cnt1);
+        const int cnt_cur = cnt, off_cur = off;
+        const int qx = (int)(q % a.L.nqx), qy = (int)(q / a.L.nqx);
+        const long qx0 = 32L * qx, qy0 = 32L * qy;
+        if (cnt_cur != 0) {
+        if (cnt_cur < 0 || cnt_cur > QC) {
+            // slow path: list too long for the fast path (scan it from global memory) or overflow of
+            // the builder (scan the complete generator table)
+            if (cnt_cur > 0)
+                tess_quadrant_scan<MODE, HAS_SCALE>(a, labels, qx0, qy0, a.L.xy + off_cur, a.L.gid + off_cur,
+                                                    HAS_SCALE ? a.L.inv + off_cur : nullptr, cnt_cur);
+            else
+                tess_quadrant_scan<MODE, HAS_SCALE>(a, labels, qx0, qy0, reinterpret_cast<const double2*>(a.node), nullptr,
+                                                    a.inv_s2, a.k);
+        } else {
+        const double2* const qxy = sm.qxy[buf];
+        const double* const qinv = HAS_SCALE ? sm.qinv[buf] : nullptr;
+        const int* const gidv = sm.qgid[buf];
+        const int c_q = cnt_cur;
+        // interior quadrant: every pixel access is in bounds (and 16-byte aligned: VEC)
+        const bool interior = VEC && (qx0 + 32 <= a.W) && (qy0 + 32 <= a.H);
         const long px = qx0 + 2 * cx;                    // first column of this lane
         const double X0 = a.x0 + (double)px, X1 = a.x0 + (double)(px + 1);
 
-        // ---- stage the candidate list
-        {
-            const int off = a.list_off[tile];
-            for (int i = tid; i < cnt; i += TESS_MAIN_THREADS) {
-                const int gid = a.list_items[off + i];
-                s_gid[i] = gid;
-                s_g[i] = make_double2(a.node[2 * (long)gid], a.node[2 * (long)gid + 1]);
-                if (HAS_SCALE) s_inv[i] = a.inv_s2[gid];
-            }
-        }
-        __syncthreads();
-
-        // ---- request the pixels of the first warp tile (consumed after the list work below)
+        // ---- request the pixels of the first warp tile; clear the accumulator table
         double wn_[4][2], nn_[4][2];
-        if (MODE != 0 && q_in) tess_load_patch<MODE, VEC>(a, src, interior, px, qy0 + 4 * ry, wn_, nn_);
-
-        // ---- quadrant list: staged list -> slots that can win somewhere in the 32x32 quadrant
-        int c_q = cnt;
-        bool q_ident = true;       // true: the quadrant list is the staged list itself
-        if (q_in && cnt > 1) {
-            const double hx = 0.5 * (double)(qx1 - qx0), hy = 0.5 * (double)(qy1 - qy0);
-            const double rho = interior ? 21.920310216783 : sqrt(hx * hx + hy * hy) * 1.0000001;   // 15.5 sqrt 2
-            const int n = tess_filter<32, HAS_SCALE, true, false>(
-                s_g, s_inv, s_gid, nullptr, true, nullptr, true, cnt, cnt, a.x0 + 0.5 * (double)(qx0 + qx1),
-                a.y0 + 0.5 * (double)(qy0 + qy1), rho, true, lane, ql, s_qgid[wib],
-                nullptr, nullptr, TESS_QCAP);
-            if (n <= TESS_QCAP) { c_q = n; q_ident = false; }
-        }
-        const int* const gidv = q_ident ? s_gid : s_qgid[wib];    // quadrant-list position -> generator index
-        if (MODE != 0 && q_in) {
-            const int na = min(c_q, TQ) * (NV + 1);
+        if (MODE != 0) {
+            tess_load_patch<MODE, VEC>(a, src, interior, px, qy0 + 4 * ry, wn_, nn_);
+            const int na = c_q * (NV + 1);
             for (int i = lane; i < na; i += 32) tab[i] = 0.0;
             __syncwarp();
         }
@@ -444,7 +448,7 @@ k_image_main(TessImgArgs a) {
         bool p_ident = true;
         int p_len = c_q;
 
-        for (int step = 0; step < 4 && q_in; ++step) {
+        for (int step = 0; step < 4; ++step) {
             const long wy0 = qy0 + 8 * step;
             if (wy0 >= a.H) break;                         // warp-uniform
             const long py = wy0 + 4 * ry;                  // first row of this lane
@@ -453,8 +457,7 @@ k_image_main(TessImgArgs a) {
 #pragma unroll
             for (int r = 0; r < 4; ++r) Y[r] = a.y0 + (double)(py + r);
 
-            // ---- pixel data of this warp tile was requested one warp tile ahead (software pipeline:
-            //      the loads of warp tile s+1 are in flight while warp tile s is processed).
+            // ---- pixel data of this warp tile was requested one warp tile ahead (software pipeline).
             //      Pixels outside the image read as NaN and drop out with the masked ones.
             double w_[4][2], n_[4][2];                     // MODE 1: weight; MODE 2: signal, noise
             if (MODE != 0) {
@@ -472,19 +475,19 @@ k_image_main(TessImgArgs a) {
                     const long bx0 = qx0 + 16 * blk, bx1 = min(bx0 + 15, a.W - 1), by1 = min(wy0 + 15, a.H - 1);
                     const double hx = 0.5 * (double)(bx1 - bx0), hy = 0.5 * (double)(by1 - wy0);
                     const double rho = interior ? 10.606602778 : sqrt(hx * hx + hy * hy) * 1.0000001;   // 7.5 sqrt 2
-                    const int n = tess_filter<16, HAS_SCALE, false, false>(
-                        s_g, s_inv, s_gid, ql, q_ident, nullptr, true, c_q, c_q, a.x0 + 0.5 * (double)(bx0 + bx1),
-                        a.y0 + 0.5 * (double)(wy0 + by1), rho, bx0 < a.W, lane,
-                        s_bl[wib][blk], nullptr, nullptr, nullptr, TESS_BCAP);
+                    const int n = tess_filter<16, HAS_SCALE, false>(qxy, qinv, nullptr, true, c_q, c_q,
+                                                                    a.x0 + 0.5 * (double)(bx0 + bx1),
+                                                                    a.y0 + 0.5 * (double)(wy0 + by1), rho, bx0 < a.W, lane,
+                                                                    sm.bl[blk], nullptr, nullptr, TESS_BCAP);
                     // both blocks must fit for the (warp-uniform) parent switch
-                    if (__all_sync(TESS_FULL, n <= TESS_BCAP)) { pl = s_bl[wib][blk]; p_ident = false; p_len = n; }
+                    if (__all_sync(TESS_FULL, n <= TESS_BCAP)) { pl = sm.bl[blk]; p_ident = false; p_len = n; }
                 }
             }
 
             // ---- candidates of this lane's 8x8 leaf
-            double2* const lg = s_lg[wib][leaf];
-            unsigned short* const ls = s_ls[wib][leaf];
-            double* const li = HAS_SCALE ? s_li[wib][leaf] : nullptr;
+            double2* const lg = sm.lg[leaf];
+            unsigned short* const ls = sm.ls[leaf];
+            double* const li = HAS_SCALE ? sm.li[leaf] : nullptr;
             int len = 0;
             bool use_leaf = false;
             bool uniform = (c_q == 1);                     // the whole warp tile belongs to one bin
@@ -496,10 +499,10 @@ k_image_main(TessImgArgs a) {
                     const long lx1 = min(lx0 + 7, a.W - 1), ly1 = min(wy0 + 7, a.H - 1);
                     const double hx = 0.5 * (double)(lx1 - lx0), hy = 0.5 * (double)(ly1 - wy0);
                     const double rho = interior ? 4.9497479632 : sqrt(hx * hx + hy * hy) * 1.0000001;   // 3.5 sqrt 2
-                    len = tess_filter<8, HAS_SCALE, false, true>(
-                        s_g, s_inv, s_gid, ql, q_ident, pl, p_ident, p_len, p_max, a.x0 + 0.5 * (double)(lx0 + lx1),
-                        a.y0 + 0.5 * (double)(wy0 + ly1), rho, lx0 < a.W, lane, ls,
-                        nullptr, lg, li, TESS_LEAF_CAP);
+                    len = tess_filter<8, HAS_SCALE, true>(qxy, qinv, pl, p_ident, p_len, p_max,
+                                                          a.x0 + 0.5 * (double)(lx0 + lx1),
+                                                          a.y0 + 0.5 * (double)(wy0 + ly1), rho, lx0 < a.W, lane, ls, lg, li,
+                                                          TESS_LEAF_CAP);
                     use_leaf = (len <= TESS_LEAF_CAP);
                     // all (in-image) leaves ended with the same single candidate?
                     const int one = (len == 1) ? (int)ls[0] : ((lx0 < a.W) ? -1 : -3);
@@ -544,9 +547,8 @@ k_image_main(TessImgArgs a) {
                         if (HAS_SCALE) inv = li[j];
                     } else {
                         e = p_ident ? j : (int)pl[j];
-                        const int sl = q_ident ? e : (int)ql[e];
-                        g = s_g[sl];
-                        if (HAS_SCALE) inv = s_inv[sl];
+                        g = qxy[e];
+                        if (HAS_SCALE) inv = qinv[e];
                     }
                     const double dx0 = __dsub_rn(X0, g.x), dx1 = __dsub_rn(X1, g.x);
                     const double dxx0 = __dmul_rn(dx0, dx0), dxx1 = __dmul_rn(dx1, dx1);
@@ -589,7 +591,7 @@ k_image_main(TessImgArgs a) {
                     if (MODE == 2) {
                         const double S = w_[r][c], N = n_[r][c];
                         w = 1.0;
-                        if (!a.uniform_weight) { const double q = __ddiv_rn(S, N); w = __dmul_rn(q, q); }
+                        if (!a.uniform_weight) { const double qq = __ddiv_rn(S, N); w = __dmul_rn(qq, qq); }
                         ok = (fabs(w) <= 1.7976931348623157e308) && (fabs(S) <= 1.7976931348623157e308) &&
                              (fabs(N) <= 1.7976931348623157e308);
                     } else {
@@ -603,7 +605,7 @@ k_image_main(TessImgArgs a) {
                 // closed form for a one-bin patch: sum w x = X0 col0 + X1 col1, sum w y = sum_r Y_r row_r
                 const bool sw = (cur.key != ukey);
                 if (__any_sync(TESS_FULL, sw)) {
-                    tess_table_flush<NV>(sw && cur.n > 0, cur.key, cur.n, cur.v, tab, gidv, a.mom, lane);
+                    tess_table_flush<NV>(sw && cur.n > 0, cur.key, cur.n, cur.v, tab, lane);
                     cur.key = ukey;
                     cur.n = sw ? 0 : cur.n;
 #pragma unroll
@@ -643,7 +645,7 @@ k_image_main(TessImgArgs a) {
                     for (int r = 0; r < 4; ++r) present = present || (bs[r][0] == cur.key) || (bs[r][1] == cur.key);
                     const bool sw = (rest >= 0) && !present;
                     if (__any_sync(TESS_FULL, sw)) {
-                        tess_table_flush<NV>(sw && cur.n > 0, cur.key, cur.n, cur.v, tab, gidv, a.mom, lane);
+                        tess_table_flush<NV>(sw && cur.n > 0, cur.key, cur.n, cur.v, tab, lane);
                         cur.key = sw ? rest : cur.key;
                         cur.n = sw ? 0 : cur.n;
 #pragma unroll
@@ -672,10 +674,9 @@ k_image_main(TessImgArgs a) {
         }   // steps
 
         // ---- end of the quadrant: retire the live runs (merged across the warp), table -> global
-        if (MODE != 0 && q_in) {
-            tess_warp_retire<NV>(cur, tab, gidv, a.mom, lane);
-            const int na = min(c_q, TQ);
-            for (int e = lane; e < na; e += 32) {
+        if (MODE != 0) {
+            tess_warp_retire<NV>(cur, tab, lane);
+            for (int e = lane; e < c_q; e += 32) {
                 const double* t = tab + e * (NV + 1);
                 if (t[0] != 0.0) {
                     double* m = a.mom + (long)gidv[e] * (NV + 1);
@@ -683,10 +684,15 @@ k_image_main(TessImgArgs a) {
                     for (int i = 0; i <= NV; ++i) tess_gmem_add(m + i, t[i]);
                 }
             }
+            __syncwarp();
         }
-        __syncthreads();   // the staged list is rewritten by the next tile
-        tile = s_tile[(it + 1) & 1];
-    }       // tiles
+        }   // fast path
+        }   // cnt != 0
+        // ---- rotate the pipeline
+        q = q1; cnt = cnt1; off = off1;
+        q1 = q2; cnt1 = cnt2; off1 = off2;
+        buf ^= 1;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

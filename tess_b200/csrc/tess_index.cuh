@@ -127,165 +127,231 @@ TESS_DEVFN TessRect tess_tile_rect(const TessTiles& T, int t) {
     return r;
 }
 
-// Visit, warp-cooperatively, every generator slot stored in the grid cells
-//   base, base+stride, ..., base+(count-1)*stride.
-// 32 cells are inspected per step; the slot ranges of the non-empty ones are then walked by
-// all lanes.  `f(slot)` is called by individual lanes (divergent); no collectives inside f.
-template <class F>
-TESS_DEVFN void tess_visit_cells(const int* cell_start, long base, long stride, int count, int lane, F f) {
-    for (int c0 = 0; c0 < count; c0 += 32) {
-        int c = c0 + lane;
-        int s = 0, e = 0;
-        if (c < count) {
-            long cell = base + (long)c * stride;
-            s = cell_start[cell];
-            e = cell_start[cell + 1];
-        }
-        if (stride == 1) {
-            // consecutive cells hold consecutive slots: one flat range [s(lane 0), max e).
-            // (valid lanes' e are non-decreasing; lanes beyond `count` contribute 0)
-            int first = __shfl_sync(TESS_FULL, s, 0);
-            int last = e;
-#pragma unroll
-            for (int m = 16; m >= 1; m >>= 1) last = max(last, __shfl_xor_sync(TESS_FULL, last, m));
-            for (int i = first + lane; i < last; i += 32) f(i);
-        } else {
-            unsigned any = __ballot_sync(TESS_FULL, e > s);
-            while (any) {
-                int src = __ffs((int)any) - 1;
-                any &= any - 1;
-                int ss = __shfl_sync(TESS_FULL, s, src);
-                int ee = __shfl_sync(TESS_FULL, e, src);
-                for (int i = ss + lane; i < ee; i += 32) f(i);
-            }
-        }
-    }
-}
+// ---------------------------------------------------------------------------------------------
+// Per-quadrant candidate lists.  A quadrant is a 32x32-px quarter of a tile; its list holds every
+// generator that can be nearest to some pixel of the quadrant, as arena records (coordinates,
+// generator index[, 1/scale^2]) in ascending generator index.
+struct TessQLists {
+    int* q_off;        // [nqx*nqy] first arena record of the quadrant's list
+    int* q_cnt;        // [nqx*nqy] records; 0: quadrant outside the window; -1: overflow -> scan all generators
+    double2* xy;       // arena
+    int* gid;
+    double* inv;       // arena (scaled metric only)
+    unsigned capacity; // arena records
+    int nqx, nqy;      // quadrant grid (2 tiles_x, 2 tiles_y)
+};
 
-#define TESS_LIST_WARPS 4
+#define TESS_LIST_WARPS 2
 
-// One warp per tile (grid-stride over tiles).
+// One warp per 64x64 tile (grid-stride).
+//  1. Box search: the generators of the grid cells within `ring` cells of the tile are scanned for
+//     R = min_h maxd2(h, tile) [* inv_s2_h]; the ring doubles until every generator outside the box is
+//     provably too far, (ring cs)^2 min_inv > R -- the search radius is bounded by the LARGEST scale.
+//  2. The box generators with mind2 [* inv_s2] <= R are staged in shared memory: no other generator
+//     can be nearest to any pixel of the tile.
+//  3. They are sorted by generator index (bitonic): every list derived from a sorted list by an
+//     order-preserving compaction lets the evaluators implement "lowest index wins an exact tie"
+//     with a strict '<'.
+//  4. Each of the four quadrants keeps those that pass the centre + radius test
+//     u(c,g) <= min_h u(c,h) + 2 rho / s_min and writes them to the arena.
 template <bool HAS_SCALE>
 __global__ void __launch_bounds__(TESS_LIST_WARPS * 32)
-k_build_lists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cell_start, const int* cell_items,
-              const double2* cell_xy, const double* cell_inv, int* list_off, int* list_cnt, int* list_items,
-              unsigned list_capacity) {
+k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cell_start, const int* cell_items,
+               const double2* cell_xy, const double* cell_inv, TessQLists L) {
     if (TESS_STOPPED(st, honor)) return;
-    __shared__ int s_stage[TESS_LIST_WARPS][TESS_CAP];
+    __shared__ __align__(16) double2 s_xy[TESS_LIST_WARPS][TESS_CAP];
+    __shared__ double s_iv[HAS_SCALE ? TESS_LIST_WARPS : 1][HAS_SCALE ? TESS_CAP : 1];
+    __shared__ unsigned long long s_key[TESS_LIST_WARPS][TESS_CAP];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int warp = blockIdx.x * TESS_LIST_WARPS + wib;
     const int n_warps = gridDim.x * TESS_LIST_WARPS;
     const double min_inv = HAS_SCALE ? st->min_inv_s2 : 1.0;
-    int* stage = s_stage[wib];
+    double2* const xy = s_xy[wib];
+    double* const iv = HAS_SCALE ? s_iv[wib] : nullptr;
+    unsigned long long* const key = s_key[wib];
 
     for (int t = warp; t < T.n_tiles; t += n_warps) {
-        TessRect r = tess_tile_rect(T, t);
+        const TessRect r = tess_tile_rect(T, t);
+        const int tx = t % T.tiles_x, ty = t / T.tiles_x;
         // cell range overlapped by the rectangle
         const int ci0 = tess_cell_coord(r.x0, g.ox, g.inv_cs, g.gw), ci1 = tess_cell_coord(r.x1, g.ox, g.inv_cs, g.gw);
         const int cj0 = tess_cell_coord(r.y0, g.oy, g.inv_cs, g.gh), cj1 = tess_cell_coord(r.y1, g.oy, g.inv_cs, g.gh);
 
-        // ---- phase 1: R = min_h maxd2(h, tile) [* inv_s2_h], rings outward until provably complete
-        double rbest = INFINITY;
-        auto upd = [&](int slot) {
-            const double2 p = cell_xy[slot];
-            double d = tess_maxd2(r, p.x, p.y);
-            if (HAS_SCALE) d *= cell_inv[slot];
-            rbest = fmin(rbest, d);
-        };
-        int ring = 0;
+        // ---- 1. box search for R
+        double rbest;
+        int ring = 1;
+        int xi0, xi1, xj0, xj1;
         for (;;) {
-            const int bi0 = ci0 - ring, bi1 = ci1 + ring, bj0 = cj0 - ring, bj1 = cj1 + ring;
-            const int xi0 = max(bi0, 0), xi1 = min(bi1, g.gw - 1);
-            const int xj0 = max(bj0, 0), xj1 = min(bj1, g.gh - 1);
-            if (ring == 0) {
-                for (int j = xj0; j <= xj1; ++j)
-                    tess_visit_cells(cell_start, (long)j * g.gw + xi0, 1, xi1 - xi0 + 1, lane, upd);
-            } else {
-                if (bj0 >= 0) tess_visit_cells(cell_start, (long)bj0 * g.gw + xi0, 1, xi1 - xi0 + 1, lane, upd);
-                if (bj1 < g.gh) tess_visit_cells(cell_start, (long)bj1 * g.gw + xi0, 1, xi1 - xi0 + 1, lane, upd);
-                const int yj0 = max(bj0 + 1, 0), yj1 = min(bj1 - 1, g.gh - 1);
-                if (yj1 >= yj0) {
-                    if (bi0 >= 0) tess_visit_cells(cell_start, (long)yj0 * g.gw + bi0, g.gw, yj1 - yj0 + 1, lane, upd);
-                    if (bi1 < g.gw) tess_visit_cells(cell_start, (long)yj0 * g.gw + bi1, g.gw, yj1 - yj0 + 1, lane, upd);
+            xi0 = max(ci0 - ring, 0); xi1 = min(ci1 + ring, g.gw - 1);
+            xj0 = max(cj0 - ring, 0); xj1 = min(cj1 + ring, g.gh - 1);
+            rbest = INFINITY;
+            for (int j0 = xj0; j0 <= xj1; j0 += 32) {
+                // one box row per lane: its cells are one contiguous slot range
+                const int j = j0 + lane;
+                int s = 0, e = 0;
+                if (j <= xj1) {
+                    s = cell_start[(long)j * g.gw + xi0];
+                    e = cell_start[(long)j * g.gw + xi1 + 1];
+                }
+                const int rows = min(32, xj1 - j0 + 1);
+                for (int src = 0; src < rows; ++src) {
+                    const int ss = __shfl_sync(TESS_FULL, s, src), ee = __shfl_sync(TESS_FULL, e, src);
+                    for (int i = ss + lane; i < ee; i += 32) {
+                        const double2 p = cell_xy[i];
+                        double d = tess_maxd2(r, p.x, p.y);
+                        if (HAS_SCALE) d *= cell_inv[i];
+                        rbest = fmin(rbest, d);
+                    }
                 }
             }
             rbest = tess_warp_min(rbest);
-            const bool whole = (bi0 <= 0 && bj0 <= 0 && bi1 >= g.gw - 1 && bj1 >= g.gh - 1);
+            const bool whole = (ci0 - ring <= 0 && cj0 - ring <= 0 && ci1 + ring >= g.gw - 1 && cj1 + ring >= g.gh - 1);
             if (whole) break;
             // every generator outside the box is at least `ring` whole cells away from the tile
-            double lb = fmax(g.cs * (double)ring - g.tol, 0.0);
+            const double lb = fmax(g.cs * (double)ring - g.tol, 0.0);
             if (lb * lb * min_inv > rbest * TESS_SLACK) break;
-            ++ring;
+            ring *= 2;
         }
         const double thr = rbest * TESS_SLACK;
 
-        // ---- phase 2: keep every generator of the box with mind2 [* inv_s2] <= R
+        // ---- 2. stage every generator of the box with mind2 [* inv_s2] <= R
         int cnt = 0;   // warp-uniform
-        {
-            const int xi0 = max(ci0 - ring, 0), xi1 = min(ci1 + ring, g.gw - 1);
-            const int xj0 = max(cj0 - ring, 0), xj1 = min(cj1 + ring, g.gh - 1);
-            for (int j = xj0; j <= xj1; ++j) {
-                // cells xi0..xi1 of one grid row are one contiguous slot range
-                const int ss = cell_start[(long)j * g.gw + xi0];
-                const int ee = cell_start[(long)j * g.gw + xi1 + 1];
+        for (int j0 = xj0; j0 <= xj1; j0 += 32) {
+            const int j = j0 + lane;
+            int s = 0, e = 0;
+            if (j <= xj1) {
+                s = cell_start[(long)j * g.gw + xi0];
+                e = cell_start[(long)j * g.gw + xi1 + 1];
+            }
+            const int rows = min(32, xj1 - j0 + 1);
+            for (int src = 0; src < rows; ++src) {
+                const int ss = __shfl_sync(TESS_FULL, s, src), ee = __shfl_sync(TESS_FULL, e, src);
                 for (int i0 = ss; i0 < ee; i0 += 32) {
                     const int i = i0 + lane;
-                    int gid = -1;
                     bool keep = false;
+                    double2 p = make_double2(0.0, 0.0);
+                    double pv = 1.0;
                     if (i < ee) {
-                        const double2 p = cell_xy[i];
+                        p = cell_xy[i];
                         double d = tess_mind2(r, p.x, p.y);
-                        if (HAS_SCALE) d *= cell_inv[i];
+                        if (HAS_SCALE) { pv = cell_inv[i]; d *= pv; }
                         keep = d <= thr;
-                        if (keep) gid = cell_items[i];
                     }
-                    unsigned b = __ballot_sync(TESS_FULL, keep);
-                    int pos = cnt + __popc(b & tess_lanemask_lt(lane));
-                    if (keep && pos < TESS_CAP) stage[pos] = gid;
+                    const unsigned b = __ballot_sync(TESS_FULL, keep);
+                    const int pos = cnt + __popc(b & tess_lanemask_lt(lane));
+                    if (keep && pos < TESS_CAP) {
+                        xy[pos] = p;
+                        if (HAS_SCALE) iv[pos] = pv;
+                        key[pos] = (unsigned long long)(unsigned)i;      // slot for now
+                    }
                     cnt += __popc(b);
                 }
             }
         }
         __syncwarp();
-        // ---- sort by generator index (bitonic, in shared memory): every list derived from this one
-        // is an order-preserving compaction, so the evaluators implement "lowest index wins a tie"
-        // with a strict '<'
-        if (cnt > 1 && cnt <= TESS_CAP) {
-            int n2 = 2;
+        const bool overflow = cnt > TESS_CAP;
+
+        // ---- 3. sort by generator index; the low word carries the staging position
+        if (!overflow) {
+            for (int i = lane; i < cnt; i += 32)
+                key[i] = ((unsigned long long)(unsigned)cell_items[(int)key[i]] << 32) | (unsigned)i;
+            int n2 = 1;
             while (n2 < cnt) n2 <<= 1;
-            for (int i = cnt + lane; i < n2; i += 32) stage[i] = 0x7fffffff;
+            for (int i = cnt + lane; i < n2; i += 32) key[i] = ~0ull;
             __syncwarp();
             for (int k2 = 2; k2 <= n2; k2 <<= 1) {
                 for (int j = k2 >> 1; j > 0; j >>= 1) {
                     for (int i = lane; i < n2; i += 32) {
                         const int ixj = i ^ j;
                         if (ixj > i) {
-                            const int va = stage[i], vb = stage[ixj];
+                            const unsigned long long va = key[i], vb = key[ixj];
                             const bool up = ((i & k2) == 0);
-                            if ((va > vb) == up) { stage[i] = vb; stage[ixj] = va; }
+                            if ((va > vb) == up) { key[i] = vb; key[ixj] = va; }
                         }
                     }
                     __syncwarp();
                 }
             }
         }
-        // ---- publish
-        unsigned off = 0;
-        int ok = 1;
-        if (lane == 0) {
-            if (cnt > TESS_CAP) ok = 0;
-            else {
-                off = atomicAdd(&st->list_cursor, (unsigned)cnt);
-                if (off + (unsigned)cnt > list_capacity) ok = 0;
+
+        // ---- 4. the four quadrants
+        for (int q = 0; q < 4; ++q) {
+            const int qx = 2 * tx + (q & 1), qy = 2 * ty + (q >> 1);
+            const long px0 = (long)tx * TESS_TS + 32 * (q & 1), py0 = (long)ty * TESS_TS + 32 * (q >> 1);
+            const long qid = (long)qy * L.nqx + qx;
+            if (px0 >= T.W || py0 >= T.H) {
+                if (lane == 0) { L.q_off[qid] = 0; L.q_cnt[qid] = 0; }
+                continue;
             }
-            list_off[t] = ok ? (int)off : 0;
-            list_cnt[t] = ok ? cnt : TESS_BRUTE;
-            if (!ok) atomicAdd(&st->n_brute, 1);
+            if (overflow) {
+                if (lane == 0) { L.q_off[qid] = 0; L.q_cnt[qid] = -1; atomicAdd(&st->n_brute, 1); }
+                continue;
+            }
+            const long px1 = min(px0 + 31, T.W - 1), py1 = min(py0 + 31, T.H - 1);
+            const double ccx = T.x0 + 0.5 * (double)(px0 + px1), ccy = T.y0 + 0.5 * (double)(py0 + py1);
+            const double hx = 0.5 * (double)(px1 - px0), hy = 0.5 * (double)(py1 - py0);
+            const double rho = sqrt(hx * hx + hy * hy) * 1.0000001;
+            double umin = INFINITY, imax = 1.0;
+            for (int i = lane; i < cnt; i += 32) {
+                const int ix = (int)(unsigned)key[i];
+                const double2 p = xy[ix];
+                const double dx = ccx - p.x, dy = ccy - p.y;
+                double d = dx * dx + dy * dy;
+                if (HAS_SCALE) { const double v = iv[ix]; d *= v; imax = fmax(imax, v); }
+                umin = fmin(umin, d);
+            }
+            umin = tess_warp_min(umin);
+            double c = 2.0 * rho;
+            if (HAS_SCALE) {
+                imax = -tess_warp_min(-imax);
+                c *= (double)sqrtf((float)imax) * 1.000001 + 1e-18;
+            }
+            const double su = (double)sqrtf((float)umin) * 1.000001 + 1e-18;      // >= sqrt(umin)
+            const double qthr = (umin + 2.0 * c * su + c * c) * TESS_SLACK;
+            // keep flags of this lane's entries (entry i = 32 b + lane -> bit b), then the count
+            unsigned bits = 0;
+            int n = 0;
+            for (int b = 0; 32 * b < cnt; ++b) {
+                const int i = 32 * b + lane;
+                bool keep = false;
+                if (i < cnt) {
+                    const int ix = (int)(unsigned)key[i];
+                    const double2 p = xy[ix];
+                    const double dx = ccx - p.x, dy = ccy - p.y;
+                    double d = dx * dx + dy * dy;
+                    if (HAS_SCALE) d *= iv[ix];
+                    keep = d <= qthr;
+                }
+                if (keep) bits |= 1u << b;
+                n += __popc(__ballot_sync(TESS_FULL, keep));
+            }
+            unsigned off = 0;
+            int ok = 1;
+            if (lane == 0) {
+                off = atomicAdd(&st->list_cursor, (unsigned)n);
+                if (off + (unsigned)n > L.capacity) ok = 0;
+                L.q_off[qid] = ok ? (int)off : 0;
+                L.q_cnt[qid] = ok ? n : -1;
+                if (!ok) atomicAdd(&st->n_brute, 1);
+            }
+            off = __shfl_sync(TESS_FULL, off, 0);
+            ok = __shfl_sync(TESS_FULL, ok, 0);
+            if (!ok) continue;
+            int wpos = 0;
+            for (int b = 0; 32 * b < cnt; ++b) {
+                const bool keep = (bits >> b) & 1u;
+                const unsigned bb = __ballot_sync(TESS_FULL, keep);
+                if (keep) {
+                    const unsigned long long kv = key[32 * b + lane];
+                    const int ix = (int)(unsigned)kv;
+                    const unsigned o = off + wpos + __popc(bb & tess_lanemask_lt(lane));
+                    L.xy[o] = xy[ix];
+                    L.gid[o] = (int)(kv >> 32);
+                    if (HAS_SCALE) L.inv[o] = iv[ix];
+                }
+                wpos += __popc(bb);
+            }
         }
-        off = __shfl_sync(TESS_FULL, off, 0);
-        ok = __shfl_sync(TESS_FULL, ok, 0);
-        if (ok)
-            for (int i = lane; i < cnt; i += 32) list_items[off + i] = stage[i];
         __syncwarp();
     }
 }

@@ -16,7 +16,8 @@ rng = np.random.default_rng(0)
 dens = torch.rand((N, N), dtype=torch.float64, device="cuda") + 0.5
 eng.set_image(density=dens)
 out = []
-for area in (40, 80, 160, 320, 700, 1500, 4000, 12000, 40000, 150000):
+AREAS = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [80, 160, 320, 700, 1500, 4000, 12000, 40000, 150000]
+for area in AREAS:
     k = max(4, int(N * N / area))
     seeds = rng.uniform(0, N - 1, (k, 2))
     eng.set_generators(seeds)
