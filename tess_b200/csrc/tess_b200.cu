@@ -76,6 +76,7 @@ struct tess_ctx {
     double* cell_inv;
     long cells_cap;
     TessQLists ql;      // per-quadrant candidate lists (arena)
+    int* tile_ring;     // per tile: box-search ring that sufficed last time (a hint, not state)
     long quads_cap;
     int arena_has_inv;
     int32_t* lab[2];
@@ -139,7 +140,7 @@ extern "C" int tess_ctx_destroy(tess_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     void* ptrs[] = {c->node, c->scale, c->inv_s2, c->st, c->cell_cnt, c->cell_start, c->cell_of, c->cell_items,
-                    c->cell_xy, c->cell_inv, c->ql.q_off, c->ql.q_cnt, c->ql.xy, c->ql.gid, c->ql.inv, c->lab[0], c->lab[1],
+                    c->cell_xy, c->cell_inv, c->ql.q_off, c->ql.q_cnt, c->ql.xy, c->ql.gid, c->ql.inv, c->tile_ring, c->lab[0], c->lab[1],
                     c->mom, c->prev_count, c->scratch};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -375,8 +376,12 @@ static int ensure_lists(tess_ctx* c, const TessTiles& T) {
     if (nq > c->quads_cap) {
         if (c->ql.q_off) cudaFree(c->ql.q_off);
         if (c->ql.q_cnt) cudaFree(c->ql.q_cnt);
+        if (c->tile_ring) cudaFree(c->tile_ring);
         c->ql.q_off = c->ql.q_cnt = nullptr;
+        c->tile_ring = nullptr;
         c->quads_cap = 0;
+        CU_TRY(cudaMalloc((void**)&c->tile_ring, sizeof(int) * (size_t)nq));      // >= n_tiles
+        CU_TRY(cudaMemset(c->tile_ring, 0, sizeof(int) * (size_t)nq));
         CU_TRY(cudaMalloc((void**)&c->ql.q_off, sizeof(int) * (size_t)nq));
         CU_TRY(cudaMalloc((void**)&c->ql.q_cnt, sizeof(int) * (size_t)nq));
         c->quads_cap = nq;
@@ -439,10 +444,10 @@ static int build_lists(tess_ctx* c, const Geometry& q, int honor, cudaStream_t s
     if (grid > c->sm_count * 32) grid = c->sm_count * 32;
     if (c->has_scale)
         TESS_LAUNCH((k_build_qlists<true>), grid, TESS_LIST_WARPS * 32, s, c->st, honor, q.T, q.g, c->cell_start,
-                    c->cell_items, c->cell_xy, c->cell_inv, c->ql);
+                    c->cell_items, c->cell_xy, c->cell_inv, c->ql, c->tile_ring);
     else
         TESS_LAUNCH((k_build_qlists<false>), grid, TESS_LIST_WARPS * 32, s, c->st, honor, q.T, q.g, c->cell_start,
-                    c->cell_items, c->cell_xy, c->cell_inv, c->ql);
+                    c->cell_items, c->cell_xy, c->cell_inv, c->ql, c->tile_ring);
     CU_TRY(cudaGetLastError());
     return TESS_OK;
 }

@@ -13,8 +13,8 @@
 // and per 8x8 leaf (8 lanes per leaf) with the centre + radius test
 //     keep g  iff  u(c,g) <= min_h u(c,h) + 2 rho / s_min        (u = distance / scale)
 // which can never drop the true nearest generator of any pixel of the rectangle, evaluates the
-// survivors with the pinned fp64 formula (ascending generator index + strict '<' = lowest index wins
-// an exact tie) and writes labels as one coalesced 128-byte line per row.
+// survivors with the pinned fp64 formula (an exact tie is detected and then resolved to the lowest
+// generator index) and writes labels as one coalesced 128-byte line per row.
 //
 // Moments ("segmented reduction"): every lane owns a 2-column x 4-row pixel patch per warp tile and
 // keeps ONE running same-bin sum in registers across the warp tiles of the quadrant (labels are
@@ -183,7 +183,7 @@ TESS_NOINLINE void tess_quadrant_scan(const TessImgArgs& a, int32_t* labels, lon
         double bd[8];
         int bi[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { bd[j] = INFINITY; bi[j] = 0; }
+        for (int j = 0; j < 8; ++j) { bd[j] = INFINITY; bi[j] = 0x7fffffff; }
         for (int i = 0; i < n; ++i) {
             const double2 g = gxy[i];
             const double iv = HAS_SCALE ? ginv[i] : 1.0;
@@ -195,7 +195,7 @@ TESS_NOINLINE void tess_quadrant_scan(const TessImgArgs& a, int32_t* labels, lon
                 const double dy = __dsub_rn(a.y0 + (double)(qy0 + r0 + j), g.y);
                 double d = __dadd_rn(dxx, __dmul_rn(dy, dy));
                 if (HAS_SCALE) d = __dmul_rn(d, iv);
-                if (d < bd[j]) { bd[j] = d; bi[j] = gid; }
+                if ((d < bd[j]) || ((d == bd[j]) && (gid < bi[j]))) { bd[j] = d; bi[j] = gid; }
             }
         }
 #pragma unroll
@@ -529,14 +529,16 @@ k_image_main(TessImgArgs a) {
 #pragma unroll
                 for (int r = 0; r < 4; ++r) { bs[r][0] = ukey; bs[r][1] = ukey; }
             } else {
-                // ---- evaluate the surviving candidates with the pinned formula (ascending index:
-                //      strict '<' keeps the lowest index on exact ties)
+                // ---- evaluate the surviving candidates with the pinned formula.  Lists are in no
+                //      particular order, so an exact tie (d == best so far) is only RECORDED here; the
+                //      rare warp that saw one re-evaluates with the full (distance, index) order below.
                 double bd[4][2];
 #pragma unroll
                 for (int r = 0; r < 4; ++r)
 #pragma unroll
                     for (int c = 0; c < 2; ++c) { bd[r][c] = INFINITY; bs[r][c] = 0; }
                 const int n_ev = use_leaf ? len : p_len;
+                bool tied = false;
                 for (int j = 0; j < n_ev; ++j) {
                     double2 g;
                     int e;
@@ -558,8 +560,35 @@ k_image_main(TessImgArgs a) {
                         const double dyy = __dmul_rn(dy, dy);
                         double d0 = __dadd_rn(dxx0, dyy), d1 = __dadd_rn(dxx1, dyy);
                         if (HAS_SCALE) { d0 = __dmul_rn(d0, inv); d1 = __dmul_rn(d1, inv); }
+                        tied = tied || (d0 == bd[r][0]) || (d1 == bd[r][1]);
                         if (d0 < bd[r][0]) { bd[r][0] = d0; bs[r][0] = e; }
                         if (d1 < bd[r][1]) { bd[r][1] = d1; bs[r][1] = e; }
+                    }
+                }
+                if (__any_sync(TESS_FULL, tied)) {
+                    // exact ties: lowest generator index wins
+                    int bg[4][2];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) { bd[r][c] = INFINITY; bs[r][c] = 0; bg[r][c] = 0x7fffffff; }
+                    for (int j = 0; j < n_ev; ++j) {
+                        int e;
+                        if (use_leaf) e = ls[j];
+                        else e = p_ident ? j : (int)pl[j];
+                        const double2 g = qxy[e];
+                        const double inv = HAS_SCALE ? qinv[e] : 1.0;
+                        const int gid = gidv[e];
+#pragma unroll
+                        for (int r = 0; r < 4; ++r)
+#pragma unroll
+                            for (int c = 0; c < 2; ++c) {
+                                double d = tess_d2_pinned(c ? X1 : X0, Y[r], g.x, g.y);
+                                if (HAS_SCALE) d = __dmul_rn(d, inv);
+                                if ((d < bd[r][c]) || ((d == bd[r][c]) && (gid < bg[r][c]))) {
+                                    bd[r][c] = d; bs[r][c] = e; bg[r][c] = gid;
+                                }
+                            }
                     }
                 }
                 __syncwarp();                              // the leaves' lists differ in length

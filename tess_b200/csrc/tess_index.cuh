@@ -130,7 +130,7 @@ TESS_DEVFN TessRect tess_tile_rect(const TessTiles& T, int t) {
 // ---------------------------------------------------------------------------------------------
 // Per-quadrant candidate lists.  A quadrant is a 32x32-px quarter of a tile; its list holds every
 // generator that can be nearest to some pixel of the quadrant, as arena records (coordinates,
-// generator index[, 1/scale^2]) in ascending generator index.
+// generator index[, 1/scale^2]) in no particular order (the evaluators break exact ties by index).
 struct TessQLists {
     int* q_off;        // [nqx*nqy] first arena record of the quadrant's list
     int* q_cnt;        // [nqx*nqy] records; 0: quadrant outside the window; -1: overflow -> scan all generators
@@ -142,6 +142,7 @@ struct TessQLists {
 };
 
 #define TESS_LIST_WARPS 2
+#define TESS_LEAF_MIN_BUILD 3   // tile lists up to this length are handed to every quadrant unfiltered
 
 // One warp per 64x64 tile (grid-stride).
 //  1. Box search: the generators of the grid cells within `ring` cells of the tile are scanned for
@@ -149,19 +150,17 @@ struct TessQLists {
 //     provably too far, (ring cs)^2 min_inv > R -- the search radius is bounded by the LARGEST scale.
 //  2. The box generators with mind2 [* inv_s2] <= R are staged in shared memory: no other generator
 //     can be nearest to any pixel of the tile.
-//  3. They are sorted by generator index (bitonic): every list derived from a sorted list by an
-//     order-preserving compaction lets the evaluators implement "lowest index wins an exact tie"
-//     with a strict '<'.
-//  4. Each of the four quadrants keeps those that pass the centre + radius test
+//  3. Each of the four quadrants keeps those that pass the centre + radius test
 //     u(c,g) <= min_h u(c,h) + 2 rho / s_min and writes them to the arena.
 template <bool HAS_SCALE>
 __global__ void __launch_bounds__(TESS_LIST_WARPS * 32)
 k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cell_start, const int* cell_items,
-               const double2* cell_xy, const double* cell_inv, TessQLists L) {
+               const double2* cell_xy, const double* cell_inv, TessQLists L, int* tile_ring) {
     if (TESS_STOPPED(st, honor)) return;
     __shared__ __align__(16) double2 s_xy[TESS_LIST_WARPS][TESS_CAP];
     __shared__ double s_iv[HAS_SCALE ? TESS_LIST_WARPS : 1][HAS_SCALE ? TESS_CAP : 1];
     __shared__ unsigned long long s_key[TESS_LIST_WARPS][TESS_CAP];
+    __shared__ int s_cnt[TESS_LIST_WARPS];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int warp = blockIdx.x * TESS_LIST_WARPS + wib;
     const int n_warps = gridDim.x * TESS_LIST_WARPS;
@@ -177,16 +176,17 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
         const int ci0 = tess_cell_coord(r.x0, g.ox, g.inv_cs, g.gw), ci1 = tess_cell_coord(r.x1, g.ox, g.inv_cs, g.gw);
         const int cj0 = tess_cell_coord(r.y0, g.oy, g.inv_cs, g.gh), cj1 = tess_cell_coord(r.y1, g.oy, g.inv_cs, g.gh);
 
-        // ---- 1. box search for R
+        // ---- 1. box search for R.  Box rows are walked 32 at a time, one row per lane; a chunk whose
+        //      rows hold few generators is walked row-parallel (every lane its own row), a dense one
+        //      row by row with all lanes.  The ring starts near the one that sufficed last time.
         double rbest;
-        int ring = 1;
+        int ring = max(1, (tile_ring[t] * 3) / 4);
         int xi0, xi1, xj0, xj1;
         for (;;) {
             xi0 = max(ci0 - ring, 0); xi1 = min(ci1 + ring, g.gw - 1);
             xj0 = max(cj0 - ring, 0); xj1 = min(cj1 + ring, g.gh - 1);
             rbest = INFINITY;
             for (int j0 = xj0; j0 <= xj1; j0 += 32) {
-                // one box row per lane: its cells are one contiguous slot range
                 const int j = j0 + lane;
                 int s = 0, e = 0;
                 if (j <= xj1) {
@@ -194,13 +194,24 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
                     e = cell_start[(long)j * g.gw + xi1 + 1];
                 }
                 const int rows = min(32, xj1 - j0 + 1);
-                for (int src = 0; src < rows; ++src) {
-                    const int ss = __shfl_sync(TESS_FULL, s, src), ee = __shfl_sync(TESS_FULL, e, src);
-                    for (int i = ss + lane; i < ee; i += 32) {
+                const int tot = __reduce_add_sync(TESS_FULL, e - s);
+                if (tot <= 6 * rows) {
+                    for (int i = s; i < e; ++i) {
                         const double2 p = cell_xy[i];
                         double d = tess_maxd2(r, p.x, p.y);
                         if (HAS_SCALE) d *= cell_inv[i];
                         rbest = fmin(rbest, d);
+                    }
+                    __syncwarp();
+                } else {
+                    for (int src = 0; src < rows; ++src) {
+                        const int ss = __shfl_sync(TESS_FULL, s, src), ee = __shfl_sync(TESS_FULL, e, src);
+                        for (int i = ss + lane; i < ee; i += 32) {
+                            const double2 p = cell_xy[i];
+                            double d = tess_maxd2(r, p.x, p.y);
+                            if (HAS_SCALE) d *= cell_inv[i];
+                            rbest = fmin(rbest, d);
+                        }
                     }
                 }
             }
@@ -212,10 +223,12 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
             if (lb * lb * min_inv > rbest * TESS_SLACK) break;
             ring *= 2;
         }
+        if (lane == 0) tile_ring[t] = ring;
         const double thr = rbest * TESS_SLACK;
 
-        // ---- 2. stage every generator of the box with mind2 [* inv_s2] <= R
-        int cnt = 0;   // warp-uniform
+        // ---- 2. stage every generator of the box with mind2 [* inv_s2] <= R (any order: sorted below)
+        if (lane == 0) s_cnt[wib] = 0;
+        __syncwarp();
         for (int j0 = xj0; j0 <= xj1; j0 += 32) {
             const int j = j0 + lane;
             int s = 0, e = 0;
@@ -224,132 +237,140 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
                 e = cell_start[(long)j * g.gw + xi1 + 1];
             }
             const int rows = min(32, xj1 - j0 + 1);
-            for (int src = 0; src < rows; ++src) {
-                const int ss = __shfl_sync(TESS_FULL, s, src), ee = __shfl_sync(TESS_FULL, e, src);
-                for (int i0 = ss; i0 < ee; i0 += 32) {
-                    const int i = i0 + lane;
-                    bool keep = false;
-                    double2 p = make_double2(0.0, 0.0);
-                    double pv = 1.0;
-                    if (i < ee) {
-                        p = cell_xy[i];
-                        double d = tess_mind2(r, p.x, p.y);
-                        if (HAS_SCALE) { pv = cell_inv[i]; d *= pv; }
-                        keep = d <= thr;
-                    }
-                    const unsigned b = __ballot_sync(TESS_FULL, keep);
-                    const int pos = cnt + __popc(b & tess_lanemask_lt(lane));
-                    if (keep && pos < TESS_CAP) {
+            const int tot = __reduce_add_sync(TESS_FULL, e - s);
+            auto take = [&](int i) {
+                const double2 p = cell_xy[i];
+                double d = tess_mind2(r, p.x, p.y);
+                double pv = 1.0;
+                if (HAS_SCALE) { pv = cell_inv[i]; d *= pv; }
+                if (d <= thr) {
+                    const int pos = atomicAdd(&s_cnt[wib], 1);
+                    if (pos < TESS_CAP) {
                         xy[pos] = p;
                         if (HAS_SCALE) iv[pos] = pv;
                         key[pos] = (unsigned long long)(unsigned)i;      // slot for now
                     }
-                    cnt += __popc(b);
                 }
-            }
-        }
-        __syncwarp();
-        const bool overflow = cnt > TESS_CAP;
-
-        // ---- 3. sort by generator index; the low word carries the staging position
-        if (!overflow) {
-            for (int i = lane; i < cnt; i += 32)
-                key[i] = ((unsigned long long)(unsigned)cell_items[(int)key[i]] << 32) | (unsigned)i;
-            int n2 = 1;
-            while (n2 < cnt) n2 <<= 1;
-            for (int i = cnt + lane; i < n2; i += 32) key[i] = ~0ull;
-            __syncwarp();
-            for (int k2 = 2; k2 <= n2; k2 <<= 1) {
-                for (int j = k2 >> 1; j > 0; j >>= 1) {
-                    for (int i = lane; i < n2; i += 32) {
-                        const int ixj = i ^ j;
-                        if (ixj > i) {
-                            const unsigned long long va = key[i], vb = key[ixj];
-                            const bool up = ((i & k2) == 0);
-                            if ((va > vb) == up) { key[i] = vb; key[ixj] = va; }
-                        }
-                    }
+            };
+            if (tot <= 6 * rows) {
+                for (int i = s; i < e; ++i) take(i);
+                __syncwarp();
+            } else {
+                for (int src = 0; src < rows; ++src) {
+                    const int ss = __shfl_sync(TESS_FULL, s, src), ee = __shfl_sync(TESS_FULL, e, src);
+                    for (int i = ss + lane; i < ee; i += 32) take(i);
                     __syncwarp();
                 }
             }
         }
+        __syncwarp();
+        const int cnt = s_cnt[wib];   // warp-uniform
+        const bool overflow = cnt > TESS_CAP;
 
-        // ---- 4. the four quadrants
+        // ---- 3. generator indices of the staged candidates
+        if (!overflow)
+            for (int i = lane; i < cnt; i += 32) key[i] = (unsigned long long)(unsigned)cell_items[(int)key[i]];
+        __syncwarp();
+
+        // ---- 4. the four quadrants: one pass for the four centre minima, one for the keep flags
+        //      (entry i = 32 b + lane -> bit b of the lane's flag word), one arena reservation for
+        //      the tile, then the writes
+        const bool whole_tile = ((long)(tx + 1) * TESS_TS <= T.W) && ((long)(ty + 1) * TESS_TS <= T.H);
+        double qcx[4], qcy[4], qthr[4];
+        bool qin[4];
+#pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const int qx = 2 * tx + (q & 1), qy = 2 * ty + (q >> 1);
             const long px0 = (long)tx * TESS_TS + 32 * (q & 1), py0 = (long)ty * TESS_TS + 32 * (q >> 1);
-            const long qid = (long)qy * L.nqx + qx;
-            if (px0 >= T.W || py0 >= T.H) {
-                if (lane == 0) { L.q_off[qid] = 0; L.q_cnt[qid] = 0; }
-                continue;
-            }
-            if (overflow) {
-                if (lane == 0) { L.q_off[qid] = 0; L.q_cnt[qid] = -1; atomicAdd(&st->n_brute, 1); }
-                continue;
-            }
             const long px1 = min(px0 + 31, T.W - 1), py1 = min(py0 + 31, T.H - 1);
-            const double ccx = T.x0 + 0.5 * (double)(px0 + px1), ccy = T.y0 + 0.5 * (double)(py0 + py1);
+            qin[q] = (px0 < T.W) && (py0 < T.H);
+            qcx[q] = T.x0 + 0.5 * (double)(px0 + px1);
+            qcy[q] = T.y0 + 0.5 * (double)(py0 + py1);
             const double hx = 0.5 * (double)(px1 - px0), hy = 0.5 * (double)(py1 - py0);
-            const double rho = sqrt(hx * hx + hy * hy) * 1.0000001;
-            double umin = INFINITY, imax = 1.0;
+            qthr[q] = whole_tile ? 21.920310216783 : sqrt(fmax(hx * hx + hy * hy, 0.0)) * 1.0000001;   // rho (15.5 sqrt 2)
+        }
+        unsigned bits[4] = {0u, 0u, 0u, 0u};
+        int nq_[4] = {0, 0, 0, 0};
+        if (!overflow && cnt > TESS_LEAF_MIN_BUILD) {
+            double umin[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+            double imax = 1.0;
             for (int i = lane; i < cnt; i += 32) {
-                const int ix = (int)(unsigned)key[i];
-                const double2 p = xy[ix];
-                const double dx = ccx - p.x, dy = ccy - p.y;
-                double d = dx * dx + dy * dy;
-                if (HAS_SCALE) { const double v = iv[ix]; d *= v; imax = fmax(imax, v); }
-                umin = fmin(umin, d);
+                const double2 p = xy[i];
+                double v = 1.0;
+                if (HAS_SCALE) { v = iv[i]; imax = fmax(imax, v); }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double dx = qcx[q] - p.x, dy = qcy[q] - p.y;
+                    double d = dx * dx + dy * dy;
+                    if (HAS_SCALE) d *= v;
+                    umin[q] = fmin(umin[q], d);
+                }
             }
-            umin = tess_warp_min(umin);
-            double c = 2.0 * rho;
+            double cs = 1.0;
             if (HAS_SCALE) {
                 imax = -tess_warp_min(-imax);
-                c *= (double)sqrtf((float)imax) * 1.000001 + 1e-18;
+                cs = (double)sqrtf((float)imax) * 1.000001 + 1e-18;
             }
-            const double su = (double)sqrtf((float)umin) * 1.000001 + 1e-18;      // >= sqrt(umin)
-            const double qthr = (umin + 2.0 * c * su + c * c) * TESS_SLACK;
-            // keep flags of this lane's entries (entry i = 32 b + lane -> bit b), then the count
-            unsigned bits = 0;
-            int n = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double um = tess_warp_min(umin[q]);
+                const double c = 2.0 * qthr[q] * cs;
+                const double su = (double)sqrtf((float)um) * 1.000001 + 1e-18;      // >= sqrt(umin)
+                qthr[q] = (um + 2.0 * c * su + c * c) * TESS_SLACK;
+            }
             for (int b = 0; 32 * b < cnt; ++b) {
                 const int i = 32 * b + lane;
-                bool keep = false;
-                if (i < cnt) {
-                    const int ix = (int)(unsigned)key[i];
-                    const double2 p = xy[ix];
-                    const double dx = ccx - p.x, dy = ccy - p.y;
+                double2 p = make_double2(0.0, 0.0);
+                double v = 1.0;
+                if (i < cnt) { p = xy[i]; if (HAS_SCALE) v = iv[i]; }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double dx = qcx[q] - p.x, dy = qcy[q] - p.y;
                     double d = dx * dx + dy * dy;
-                    if (HAS_SCALE) d *= iv[ix];
-                    keep = d <= qthr;
+                    if (HAS_SCALE) d *= v;
+                    const bool keep = (i < cnt) && qin[q] && (d <= qthr[q]);
+                    if (keep) bits[q] |= 1u << b;
+                    nq_[q] += __popc(__ballot_sync(TESS_FULL, keep));
                 }
-                if (keep) bits |= 1u << b;
-                n += __popc(__ballot_sync(TESS_FULL, keep));
             }
-            unsigned off = 0;
-            int ok = 1;
+        } else if (!overflow) {
+            // a handful of candidates: every quadrant takes them all
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (qin[q]) { bits[q] = (lane < cnt) ? 1u : 0u; nq_[q] = cnt; }
+            }
+        }
+        const int n_all = nq_[0] + nq_[1] + nq_[2] + nq_[3];
+        unsigned off = 0;
+        int ok = overflow ? 0 : 1;
+        if (lane == 0 && ok) {
+            off = atomicAdd(&st->list_cursor, (unsigned)n_all);
+            if (off + (unsigned)n_all > L.capacity) ok = 0;
+        }
+        off = __shfl_sync(TESS_FULL, off, 0);
+        ok = __shfl_sync(TESS_FULL, ok, 0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const long qid = (long)(2 * ty + (q >> 1)) * L.nqx + (2 * tx + (q & 1));
             if (lane == 0) {
-                off = atomicAdd(&st->list_cursor, (unsigned)n);
-                if (off + (unsigned)n > L.capacity) ok = 0;
                 L.q_off[qid] = ok ? (int)off : 0;
-                L.q_cnt[qid] = ok ? n : -1;
-                if (!ok) atomicAdd(&st->n_brute, 1);
+                L.q_cnt[qid] = !qin[q] ? 0 : (ok ? nq_[q] : -1);
+                if (!ok && qin[q]) atomicAdd(&st->n_brute, 1);
             }
-            off = __shfl_sync(TESS_FULL, off, 0);
-            ok = __shfl_sync(TESS_FULL, ok, 0);
-            if (!ok) continue;
-            int wpos = 0;
-            for (int b = 0; 32 * b < cnt; ++b) {
-                const bool keep = (bits >> b) & 1u;
-                const unsigned bb = __ballot_sync(TESS_FULL, keep);
-                if (keep) {
-                    const unsigned long long kv = key[32 * b + lane];
-                    const int ix = (int)(unsigned)kv;
-                    const unsigned o = off + wpos + __popc(bb & tess_lanemask_lt(lane));
-                    L.xy[o] = xy[ix];
-                    L.gid[o] = (int)(kv >> 32);
-                    if (HAS_SCALE) L.inv[o] = iv[ix];
+            if (ok && qin[q]) {
+                int wpos = 0;
+                for (int b = 0; 32 * b < cnt; ++b) {
+                    const bool keep = (bits[q] >> b) & 1u;
+                    const unsigned bb = __ballot_sync(TESS_FULL, keep);
+                    if (keep) {
+                        const int i = 32 * b + lane;
+                        const unsigned o = off + wpos + __popc(bb & tess_lanemask_lt(lane));
+                        L.xy[o] = xy[i];
+                        L.gid[o] = (int)(unsigned)key[i];
+                        if (HAS_SCALE) L.inv[o] = iv[i];
+                    }
+                    wpos += __popc(bb);
                 }
-                wpos += __popc(bb);
+                off += (unsigned)nq_[q];
             }
         }
         __syncwarp();

@@ -113,6 +113,16 @@ static inline unsigned __ballot_sync(unsigned mask, int pred) {
     c.warp_bar->arrive_and_wait();
     return r;
 }
+static inline int __reduce_add_sync(unsigned mask, int v) {
+    assert(mask == 0xffffffffu);
+    auto& c = emu::tctx;
+    c.xchg[c.lane] = (uint64_t)(int64_t)v;
+    c.warp_bar->arrive_and_wait();
+    int r = 0;
+    for (int i = 0; i < 32; ++i) r += (int)(int64_t)c.xchg[i];
+    c.warp_bar->arrive_and_wait();
+    return r;
+}
 static inline int __reduce_max_sync(unsigned mask, int v) {
     assert(mask == 0xffffffffu);
     auto& c = emu::tctx;
