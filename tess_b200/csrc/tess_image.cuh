@@ -102,14 +102,17 @@ TESS_DEVFN void tess_cp_async_wait() {
 }
 
 // Lanes with `flush` set add their run (key, n, v) to the warp's table.  Lanes holding the same key
-// take turns (match.any elects one lane per distinct key per turn), so plain read-modify-writes are
-// enough.  All 32 lanes must call; no divergence.
+// take turns: every pending lane writes its id to claim[key], the one whose id survives does a plain
+// read-modify-write, the others try again (warp-level aggregation without atomics: the table is
+// private to the warp).  All 32 lanes must call; no divergence.
 template <int NV>
-TESS_DEVFN void tess_table_flush(bool flush, int key, int n, const double (&v)[NV], double* tab, int lane) {
+TESS_DEVFN void tess_table_flush(bool flush, int key, int n, const double (&v)[NV], double* tab,
+                                 unsigned short* claim, int lane) {
     bool pending = flush;
     while (__any_sync(TESS_FULL, pending)) {
-        const unsigned grp = __match_any_sync(TESS_FULL, pending ? key : -1 - lane);
-        if (pending && lane == __ffs((int)grp) - 1) {
+        if (pending) claim[key] = (unsigned short)lane;
+        __syncwarp();
+        if (pending && claim[key] == (unsigned short)lane) {
             double* t = tab + key * (NV + 1);
             t[0] += (double)n;
 #pragma unroll
@@ -356,6 +359,7 @@ struct TessWarpSmem {
     double li[HAS_SCALE ? 4 : 1][HAS_SCALE ? TESS_LEAF_CAP : 1];   //   1/scale^2,
     unsigned short ls[4][TESS_LEAF_CAP];                     //   quadrant-list position
     unsigned short bl[2][TESS_BCAP];                         // 16x16 block lists (positions)
+    unsigned short claim[(MODE != 0) ? QC : 1];              // election of the lane that adds to a table entry
 };
 
 // MODE 0: labels only; 1: density map (4 moments); 2: signal + noise maps (6 moments)
@@ -634,7 +638,7 @@ k_image_main(TessImgArgs a) {
                 // closed form for a one-bin patch: sum w x = X0 col0 + X1 col1, sum w y = sum_r Y_r row_r
                 const bool sw = (cur.key != ukey);
                 if (__any_sync(TESS_FULL, sw)) {
-                    tess_table_flush<NV>(sw && cur.n > 0, cur.key, cur.n, cur.v, tab, lane);
+                    tess_table_flush<NV>(sw && cur.n > 0, cur.key, cur.n, cur.v, tab, sm.claim, lane);
                     cur.key = ukey;
                     cur.n = sw ? 0 : cur.n;
 #pragma unroll
@@ -674,7 +678,7 @@ k_image_main(TessImgArgs a) {
                     for (int r = 0; r < 4; ++r) present = present || (bs[r][0] == cur.key) || (bs[r][1] == cur.key);
                     const bool sw = (rest >= 0) && !present;
                     if (__any_sync(TESS_FULL, sw)) {
-                        tess_table_flush<NV>(sw && cur.n > 0, cur.key, cur.n, cur.v, tab, lane);
+                        tess_table_flush<NV>(sw && cur.n > 0, cur.key, cur.n, cur.v, tab, sm.claim, lane);
                         cur.key = sw ? rest : cur.key;
                         cur.n = sw ? 0 : cur.n;
 #pragma unroll
