@@ -380,8 +380,8 @@ k_image_main(TessImgArgs a) {
     const int blk = cx >> 3;                           // 16-px-wide block
     double* const tab = sm.tab;
     const double* const src = (MODE == 2) ? a.sig : a.dens;   // MODE 1: weight map; MODE 2: signal map
-    const long n_q = (long)a.L.nqx * a.L.nqy;
-    const long stride = (long)gridDim.x * NW;
+    const int n_q = a.L.nqx * a.L.nqy;               // < 2^31 (checked by the host)
+    const int stride = (int)gridDim.x * NW;
 
     TessRun<NV> cur;                 // the lane's running same-bin sum (registers)
     cur.key = -1;
@@ -392,9 +392,9 @@ k_image_main(TessImgArgs a) {
     // ---- software pipeline over this warp's quadrants q, q + stride, ...: the list of quadrant i+1 is
     //      copied to shared memory (cp.async) while quadrant i is processed; (offset, count) of
     //      quadrant i+2 are loaded at the same time.
-    long q = (long)blockIdx.x * NW + wib;
+    int q = (int)blockIdx.x * NW + wib;
     int cnt = (q < n_q) ? a.L.q_cnt[q] : 0, off = (q < n_q) ? a.L.q_off[q] : 0;
-    long q1 = q + stride;
+    int q1 = q + stride;
     int cnt1 = (q1 < n_q) ? a.L.q_cnt[q1] : 0, off1 = (q1 < n_q) ? a.L.q_off[q1] : 0;
     int buf = 0;
     auto stage = [&](int b, int o, int n) {
@@ -410,14 +410,14 @@ k_image_main(TessImgArgs a) {
 
     while (q < n_q) {
         // (offset, count) of the quadrant after the next: in flight during this quadrant
-        const long q2 = q1 + stride;
+        const int q2 = q1 + stride;
         int cnt2 = 0, off2 = 0;
         if (q2 < n_q) { cnt2 = a.L.q_cnt[q2]; off2 = a.L.q_off[q2]; }
         tess_cp_async_wait();          // this quadrant's list has landed
         __syncwarp();
         if (q1 < n_q) stage(buf ^ 1, off1, cnt1);
         const int cnt_cur = cnt, off_cur = off;
-        const int qx = (int)(q % a.L.nqx), qy = (int)(q / a.L.nqx);
+        const int qy = q / a.L.nqx, qx = q - qy * a.L.nqx;
         const long qx0 = 32L * qx, qy0 = 32L * qy;
         if (cnt_cur != 0) {
         if (cnt_cur < 0 || cnt_cur > QC) {
