@@ -269,6 +269,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-single", action="store_true", help="N>1: skip rank 0's one-GPU run of the same map")
+    ap.add_argument("--fake-shard", default=None, metavar="R/N",
+                    help="profiling aid on ONE GPU: process only the rows of rank R of N (no collective)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -292,6 +294,11 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     N, k, mode = wl["N"], wl["k"], args.mode
     r0, r1 = shard_rows(N, world)[rank]
+    fake = None
+    if args.fake_shard and world == 1:
+        fr, fn = (int(x) for x in args.fake_shard.split("/"))
+        r0, r1 = shard_rows(N, fn)[fr]
+        fake = (fr, fn)
 
     def barrier():
         if world > 1:
@@ -312,6 +319,8 @@ def main():
     def setup(e, r0, r1):
         m = maps(r0, r1)
         e.set_image(y0=float(r0), **m)
+        if (r1 - r0) != N:
+            e.set_domain(0.0, 0.0, float(N), float(N))      # the generator table spans the full image
         e.set_generators(seeds)
 
     def step(n=1):
@@ -342,6 +351,8 @@ def main():
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
     value = (float(N) * N) / (ms_step * 1e-3) / 1e9
+    if fake is not None:
+        value = (float(r1 - r0) * N) / (ms_step * 1e-3) / 1e9
     conv, _ = eng.status()
 
     # ---- dominant kernel, timed live with CUDA events on its own stream (second pass)
@@ -382,6 +393,8 @@ def main():
 
         def e2e_step():
             e2.set_image(y0=float(r0), **host_in)          # H2D of this step's maps (pinned -> device)
+            if (r1 - r0) != N:
+                e2.set_domain(0.0, 0.0, float(N), float(N))
             e2.set_generators(seeds_pin)                    # H2D of the generator table
             (d2.step(1) if d2 is not None else e2.step(1))
             lab_pin.copy_(e2.labels(), non_blocking=True)   # D2H of the results
@@ -444,7 +457,7 @@ def main():
                            "bytes_per_px": BYTES_PER_PX[mode], "parallelism": "rows x%d + allreduce(moments)" % world if world > 1 else "1 GPU",
                            "l2": "inputs (%.0f MB per GPU) larger than L2 (126 MB); no flush needed" % (
                                (BYTES_PER_PX[mode] - 4) * (r1 - r0) * N / 1e6),
-                           "converged_during_run": bool(conv)},
+                           "converged_during_run": bool(conv), "fake_shard": args.fake_shard},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roof, "cpu_baseline": cpu}
         if single is not None:
             line["single_gpu_same_workload"] = single

@@ -101,6 +101,16 @@ int tess_set_image(tess_ctx* ctx, long H, long W, double x0, double y0, const do
                    const double* signal, const double* noise, void* stream);
 
 /*
+ * Optional: the rectangle [x0, x1] x [y0, y1] that contains (nearly) all generators.  The uniform
+ * grid that indexes the generators covers the union of this rectangle and the pixel window;
+ * generators outside it are clamped into its border cells (still exact, but slow if many).  A
+ * row-sharded rank passes the FULL image here so that the replicated generator table is binned
+ * properly although the rank's own window is only a slab.  Default: the pixel window itself.
+ * x1 < x0 clears it.
+ */
+int tess_set_domain(tess_ctx* ctx, double x0, double y0, double x1, double y1);
+
+/*
  * Point mode -- the `xy`, `w` arguments of lloyd() (reference tess/lloyd.pyx:10-11):
  * xy is AoS [n][2], w is [n].  Points are binned once into spatial tiles (a sorted copy is
  * kept in the context's workspace); labels are returned in the caller's point order.

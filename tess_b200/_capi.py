@@ -34,6 +34,7 @@ SIGNATURES = {
     "tess_ctx_destroy": (_i, [_vp]),
     "tess_set_option": (_i, [_vp, _i, _l]),
     "tess_set_image": (_i, [_vp, _l, _l, _d, _d, _vp, _vp, _vp, _vp]),
+    "tess_set_domain": (_i, [_vp, _d, _d, _d, _d]),
     "tess_set_points": (_i, [_vp, _l, _vp, _vp, _vp]),
     "tess_set_generators": (_i, [_vp, _l, _vp, _vp, _vp]),
     "tess_lloyd_accumulate": (_i, [_vp, _vp]),

@@ -61,6 +61,8 @@ struct tess_ctx {
     long n_pts;
     const double *pts_xy, *pts_w;
     double pb[4];   // bounding box of the points (x0, x1, y0, y1)
+    int has_domain;
+    double dom[4];  // generator domain (x0, y0, x1, y1)
     // ---- generators (owned)
     int k, k_cap;
     double* node;     // [k][2]
@@ -228,6 +230,16 @@ extern "C" int tess_set_image(tess_ctx* c, long H, long W, double x0, double y0,
     return TESS_OK;
 }
 
+extern "C" int tess_set_domain(tess_ctx* c, double x0, double y0, double x1, double y1) {
+    TRY(bind(c));
+    if (!(x1 >= x0) || !(y1 >= y0)) { c->has_domain = 0; return TESS_OK; }
+    if (!isfinite(x0) || !isfinite(y0) || !isfinite(x1) || !isfinite(y1))
+        return tess_fail(TESS_ERR_ARG, "tess_set_domain: non-finite rectangle");
+    c->has_domain = 1;
+    c->dom[0] = x0; c->dom[1] = y0; c->dom[2] = x1; c->dom[3] = y1;
+    return TESS_OK;
+}
+
 // bounding box of a point set: block partial min/max -> atomics on the bit patterns is avoided by
 // a single-CTA pass (n is at most a few million in point mode)
 __global__ void __launch_bounds__(1024) k_points_bbox(const double* xy, long n, double* out) {
@@ -324,17 +336,30 @@ struct Geometry {
     int n_cells;
 };
 
-// Grid for an H x W pixel window at (x0, y0): one cell per 64-px super-tile, generators outside
-// the window are clamped into the border cells.
-static Geometry window_geometry(double x0, double y0, long H, long W) {
+// Grid for an H x W pixel window at (x0, y0): 64-px cells over the window (united with the generator
+// domain if one was given); generators outside are clamped into the border cells.
+static Geometry window_geometry(const tess_ctx* c, double x0, double y0, long H, long W) {
     Geometry q;
     q.T.x0 = x0; q.T.y0 = y0; q.T.W = W; q.T.H = H;
     q.T.tiles_x = (int)((W + TESS_TS - 1) / TESS_TS);
     q.T.tiles_y = (int)((H + TESS_TS - 1) / TESS_TS);
     q.T.n_tiles = q.T.tiles_x * q.T.tiles_y;
-    q.g.ox = x0; q.g.oy = y0; q.g.cs = (double)TESS_TS; q.g.inv_cs = 1.0 / (double)TESS_TS;
-    q.g.gw = q.T.tiles_x; q.g.gh = q.T.tiles_y;
-    const double ext = fmax(fabs(x0) + (double)W, fabs(y0) + (double)H) + q.g.cs;
+    const double cs = (double)TESS_TS;
+    double gx0 = x0, gy0 = y0, gx1 = x0 + (double)W, gy1 = y0 + (double)H;
+    if (c->has_domain) {
+        // extend by whole cells so that tiles stay aligned with cells
+        if (c->dom[0] < gx0) gx0 -= cs * ceil((gx0 - c->dom[0]) / cs);
+        if (c->dom[1] < gy0) gy0 -= cs * ceil((gy0 - c->dom[1]) / cs);
+        if (c->dom[2] > gx1) gx1 = c->dom[2];
+        if (c->dom[3] > gy1) gy1 = c->dom[3];
+    }
+    double fw = ceil((gx1 - gx0) / cs), fh = ceil((gy1 - gy0) / cs);
+    if (fw * fh > 6.4e7) {   // cap the grid (16k x 4k cells); farther generators are clamped
+        gx0 = x0; gy0 = y0; fw = (double)q.T.tiles_x; fh = (double)q.T.tiles_y;
+    }
+    q.g.ox = gx0; q.g.oy = gy0; q.g.cs = cs; q.g.inv_cs = 1.0 / cs;
+    q.g.gw = (int)(fw < 1.0 ? 1.0 : fw); q.g.gh = (int)(fh < 1.0 ? 1.0 : fh);
+    const double ext = fmax(fmax(fabs(gx0), fabs(gx1)), fmax(fabs(gy0), fabs(gy1))) + cs;
     q.g.tol = ext * 9.094947017729282e-13 /* 2^-40 */;
     q.n_cells = q.g.gw * q.g.gh;
     return q;
@@ -569,7 +594,7 @@ extern "C" int tess_lloyd_accumulate(tess_ctx* c, void* stream) {
     const long n_mom = (long)c->k * M + TESS_TAIL;
     long n;
     if (c->source == SRC_IMAGE) {
-        Geometry q = window_geometry(c->x0, c->y0, c->H, c->W);
+        Geometry q = window_geometry(c, c->x0, c->y0, c->H, c->W);
         TRY(build_index(c, q, 1, c->mom, n_mom, s));
         TRY(build_lists(c, q, 1, s));
         timing_mark(c, s, 0);
@@ -738,7 +763,7 @@ extern "C" int tess_assign_grid(tess_ctx* c, double x0, double y0, long H, long 
     if (c->k <= 0) return tess_fail(TESS_ERR_STATE, "tess_assign_grid: call tess_set_generators first");
     if (H <= 0 || W <= 0 || !labels_out) return tess_fail(TESS_ERR_ARG, "tess_assign_grid: bad arguments");
     cudaStream_t s = S(stream);
-    Geometry q = window_geometry(x0, y0, H, W);
+    Geometry q = window_geometry(c, x0, y0, H, W);
     TRY(build_index(c, q, 0, nullptr, 0, s));
     TRY(build_lists(c, q, 0, s));
     TRY(run_image(c, q, 0, 0, labels_out, s));

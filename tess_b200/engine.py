@@ -126,6 +126,11 @@ class Engine(object):
         self._keep["input"] = arrs
         self.shape, self.n, self.source = (H, W), H * W, "image"
 
+    def set_domain(self, x0, y0, x1, y1):
+        """Rectangle containing (nearly) all generators: the generator grid covers it (a row-sharded
+        rank passes the full image; see include/tess_b200.h)."""
+        self.api.call("tess_set_domain", self.ctx, float(x0), float(y0), float(x1), float(y1))
+
     def set_points(self, xy, w):
         """Point-set mode: the `xy`, `w` arguments of lloyd() (reference tess/lloyd.pyx:10-11)."""
         xy = self._to_dev(xy)

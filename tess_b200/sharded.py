@@ -42,9 +42,13 @@ class ShardedLloyd(object):
         self._view = None
 
     # ------------------------------------------------------------------ inputs
-    def set_image_rows(self, density=None, signal=None, noise=None, row0=0, x0=0.0, y0=0.0):
-        """This rank's rows of the maps; `row0` is the global index of its first row."""
+    def set_image_rows(self, density=None, signal=None, noise=None, row0=0, x0=0.0, y0=0.0, total_rows=None):
+        """This rank's rows of the maps; `row0` is the global index of its first row, `total_rows` the
+        height of the full image (the replicated generator table is binned over the full image)."""
         self.eng.set_image(density=density, signal=signal, noise=noise, x0=x0, y0=float(y0) + float(row0))
+        if total_rows is not None:
+            W = self.eng.shape[1]
+            self.eng.set_domain(float(x0), float(y0), float(x0) + W, float(y0) + float(total_rows))
         self._view = None
 
     def set_generators(self, node_xy, scale=None):

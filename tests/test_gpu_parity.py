@@ -207,8 +207,8 @@ def test_fake_sharding_equals_single_engine(engine_cls):
     seeds = sampled_seeds(w, k, seed=3)
     one, a, b = engine_cls(0), engine_cls(0), engine_cls(0)
     one.set_image(density=w); one.set_generators(seeds)
-    a.set_image(density=w[:256], y0=0.0); a.set_generators(seeds)
-    b.set_image(density=w[256:], y0=256.0); b.set_generators(seeds)
+    a.set_image(density=w[:256], y0=0.0); a.set_domain(0.0, 0.0, N, N); a.set_generators(seeds)
+    b.set_image(density=w[256:], y0=256.0); b.set_domain(0.0, 0.0, N, N); b.set_generators(seeds)
     for it in range(4):
         one.step(1)
         a.accumulate(); b.accumulate()

@@ -45,7 +45,7 @@ def _worker(rank, world, port, q):
         dens = g["density"]
         r0, r1 = sr(dens.shape[0], world)[rank]
         sh = ShardedLloyd(EmuEngine())
-        sh.set_image_rows(density=dens[r0:r1], row0=r0)
+        sh.set_image_rows(density=dens[r0:r1], row0=r0, total_rows=dens.shape[0])
         sh.set_generators(g["seeds"])
         # teacher-free trajectory, checked every iteration on every rank
         T = int(g["n_iters"])
