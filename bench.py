@@ -326,6 +326,11 @@ def main():
     def step(n=1):
         if drv is not None:
             drv.step(n)
+        elif fake is not None:
+            # a lone shard must not move the generators (bins without pixels in this shard would
+            # collapse to the origin): accumulate only
+            for _ in range(n):
+                eng.accumulate()
         else:
             eng.step(n)
 

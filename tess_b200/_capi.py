@@ -50,6 +50,7 @@ SIGNATURES = {
     "tess_get_status": (_i, [_vp, ctypes.POINTER(_i), ctypes.POINTER(_i), _vp]),
     "tess_get_kernel_timing": (_i, [_vp, ctypes.POINTER(_d), ctypes.POINTER(_l)]),
     "tess_launch_count": (_l, []),
+    "tess_get_list_stats": (_i, [_vp, ctypes.POINTER(_l)]),
     "tess_assign_grid": (_i, [_vp, _d, _d, _l, _l, _vp, _vp]),
     "tess_assign_points": (_i, [_vp, _l, _vp, _vp, _vp]),
     "tess_label_sums": (_i, [_vp, _l, _vp, _vp, _l, _vp, _vp]),
@@ -134,3 +135,8 @@ class CApi(object):
 
     def launch_count(self):
         return int(self.dll.tess_launch_count())
+
+    def list_stats(self, ctx):
+        out = (_l * 4)()
+        self.call("tess_get_list_stats", ctx, out)
+        return dict(scan_all=out[0], arena_used=out[1], arena_capacity=out[2], scan_list=out[3])

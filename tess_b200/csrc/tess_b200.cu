@@ -541,6 +541,8 @@ static int run_points(tess_ctx* c, const Geometry& q, int mode, int honor, long 
     return TESS_OK;
 }
 
+static int fetch_state(tess_ctx* c, cudaStream_t s);
+
 // event bracket around the dominant kernel (TESS_OPT_KERNEL_TIMING)
 static void timing_mark(tess_ctx* c, cudaStream_t s, int end) {
 #ifndef TESS_EMU
@@ -577,6 +579,32 @@ extern "C" int tess_get_kernel_timing(tess_ctx* c, double* ms_total, long* launc
 }
 
 extern "C" long tess_launch_count(void) { return g_tess_launches; }
+
+__global__ void k_count_long_lists(const int* q_cnt, long nq, int cap, unsigned long long* out) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq && q_cnt[i] > cap) atomicAdd(out, 1ull);
+}
+
+extern "C" int tess_get_list_stats(tess_ctx* c, long* out4) {
+    TRY(bind(c));
+    if (!out4) return tess_fail(TESS_ERR_ARG, "tess_get_list_stats: out is null");
+    TRY(fetch_state(c, nullptr));
+    out4[0] = c->h_st->n_brute;
+    out4[1] = c->h_st->list_cursor;
+    out4[2] = c->ql.capacity;
+    out4[3] = 0;
+    const long nq = (long)c->ql.nqx * c->ql.nqy;
+    if (nq > 0 && c->ql.q_cnt) {
+        unsigned long long* d = (unsigned long long*)c->scratch;
+        CU_TRY(cudaMemset(d, 0, 8));
+        const int cap = (c->source == SRC_IMAGE && c->img_mode == 2) ? TESS_QCAP(2) : TESS_QCAP(1);
+        TESS_LAUNCH((k_count_long_lists), (int)((nq + 255) / 256), 256, nullptr, c->ql.q_cnt, nq, cap, d);
+        unsigned long long h = 0;
+        CU_TRY(cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost));
+        out4[3] = (long)h;
+    }
+    return TESS_OK;
+}
 
 static int check_ready(tess_ctx* c, const char* who) {
     TRY(bind(c));

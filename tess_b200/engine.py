@@ -201,6 +201,10 @@ class Engine(object):
         """(summed device ms, launches) of the dominant kernel since the last call (bench.py)."""
         return self.api.kernel_timing(self.ctx)
 
+    def list_stats(self):
+        """Diagnostics of the last candidate-list build (see tess_get_list_stats)."""
+        return self.api.list_stats(self.ctx)
+
     def status(self):
         """(converged latch, a generator became non-finite)."""
         return self.api.status(self.ctx, self._stream())
