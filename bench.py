@@ -269,6 +269,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-single", action="store_true", help="N>1: skip rank 0's one-GPU run of the same map")
+    ap.add_argument("--no-balance", dest="balance", action="store_false",
+                    help="N>1: equal-height row shards instead of cost-balanced ones")
     ap.add_argument("--fake-shard", default=None, metavar="R/N",
                     help="profiling aid on ONE GPU: process only the rows of rank R of N (no collective)")
     args = ap.parse_args()
@@ -283,7 +285,7 @@ def main():
     import torch.distributed as dist
     from tess_b200.engine import Engine
     from tess_b200 import _capi
-    from tess_b200.sharded import ShardedLloyd, shard_rows
+    from tess_b200.sharded import ShardedLloyd, shard_rows, balanced_row_shards
 
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -293,11 +295,14 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
     N, k, mode = wl["N"], wl["k"], args.mode
-    r0, r1 = shard_rows(N, world)[rank]
+    seeds_h = gauss_seeds(N, k)
+    shards = balanced_row_shards(seeds_h, N, N, world) if args.balance else shard_rows(N, world)
+    r0, r1 = shards[rank]
     fake = None
     if args.fake_shard and world == 1:
         fr, fn = (int(x) for x in args.fake_shard.split("/"))
-        r0, r1 = shard_rows(N, fn)[fr]
+        shards = balanced_row_shards(seeds_h, N, N, fn) if args.balance else shard_rows(N, fn)
+        r0, r1 = shards[fr]
         fake = (fr, fn)
 
     def barrier():
@@ -311,7 +316,6 @@ def main():
             return dict(density=(sig / 1.0) ** 2)
         return dict(signal=sig, noise=torch.ones_like(sig))
 
-    seeds_h = gauss_seeds(N, k)
     seeds = torch.from_numpy(seeds_h).to(device)
     eng = Engine(local)
     drv = ShardedLloyd(eng) if world > 1 else None
@@ -459,7 +463,8 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": wl["name"], "pixels": N * N, "generators": k, "mode": mode,
-                           "bytes_per_px": BYTES_PER_PX[mode], "parallelism": "rows x%d + allreduce(moments)" % world if world > 1 else "1 GPU",
+                           "bytes_per_px": BYTES_PER_PX[mode], "parallelism": ("rows x%d (%s) + allreduce(moments)" % (world, "cost-balanced" if args.balance else "equal")) if world > 1 else "1 GPU",
+                           "shard_rows": [list(x) for x in shards] if world > 1 or fake else None,
                            "l2": "inputs (%.0f MB per GPU) larger than L2 (126 MB); no flush needed" % (
                                (BYTES_PER_PX[mode] - 4) * (r1 - r0) * N / 1e6),
                            "converged_during_run": bool(conv), "fake_shard": args.fake_shard},

@@ -2,7 +2,7 @@
 // include/tess_b200.h.  Built for sm_100a only (tess_b200/build.py); there is no CPU path.
 //
 // One Lloyd iteration (reference tess/lloyd.pyx:47-90) is the launch sequence
-//   k_cell_count -> k_cell_scan -> k_cell_scatter        generator grid (replaces cKDTree build, :54)
+//   k_cell_count -> k_cell_blocksum -> k_cell_scan -> k_cell_scatter   generator grid (replaces cKDTree build, :54)
 //   k_build_qlists                                       per-quadrant candidate lists (sorted, in an arena)
 //   k_image_main | k_points_main                         assignment (:55) fused with the sums (:58-65)
 //   k_count_prefilter -> k_compare_labels                "did any label change" (convergence, :85)
@@ -73,7 +73,7 @@ struct tess_ctx {
     int wvt_update, uniform_weight;
     // ---- workspace (owned)
     TessState* st;
-    int *cell_cnt, *cell_start, *cell_of, *cell_items;
+    int *cell_cnt, *cell_start, *cell_of, *cell_items, *block_sum;
     double2* cell_xy;
     double* cell_inv;
     long cells_cap;
@@ -141,7 +141,7 @@ extern "C" int tess_ctx_destroy(tess_ctx* c) {
     if (!c) return TESS_OK;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    void* ptrs[] = {c->node, c->scale, c->inv_s2, c->st, c->cell_cnt, c->cell_start, c->cell_of, c->cell_items,
+    void* ptrs[] = {c->node, c->scale, c->inv_s2, c->st, c->cell_cnt, c->cell_start, c->block_sum, c->cell_of, c->cell_items,
                     c->cell_xy, c->cell_inv, c->ql.q_off, c->ql.q_cnt, c->ql.xy, c->ql.gid, c->ql.inv, c->tile_ring, c->lab[0], c->lab[1],
                     c->mom, c->prev_count, c->scratch};
     for (void* p : ptrs)
@@ -386,11 +386,13 @@ static int ensure_cells(tess_ctx* c, int n_cells) {
     if (n_cells + 1 <= c->cells_cap) return TESS_OK;
     if (c->cell_cnt) cudaFree(c->cell_cnt);
     if (c->cell_start) cudaFree(c->cell_start);
-    c->cell_cnt = c->cell_start = nullptr;
+    if (c->block_sum) cudaFree(c->block_sum);
+    c->cell_cnt = c->cell_start = c->block_sum = nullptr;
     c->cells_cap = 0;
     CU_TRY(cudaMalloc((void**)&c->cell_cnt, sizeof(int) * (size_t)(n_cells + 1)));
     CU_TRY(cudaMemset(c->cell_cnt, 0, sizeof(int) * (size_t)(n_cells + 1)));   // scatter keeps it zero
     CU_TRY(cudaMalloc((void**)&c->cell_start, sizeof(int) * (size_t)(n_cells + 1)));
+    CU_TRY(cudaMalloc((void**)&c->block_sum, sizeof(int) * (size_t)(n_cells / TESS_SCAN_BLOCK + 2)));
     c->cells_cap = n_cells + 1;
     return TESS_OK;
 }
@@ -456,7 +458,9 @@ static int build_index(tess_ctx* c, const Geometry& q, int honor, double* mom, l
     int grid = nb > nbz ? nb : nbz;
     if (grid > c->sm_count * 16) grid = c->sm_count * 16;
     TESS_LAUNCH((k_cell_count), grid, 256, s, c->st, honor, q.g, c->node, k, c->cell_cnt, c->cell_of, mom, n_mom);
-    TESS_LAUNCH((k_cell_scan), 1, 1024, s, c->st, honor, c->cell_cnt, c->cell_start, q.n_cells);
+    const int nsb = (q.n_cells + TESS_SCAN_BLOCK - 1) / TESS_SCAN_BLOCK;
+    TESS_LAUNCH((k_cell_blocksum), nsb, TESS_SCAN_THREADS, s, c->st, honor, c->cell_cnt, q.n_cells, c->block_sum);
+    TESS_LAUNCH((k_cell_scan), nsb, TESS_SCAN_THREADS, s, c->st, honor, c->cell_cnt, c->cell_start, q.n_cells, c->block_sum);
     TESS_LAUNCH((k_cell_scatter), nb, 256, s, c->st, honor, c->cell_of, k, c->cell_start, c->cell_cnt, c->node,
                                       c->has_scale ? c->inv_s2 : nullptr, c->cell_items, c->cell_xy, c->cell_inv);
     CU_TRY(cudaGetLastError());

@@ -30,54 +30,81 @@ k_cell_count(const TessState* st, int honor, TessGrid g, const double* node, int
     }
 }
 
-// Exclusive scan of cell_cnt[0..n_cells) -> cell_start[0..n_cells] (single CTA, 1024 threads):
-// 16 consecutive cells per thread in registers, warp-shuffle scans, one carry per 16384 cells.
-// Thread 0 also resets the per-iteration scalars of the state block.
+// Exclusive scan of cell_cnt[0..n_cells) -> cell_start[0..n_cells], reduce-then-scan over blocks of
+// TESS_SCAN_BLOCK cells: k_cell_blocksum writes one total per block, k_cell_scan adds the totals of
+// the preceding blocks to a register/shuffle scan of its own block (16 consecutive cells per thread).
+// Block 0 of k_cell_scan also resets the per-iteration scalars of the state block.
 #define TESS_SCAN_ITEMS 16
-__global__ void __launch_bounds__(1024)
-k_cell_scan(TessState* st, int honor, const int* cell_cnt, int* cell_start, int n_cells) {
+#define TESS_SCAN_THREADS 256
+#define TESS_SCAN_BLOCK (TESS_SCAN_ITEMS * TESS_SCAN_THREADS)
+
+__global__ void __launch_bounds__(TESS_SCAN_THREADS)
+k_cell_blocksum(const TessState* st, int honor, const int* cell_cnt, int n_cells, int* block_sum) {
     if (TESS_STOPPED(st, honor)) return;
-    __shared__ int s_w[32];
-    __shared__ int s_tot;
+    __shared__ int s_w[TESS_SCAN_THREADS / 32];
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-    int carry = 0;
-    for (int base = 0; base < n_cells; base += 1024 * TESS_SCAN_ITEMS) {
-        const int i0 = base + t * TESS_SCAN_ITEMS;
-        int v[TESS_SCAN_ITEMS];
+    const int base = blockIdx.x * TESS_SCAN_BLOCK;
+    int tot = 0;
 #pragma unroll
-        for (int j = 0; j < TESS_SCAN_ITEMS; ++j) v[j] = (i0 + j < n_cells) ? cell_cnt[i0 + j] : 0;
-        int tot = 0;
-#pragma unroll
-        for (int j = 0; j < TESS_SCAN_ITEMS; ++j) { const int x = v[j]; v[j] = tot; tot += x; }   // local exclusive
-        int inc = tot;                                                                           // warp inclusive
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int y = __shfl_up_sync(TESS_FULL, inc, d);
-            if (lane >= d) inc += y;
-        }
-        if (lane == 31) s_w[w] = inc;
-        __syncthreads();
-        if (w == 0) {
-            const int x = s_w[lane];
-            int wi = x;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int y = __shfl_up_sync(TESS_FULL, wi, d);
-                if (lane >= d) wi += y;
-            }
-            s_w[lane] = wi - x;                      // exclusive prefix of the warp totals
-            if (lane == 31) s_tot = wi;
-        }
-        __syncthreads();
-        const int off = carry + s_w[w] + (inc - tot);
-#pragma unroll
-        for (int j = 0; j < TESS_SCAN_ITEMS; ++j)
-            if (i0 + j < n_cells) cell_start[i0 + j] = off + v[j];
-        carry += s_tot;
-        __syncthreads();
+    for (int j = 0; j < TESS_SCAN_ITEMS; ++j) {
+        const int i = base + j * TESS_SCAN_THREADS + t;      // coalesced
+        tot += (i < n_cells) ? cell_cnt[i] : 0;
     }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) tot += __shfl_xor_sync(TESS_FULL, tot, m);
+    if (lane == 0) s_w[w] = tot;
+    __syncthreads();
     if (t == 0) {
-        cell_start[n_cells] = carry;
+        int s = 0;
+        for (int i = 0; i < TESS_SCAN_THREADS / 32; ++i) s += s_w[i];
+        block_sum[blockIdx.x] = s;
+    }
+}
+
+__global__ void __launch_bounds__(TESS_SCAN_THREADS)
+k_cell_scan(TessState* st, int honor, const int* cell_cnt, int* cell_start, int n_cells, const int* block_sum) {
+    if (TESS_STOPPED(st, honor)) return;
+    __shared__ int s_w[TESS_SCAN_THREADS / 32];
+    __shared__ int s_base;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    // totals of the preceding blocks (a few hundred at most)
+    int pre = 0;
+    for (int i = t; i < (int)blockIdx.x; i += TESS_SCAN_THREADS) pre += block_sum[i];
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) pre += __shfl_xor_sync(TESS_FULL, pre, m);
+    if (lane == 0) s_w[w] = pre;
+    __syncthreads();
+    if (t == 0) {
+        int s = 0;
+        for (int i = 0; i < TESS_SCAN_THREADS / 32; ++i) s += s_w[i];
+        s_base = s;
+    }
+    __syncthreads();
+    const int carry = s_base;
+    __syncthreads();
+    const int i0 = blockIdx.x * TESS_SCAN_BLOCK + t * TESS_SCAN_ITEMS;
+    int v[TESS_SCAN_ITEMS];
+#pragma unroll
+    for (int j = 0; j < TESS_SCAN_ITEMS; ++j) v[j] = (i0 + j < n_cells) ? cell_cnt[i0 + j] : 0;
+    int tot = 0;
+#pragma unroll
+    for (int j = 0; j < TESS_SCAN_ITEMS; ++j) { const int x = v[j]; v[j] = tot; tot += x; }   // local exclusive
+    int inc = tot;                                                                           // warp inclusive
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int y = __shfl_up_sync(TESS_FULL, inc, d);
+        if (lane >= d) inc += y;
+    }
+    if (lane == 31) s_w[w] = inc;
+    __syncthreads();
+    int woff = 0;
+    for (int i = 0; i < w; ++i) woff += s_w[i];
+    const int off = carry + woff + (inc - tot);
+#pragma unroll
+    for (int j = 0; j < TESS_SCAN_ITEMS; ++j)
+        if (i0 + j < n_cells) cell_start[i0 + j] = off + v[j];
+    if (i0 <= n_cells - 1 && n_cells - 1 < i0 + TESS_SCAN_ITEMS) cell_start[n_cells] = off + tot;   // owner of the last cell
+    if (blockIdx.x == 0 && t == 0) {
         if (honor) {   // part of a Lloyd iteration (not a stand-alone assignment query)
             st->delta = 0.0;
             st->n_changed = 0ull;

@@ -27,6 +27,32 @@ def shard_rows(H, world, align=64):
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
+def balanced_row_shards(generators, H, W, world, x0=0.0, y0=0.0, align=64):
+    """Row ranges whose estimated cost is equal: the image kernel's time per pixel grows with the
+    local generator density rho roughly like c0 + c1 sqrt(rho) (profiles/r01_regimes_4096.jsonl:
+    4.5 ps/px for empty regions, +105 ps/px at one generator per pixel), so equal-height shards of a
+    centrally concentrated map would leave the central ranks 2-3x slower than the outer ones.
+    `generators` is the (k, 2) table (host array); boundaries fall on multiples of `align` rows."""
+    import numpy as np
+    g = np.asarray(generators, dtype=np.float64)
+    nty, ntx = (H + align - 1) // align, (W + align - 1) // align
+    if world <= 1 or nty < world:
+        return shard_rows(H, world, align)
+    ix = np.clip(((g[:, 0] - x0) // align).astype(np.int64), 0, ntx - 1)
+    iy = np.clip(((g[:, 1] - y0) // align).astype(np.int64), 0, nty - 1)
+    cnt = np.bincount(iy * ntx + ix, minlength=nty * ntx).reshape(nty, ntx).astype(np.float64)
+    tile_px = float(align * align)
+    cost = (tile_px * (4.5 + 105.0 * np.sqrt(cnt / tile_px))).sum(axis=1)      # per tile row
+    cum = np.concatenate(([0.0], np.cumsum(cost)))
+    cuts = [0]
+    for r in range(1, world):
+        t = int(np.searchsorted(cum, cum[-1] * r / world))
+        t = min(max(t, cuts[-1] // align + 1), nty - (world - r))              # at least one tile row each
+        cuts.append(t * align)
+    cuts.append(H)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
 class ShardedLloyd(object):
     """Drives one `Engine` per rank; `dist` is torch.distributed (already initialised)."""
 

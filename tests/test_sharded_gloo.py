@@ -23,6 +23,19 @@ def test_shard_rows_cover_and_align():
             assert all(a % 64 == 0 for a, _ in r) and all(b > a for a, b in r)
 
 
+def test_balanced_row_shards():
+    from tess_b200.sharded import balanced_row_shards
+    rng = np.random.default_rng(0)
+    H = W = 4096
+    g = np.column_stack((rng.normal(W / 2, 300, 20000), rng.normal(H / 2, 300, 20000)))
+    r = balanced_row_shards(g, H, W, 8)
+    assert r[0][0] == 0 and r[-1][1] == H and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+    assert all(a % 64 == 0 for a, _ in r) and all(b > a for a, b in r)
+    heights = [b - a for a, b in r]
+    assert min(heights[3:5]) < heights[0]            # central shards are thinner than the outer ones
+    assert balanced_row_shards(g, 100, W, 4) == shard_rows(100, 4)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
