@@ -291,6 +291,11 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    # stdout carries exactly ONE JSON line: park fd 1 on stderr while libraries (NCCL prints its
+    # version banner to stdout) initialise and run, restore it for the final print
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
@@ -388,6 +393,28 @@ def main():
             except Exception:
                 pass
 
+    # ---- N > 1: where the iteration goes on every rank (accumulate | all-reduce | update), stderr only
+    breakdown = None
+    if world > 1:
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(8)]
+        mv = drv._moments()
+        for e4 in ev:
+            e4[0].record(); eng.accumulate(); e4[1].record()
+            dist.all_reduce(mv, op=dist.ReduceOp.SUM); e4[2].record()
+            eng.update(); e4[3].record()
+        torch.cuda.synchronize()
+        acc = float(np.mean([e4[0].elapsed_time(e4[1]) for e4 in ev[2:]]))
+        arr = float(np.mean([e4[1].elapsed_time(e4[2]) for e4 in ev[2:]]))
+        upd = float(np.mean([e4[2].elapsed_time(e4[3]) for e4 in ev[2:]]))
+        t = torch.tensor([acc, arr, upd, float(r1 - r0)], dtype=torch.float64, device=device)
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        breakdown = [dict(rank=i, rows=int(x[3].item()), accumulate_ms=round(x[0].item(), 4),
+                          allreduce_wait_ms=round(x[1].item(), 4), update_ms=round(x[2].item(), 4))
+                     for i, x in enumerate(allt)]
+        if rank == 0:
+            sys.stderr.write("per-rank breakdown: %s\n" % json.dumps(breakdown))
+
     # ---- end to end through the public API with pinned host buffers
     e2e = None
     if not args.no_e2e:
@@ -471,7 +498,12 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roof, "cpu_baseline": cpu}
         if single is not None:
             line["single_gpu_same_workload"] = single
+        if breakdown is not None:
+            line["per_rank_breakdown"] = breakdown
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line))
+        sys.stdout.flush()
     eng.close()
     if world > 1:
         dist.destroy_process_group()

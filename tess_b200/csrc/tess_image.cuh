@@ -383,6 +383,10 @@ k_image_main(TessImgArgs a) {
     const int n_q = a.L.nqx * a.L.nqy;               // < 2^31 (checked by the host)
     const int stride = (int)gridDim.x * NW;
 
+    if (MODE != 0) {
+        for (int i = lane; i < QC * (NV + 1); i += 32) tab[i] = 0.0;
+        __syncwarp();
+    }
     TessRun<NV> cur;                 // the lane's running same-bin sum (registers)
     cur.key = -1;
     cur.n = 0;
@@ -439,14 +443,12 @@ k_image_main(TessImgArgs a) {
         const long px = qx0 + 2 * cx;                    // first column of this lane
         const double X0 = a.x0 + (double)px, X1 = a.x0 + (double)(px + 1);
 
-        // ---- request the pixels of the first warp tile; clear the accumulator table
+        // ---- request the pixels of the first warp tile (the accumulator table is all zero here: it
+        //      is cleared once at kernel start and every entry is zeroed again when it is flushed)
+#if TESS_PREFETCH
         double wn_[4][2], nn_[4][2];
-        if (MODE != 0) {
-            tess_load_patch<MODE, VEC>(a, src, interior, px, qy0 + 4 * ry, wn_, nn_);
-            const int na = c_q * (NV + 1);
-            for (int i = lane; i < na; i += 32) tab[i] = 0.0;
-            __syncwarp();
-        }
+        if (MODE != 0) tess_load_patch<MODE, VEC>(a, src, interior, px, qy0 + 4 * ry, wn_, nn_);
+#endif
 
         const unsigned short* pl = nullptr;   // parent list of the leaf filter (quadrant-list positions)
         bool p_ident = true;
@@ -465,11 +467,15 @@ k_image_main(TessImgArgs a) {
             //      Pixels outside the image read as NaN and drop out with the masked ones.
             double w_[4][2], n_[4][2];                     // MODE 1: weight; MODE 2: signal, noise
             if (MODE != 0) {
+#if TESS_PREFETCH
 #pragma unroll
                 for (int r = 0; r < 4; ++r)
 #pragma unroll
                     for (int c = 0; c < 2; ++c) { w_[r][c] = wn_[r][c]; if (MODE == 2) n_[r][c] = nn_[r][c]; }
                 if (step < 3 && wy0 + 8 < a.H) tess_load_patch<MODE, VEC>(a, src, interior, px, py + 8, wn_, nn_);
+#else
+                tess_load_patch<MODE, VEC>(a, src, interior, px, py, w_, n_);
+#endif
             }
 
             // ---- 16x16 block lists (every other step), only where the quadrant list is long
@@ -714,7 +720,7 @@ k_image_main(TessImgArgs a) {
                 if (t[0] != 0.0) {
                     double* m = a.mom + (long)gidv[e] * (NV + 1);
 #pragma unroll
-                    for (int i = 0; i <= NV; ++i) tess_gmem_add(m + i, t[i]);
+                    for (int i = 0; i <= NV; ++i) { tess_gmem_add(m + i, t[i]); tab[e * (NV + 1) + i] = 0.0; }
                 }
             }
             __syncwarp();
