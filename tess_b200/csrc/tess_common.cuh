@@ -32,7 +32,10 @@ static long g_tess_launches = 0;   // kernels launched by the library (host-side
 #define TESS_MAIN_MINBLOCKS 8 // CTAs per SM the main kernel is compiled for (<= 128 registers)
 #endif
 #ifndef TESS_PREFETCH
-#define TESS_PREFETCH 1         // request the pixels of warp tile s+1 while warp tile s is processed
+#define TESS_PREFETCH 0         // request the pixels of warp tile s+1 while warp tile s is processed
+#endif
+#ifndef TESS_PREFETCH_CACHE
+#define TESS_PREFETCH_CACHE 0   // 0: none; 1: prefetch.global.L2 of the next warp tile's rows; 2: into L1
 #endif
 #ifndef TESS_MAIN_MINBLOCKS_SN
 #define TESS_MAIN_MINBLOCKS_SN 6 // same for the signal/noise mode (two maps in flight: <= 168 registers)

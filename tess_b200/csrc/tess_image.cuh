@@ -95,6 +95,18 @@ TESS_DEVFN void tess_cp_async4(void* dst, const void* src) {
     memcpy(dst, src, 4);
 #endif
 }
+// prefetch of one global address into L2 (TESS_PREFETCH_CACHE 1) or L1 (2); nothing under the emulator
+TESS_DEVFN void tess_prefetch(const void* p) {
+#ifndef TESS_EMU
+#if TESS_PREFETCH_CACHE == 2
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+#else
+    (void)p;
+#endif
+}
 TESS_DEVFN void tess_cp_async_wait() {
 #ifndef TESS_EMU
     asm volatile("cp.async.wait_all;" ::: "memory");
@@ -381,6 +393,7 @@ k_image_main(TessImgArgs a) {
     double* const tab = sm.tab;
     const double* const src = (MODE == 2) ? a.sig : a.dens;   // MODE 1: weight map; MODE 2: signal map
     const int n_q = a.L.nqx * a.L.nqy;               // < 2^31 (checked by the host)
+    const int Wi = (int)a.W, Hi = (int)a.H;
     const int stride = (int)gridDim.x * NW;
 
     if (MODE != 0) {
@@ -422,7 +435,7 @@ k_image_main(TessImgArgs a) {
         if (q1 < n_q) stage(buf ^ 1, off1, cnt1);
         const int cnt_cur = cnt, off_cur = off;
         const int qy = q / a.L.nqx, qx = q - qy * a.L.nqx;
-        const long qx0 = 32L * qx, qy0 = 32L * qy;
+        const int qx0 = 32 * qx, qy0 = 32 * qy;            // pixel coordinates fit 32 bits (host-checked)
         if (cnt_cur != 0) {
         if (cnt_cur < 0 || cnt_cur > QC) {
             // slow path: list too long for the fast path (scan it from global memory) or overflow of
@@ -440,7 +453,7 @@ k_image_main(TessImgArgs a) {
         const int c_q = cnt_cur;
         // interior quadrant: every pixel access is in bounds (and 16-byte aligned: VEC)
         const bool interior = VEC && (qx0 + 32 <= a.W) && (qy0 + 32 <= a.H);
-        const long px = qx0 + 2 * cx;                    // first column of this lane
+        const int px = qx0 + 2 * cx;                     // first column of this lane
         const double X0 = a.x0 + (double)px, X1 = a.x0 + (double)(px + 1);
 
         // ---- request the pixels of the first warp tile (the accumulator table is all zero here: it
@@ -455,10 +468,10 @@ k_image_main(TessImgArgs a) {
         int p_len = c_q;
 
         for (int step = 0; step < 4; ++step) {
-            const long wy0 = qy0 + 8 * step;
+            const int wy0 = qy0 + 8 * step;
             if (wy0 >= a.H) break;                         // warp-uniform
-            const long py = wy0 + 4 * ry;                  // first row of this lane
-            const long base0 = py * a.W + px;              // flat index of the patch's first pixel
+            const int py = wy0 + 4 * ry;                   // first row of this lane
+            const long base0 = (long)py * a.W + px;              // flat index of the patch's first pixel
             double Y[4];
 #pragma unroll
             for (int r = 0; r < 4; ++r) Y[r] = a.y0 + (double)(py + r);
@@ -475,6 +488,15 @@ k_image_main(TessImgArgs a) {
                 if (step < 3 && wy0 + 8 < a.H) tess_load_patch<MODE, VEC>(a, src, interior, px, py + 8, wn_, nn_);
 #else
                 tess_load_patch<MODE, VEC>(a, src, interior, px, py, w_, n_);
+                // cache prefetch of the next warp tile's rows (no registers held): its loads then hit
+                // in L2 / L1 instead of paying the full HBM latency
+                if (TESS_PREFETCH_CACHE && interior && step < 3) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        tess_prefetch(src + base0 + (8 + r) * a.W);
+                        if (MODE == 2) tess_prefetch(a.noise + base0 + (8 + r) * a.W);
+                    }
+                }
 #endif
             }
 
@@ -482,7 +504,7 @@ k_image_main(TessImgArgs a) {
             if ((step & 1) == 0) {
                 pl = nullptr; p_ident = true; p_len = c_q;
                 if (c_q > TESS_BLOCK_MIN) {
-                    const long bx0 = qx0 + 16 * blk, bx1 = min(bx0 + 15, a.W - 1), by1 = min(wy0 + 15, a.H - 1);
+                    const int bx0 = qx0 + 16 * blk, bx1 = min(bx0 + 15, Wi - 1), by1 = min(wy0 + 15, Hi - 1);
                     const double hx = 0.5 * (double)(bx1 - bx0), hy = 0.5 * (double)(by1 - wy0);
                     const double rho = interior ? 10.606602778 : sqrt(hx * hx + hy * hy) * 1.0000001;   // 7.5 sqrt 2
                     const int n = tess_filter<16, HAS_SCALE, false>(qxy, qinv, nullptr, true, c_q, c_q,
@@ -505,8 +527,8 @@ k_image_main(TessImgArgs a) {
             if (!uniform) {
                 const int p_max = __reduce_max_sync(TESS_FULL, p_len);    // the two blocks' lists differ in length
                 if (p_max > TESS_LEAF_MIN) {
-                    const long lx0 = qx0 + 8 * leaf;
-                    const long lx1 = min(lx0 + 7, a.W - 1), ly1 = min(wy0 + 7, a.H - 1);
+                    const int lx0 = qx0 + 8 * leaf;
+                    const int lx1 = min(lx0 + 7, Wi - 1), ly1 = min(wy0 + 7, Hi - 1);
                     const double hx = 0.5 * (double)(lx1 - lx0), hy = 0.5 * (double)(ly1 - wy0);
                     const double rho = interior ? 4.9497479632 : sqrt(hx * hx + hy * hy) * 1.0000001;   // 3.5 sqrt 2
                     len = tess_filter<8, HAS_SCALE, true>(qxy, qinv, pl, p_ident, p_len, p_max,
@@ -617,30 +639,37 @@ k_image_main(TessImgArgs a) {
             }
             if (MODE == 0) continue;
 
-            // ---- moments.  Weights first; masked pixels (non-finite weight, signal or noise; outside
-            //      the image) are marked consumed (key -2).
+            // ---- moments.  Weights first.  The sum of the patch's weights is finite iff all of them
+            //      are (up to a harmless false alarm on overflow), so one test per lane decides whether
+            //      any pixel of the warp tile is masked (non-finite weight, signal or noise; outside
+            //      the image); only then are the masked pixels marked consumed (key -2) one by one.
             double wv[4][2];
-            bool clean = true;                             // no masked pixel in this patch
 #pragma unroll
             for (int r = 0; r < 4; ++r)
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     double w = w_[r][c];
-                    bool ok;
                     if (MODE == 2) {
                         const double S = w_[r][c], N = n_[r][c];
                         w = 1.0;
                         if (!a.uniform_weight) { const double qq = __ddiv_rn(S, N); w = __dmul_rn(qq, qq); }
-                        ok = (fabs(w) <= 1.7976931348623157e308) && (fabs(S) <= 1.7976931348623157e308) &&
-                             (fabs(N) <= 1.7976931348623157e308);
-                    } else {
-                        ok = fabs(w) <= 1.7976931348623157e308;
+                        // a non-finite signal or noise poisons the weight
+                        if (!((fabs(S) <= 1.7976931348623157e308) && (fabs(N) <= 1.7976931348623157e308))) w = TESS_NAN;
                     }
                     wv[r][c] = w;
-                    clean = clean && ok;
-                    bs[r][c] = ok ? bs[r][c] : -2;
                 }
-            if (uniform && __all_sync(TESS_FULL, clean)) {
+            const double c0 = __dadd_rn(__dadd_rn(wv[0][0], wv[1][0]), __dadd_rn(wv[2][0], wv[3][0]));
+            const double c1 = __dadd_rn(__dadd_rn(wv[0][1], wv[1][1]), __dadd_rn(wv[2][1], wv[3][1]));
+            const double wtot = __dadd_rn(c0, c1);
+            const bool all_clean = __all_sync(TESS_FULL, fabs(wtot) <= 1.7976931348623157e308);
+            if (!all_clean) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+                        bs[r][c] = (fabs(wv[r][c]) <= 1.7976931348623157e308) ? bs[r][c] : -2;
+            }
+            if (uniform && all_clean) {
                 // closed form for a one-bin patch: sum w x = X0 col0 + X1 col1, sum w y = sum_r Y_r row_r
                 const bool sw = (cur.key != ukey);
                 if (__any_sync(TESS_FULL, sw)) {
@@ -650,13 +679,11 @@ k_image_main(TessImgArgs a) {
 #pragma unroll
                     for (int i = 0; i < NV; ++i) cur.v[i] = sw ? 0.0 : cur.v[i];
                 }
-                const double c0 = __dadd_rn(__dadd_rn(wv[0][0], wv[1][0]), __dadd_rn(wv[2][0], wv[3][0]));
-                const double c1 = __dadd_rn(__dadd_rn(wv[0][1], wv[1][1]), __dadd_rn(wv[2][1], wv[3][1]));
                 double sy = 0.0;
 #pragma unroll
                 for (int r = 0; r < 4; ++r) sy = __dadd_rn(sy, __dmul_rn(__dadd_rn(wv[r][0], wv[r][1]), Y[r]));
                 cur.n += 8;
-                cur.v[0] = __dadd_rn(cur.v[0], __dadd_rn(c0, c1));
+                cur.v[0] = __dadd_rn(cur.v[0], wtot);
                 cur.v[1] = __dadd_rn(cur.v[1], __dadd_rn(__dmul_rn(c0, X0), __dmul_rn(c1, X1)));
                 cur.v[2] = __dadd_rn(cur.v[2], sy);
                 if (MODE == 2) {
