@@ -3,7 +3,7 @@
 bench.py -- throughput of the Lloyd / WVT iteration (BASELINE.json: "WVT Lloyd ms/iter and Gpix/s,
 8192^2 px x 1e5 bins; 1/2/4/8 B200 vs HBM roofline").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c4|c2] [--mode cvt|sn]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c4|small] [--mode cvt|sn]
 
 A "step" is one Lloyd iteration (grid index rebuild + assignment + per-bin sums + node update) over
 the whole synthetic map.  N = 1: configs[2], 8192^2 px x 1e5 generators (headline).  N > 1 (under

@@ -156,3 +156,45 @@ def test_zero_weight_bin_raises_like_the_reference(eng):
     w = np.array([1.0, 1.0, 1.0, -1.0])          # second bin: count 2, sum w == 0 -> NaN node
     with pytest.raises(ValueError):
         lloyd(xy, w, np.array([[0.4, 0.1], [10.4, 0.1]]), 10, engine=eng)
+
+
+def test_options_and_dense_fallbacks(eng):
+    """WVT scale update, uniform weights, list diagnostics and the scan fallbacks (see the GPU twin in
+    tests/test_gpu_parity.py)."""
+    from tess_b200 import _capi
+    N, k = 96, 40
+    sig = gaussian_image(N) + 1.0
+    noise = np.sqrt(sig + 1.0)
+    seeds = sampled_seeds((sig / noise) ** 2, k, seed=6)
+    x, y = np.meshgrid(np.arange(N, dtype=float), np.arange(N, dtype=float))
+    xy = np.column_stack((x.ravel(), y.ravel()))
+    eng.set_option(_capi.OPT_UNIFORM_WEIGHT, 1)
+    eng.set_option(_capi.OPT_WVT_SCALE_UPDATE, 1)
+    eng.set_image(signal=sig, noise=noise)
+    eng.set_generators(seeds)
+    eng.step(1)
+    lab = O.c_assign_grid(N, N, seeds)
+    assert np.array_equal(eng.labels(), lab)
+    rm = O.np_moments(xy, np.ones(N * N), lab.ravel(), k, signal=sig.ravel(), noise=noise.ravel())
+    np.testing.assert_allclose(eng.moments(), rm, rtol=1e-12, atol=0)
+    sc = np.sqrt(rm[:, 0] / O.bin_sn(rm))
+    np.testing.assert_allclose(eng.scales(), sc, rtol=1e-13)
+    node, _ = O.np_update_nodes(rm, seeds)
+    eng.step(1)
+    assert np.array_equal(eng.labels(), O.c_assign_grid(N, N, node, scale=sc))
+    eng.set_option(_capi.OPT_UNIFORM_WEIGHT, 0)
+    eng.set_option(_capi.OPT_WVT_SCALE_UPDATE, 0)
+    # dense generators: quadrant lists beyond the fast path, tile overflow
+    rng = np.random.default_rng(3)
+    dense = rng.uniform(0, 64, (64 * 64 // 6, 2))
+    w = rng.uniform(0.5, 1.5, (64, 64))
+    eng.set_image(density=w)
+    eng.set_generators(dense)
+    eng.accumulate()
+    ref = O.c_assign_grid(64, 64, dense)
+    assert np.array_equal(eng.labels(), ref)
+    x, y = np.meshgrid(np.arange(64.0), np.arange(64.0))
+    rm = O.np_moments(np.column_stack((x.ravel(), y.ravel())), w.ravel(), ref.ravel(), dense.shape[0])
+    np.testing.assert_allclose(eng.moments()[:, :4], rm[:, :4], rtol=1e-12, atol=0)
+    st = eng.list_stats()
+    assert st["scan_all"] + st["scan_list"] > 0

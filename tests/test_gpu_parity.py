@@ -321,3 +321,82 @@ def test_config_c5_segmap_large(eng):
         assert torch.equal(ex, seg[y0:y0 + H, x0:x0 + W])
     # idempotence: the same call returns the same map
     assert torch.equal(eng.assign_grid(0.0, 0.0, N, N), seg)
+
+
+# ---------------------------------------------------------------- WVT extension, options, diagnostics
+def test_wvt_scaled_lloyd_iterations_vs_oracle(eng):
+    """Scale-weighted metric in the Lloyd loop (no reference counterpart: parity is against the
+    restatement, oracle/oracle.py, which degenerates bit-exactly to the reference at scale == 1)."""
+    N, k = 384, 260
+    sig = gaussian_image(N) + 1.0
+    noise = np.sqrt(sig + 1.0)
+    w = (sig / noise) ** 2
+    seeds = sampled_seeds(w, k, seed=4)
+    scale = np.random.default_rng(9).uniform(0.7, 1.8, k)
+    x, y = np.meshgrid(np.arange(N, dtype=float), np.arange(N, dtype=float))
+    xy = np.column_stack((x.ravel(), y.ravel()))
+    eng.set_image(signal=sig, noise=noise)
+    node = seeds
+    for it in range(3):
+        eng.set_generators(node, scale)
+        eng.accumulate()
+        lab = h(eng.labels())
+        ref = O.c_assign_grid(N, N, node, scale=scale)
+        assert np.array_equal(lab, ref), it
+        rm = O.np_moments(xy, w.ravel(), ref.ravel(), k, signal=sig.ravel(), noise=noise.ravel())
+        np.testing.assert_allclose(h(eng.moments()), rm, rtol=1e-12, atol=0)
+        eng.update()
+        node, _ = O.np_update_nodes(rm, node)
+        assert np.abs(h(eng.generators()) - node).max() < 1e-9
+        assert np.array_equal(h(eng.scales()), scale)
+    # scale == 1 is bit-identical to no scales at all
+    eng.set_generators(seeds, np.ones(k)); eng.accumulate(); a = h(eng.labels())
+    eng.set_generators(seeds); eng.accumulate()
+    assert np.array_equal(a, h(eng.labels()))
+
+
+def test_options_uniform_weight_and_scale_update(eng):
+    from tess_b200 import _capi
+    N, k = 256, 120
+    sig = gaussian_image(N) + 1.0
+    noise = np.sqrt(sig + 1.0)
+    seeds = sampled_seeds((sig / noise) ** 2, k, seed=6)
+    x, y = np.meshgrid(np.arange(N, dtype=float), np.arange(N, dtype=float))
+    xy = np.column_stack((x.ravel(), y.ravel()))
+    eng.set_option(_capi.OPT_UNIFORM_WEIGHT, 1)         # geometric centroids: w = 1
+    eng.set_option(_capi.OPT_WVT_SCALE_UPDATE, 1)       # scale_j = sqrt(count_j / (S/N)_j) after each update
+    eng.set_image(signal=sig, noise=noise)
+    eng.set_generators(seeds)
+    eng.step(1)
+    lab = O.c_assign_grid(N, N, seeds)
+    assert np.array_equal(h(eng.labels()), lab)
+    rm = O.np_moments(xy, np.ones(N * N), lab.ravel(), k, signal=sig.ravel(), noise=noise.ravel())
+    np.testing.assert_allclose(h(eng.moments()), rm, rtol=1e-12, atol=0)
+    sn = O.bin_sn(rm)
+    np.testing.assert_allclose(h(eng.scales()), np.sqrt(rm[:, 0] / sn), rtol=1e-13)
+    # the next iteration uses the updated scales
+    node, _ = O.np_update_nodes(rm, seeds)
+    eng.step(1)
+    assert np.array_equal(h(eng.labels()), O.c_assign_grid(N, N, node, scale=np.sqrt(rm[:, 0] / sn)))
+    eng.set_option(_capi.OPT_UNIFORM_WEIGHT, 0)
+    eng.set_option(_capi.OPT_WVT_SCALE_UPDATE, 0)
+
+
+def test_list_diagnostics_and_dense_fallbacks(eng):
+    """More generators than pixels per quadrant can hold on the fast path: the scan fallbacks are
+    exact; tess_get_list_stats reports them."""
+    rng = np.random.default_rng(3)
+    N = 192
+    dense = rng.uniform(0, N, (N * N // 20, 2))          # one generator per 20 px
+    w = rng.uniform(0.5, 1.5, (N, N))
+    x, y = np.meshgrid(np.arange(N, dtype=float), np.arange(N, dtype=float))
+    xy = np.column_stack((x.ravel(), y.ravel()))
+    eng.set_image(density=w)
+    eng.set_generators(dense)
+    eng.accumulate()
+    ref = O.c_assign_grid(N, N, dense)
+    assert np.array_equal(h(eng.labels()), ref)
+    np.testing.assert_allclose(h(eng.moments())[:, :4], O.np_moments(xy, w.ravel(), ref.ravel(), dense.shape[0])[:, :4],
+                               rtol=1e-12, atol=0)
+    st = eng.list_stats()
+    assert st["scan_all"] + st["scan_list"] > 0 and st["arena_used"] <= st["arena_capacity"]
