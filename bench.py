@@ -267,6 +267,7 @@ def main():
     ap.add_argument("--mode", default="cvt", choices=["cvt", "sn"],
                     help="cvt: density map, 4 moments, 12 B/px (reference parity); sn: signal+noise maps, 6 moments, 20 B/px")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="do not sample clocks during the timed region")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-single", action="store_true", help="N>1: skip rank 0's one-GPU run of the same map")
     ap.add_argument("--no-balance", dest="balance", action="store_false",
@@ -348,17 +349,19 @@ def main():
     step(args.warmup)
     barrier()
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not args.no_clocks:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = eng.api.launch_count()
     ev0.record()
+    t_enq = time.perf_counter()
     step(args.steps)
+    enqueue_ms = 1e3 * (time.perf_counter() - t_enq) / args.steps      # host time to enqueue one step
     ev1.record()
     barrier()
     gpu_launches = eng.api.launch_count() - l0
     ms_total = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if (rank == 0 and not args.no_clocks) else None
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -494,7 +497,8 @@ def main():
                            "shard_rows": [list(x) for x in shards] if world > 1 or fake else None,
                            "l2": "inputs (%.0f MB per GPU) larger than L2 (126 MB); no flush needed" % (
                                (BYTES_PER_PX[mode] - 4) * (r1 - r0) * N / 1e6),
-                           "converged_during_run": bool(conv), "fake_shard": args.fake_shard},
+                           "converged_during_run": bool(conv), "fake_shard": args.fake_shard,
+                           "host_enqueue_ms_per_step": round(enqueue_ms, 4)},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roof, "cpu_baseline": cpu}
         if single is not None:
             line["single_gpu_same_workload"] = single

@@ -456,6 +456,49 @@ k_image_main(TessImgArgs a) {
         const int px = qx0 + 2 * cx;                     // first column of this lane
         const double X0 = a.x0 + (double)px, X1 = a.x0 + (double)(px + 1);
 
+        // ---- one-bin quadrant (a single candidate, interior, MODE 1): constant labels, closed-form
+        //      patch sums, one shuffle reduction and four global reductions for the whole quadrant
+        if (MODE == 1 && c_q == 1 && interior) {
+            const int gid = gidv[0];
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+            bool clean = true;
+#pragma unroll
+            for (int step = 0; step < 4; ++step) {
+                const int py = qy0 + 8 * step + 4 * ry;
+                const long base0 = (long)py * a.W + px;
+                double2 v[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    v[r] = *reinterpret_cast<const double2*>(src + base0 + r * a.W);
+                    *reinterpret_cast<int2*>(labels + base0 + r * a.W) = make_int2(gid, gid);
+                }
+                const double c0 = __dadd_rn(__dadd_rn(v[0].x, v[1].x), __dadd_rn(v[2].x, v[3].x));
+                const double c1 = __dadd_rn(__dadd_rn(v[0].y, v[1].y), __dadd_rn(v[2].y, v[3].y));
+                double sy = 0.0;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) sy = __dadd_rn(sy, __dmul_rn(__dadd_rn(v[r].x, v[r].y), a.y0 + (double)(py + r)));
+                const double t = __dadd_rn(c0, c1);
+                clean = clean && (fabs(t) <= 1.7976931348623157e308);
+                s0 = __dadd_rn(s0, t);
+                s1 = __dadd_rn(s1, __dadd_rn(__dmul_rn(c0, X0), __dmul_rn(c1, X1)));
+                s2 = __dadd_rn(s2, sy);
+            }
+            if (__all_sync(TESS_FULL, clean)) {
+#pragma unroll
+                for (int m = 16; m >= 1; m >>= 1) {
+                    s0 = __dadd_rn(s0, __shfl_xor_sync(TESS_FULL, s0, m));
+                    s1 = __dadd_rn(s1, __shfl_xor_sync(TESS_FULL, s1, m));
+                    s2 = __dadd_rn(s2, __shfl_xor_sync(TESS_FULL, s2, m));
+                }
+                if (lane < 4) {
+                    double* m = a.mom + (long)gid * (NV + 1);
+                    tess_gmem_add(m + lane, lane == 0 ? 1024.0 : (lane == 1 ? s0 : (lane == 2 ? s1 : s2)));
+                }
+                goto quadrant_done;
+            }
+            // a masked pixel somewhere: fall through to the general path (labels are rewritten there)
+        }
+
         // ---- request the pixels of the first warp tile (the accumulator table is all zero here: it
         //      is cleared once at kernel start and every entry is zeroed again when it is flushed)
 #if TESS_PREFETCH
@@ -754,6 +797,7 @@ k_image_main(TessImgArgs a) {
         }
         }   // fast path
         }   // cnt != 0
+    quadrant_done:
         // ---- rotate the pipeline
         q = q1; cnt = cnt1; off = off1;
         q1 = q2; cnt1 = cnt2; off1 = off2;
