@@ -481,15 +481,37 @@ static int build_lists(tess_ctx* c, const Geometry& q, int honor, cudaStream_t s
     return TESS_OK;
 }
 
+// persistent grid: exactly the CTAs that are resident at once (the kernel strides over quadrants)
+template <class K>
+static int resident_ctas(tess_ctx* c, K kern) {
+#ifndef TESS_EMU
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TESS_MAIN_THREADS, 0) != cudaSuccess || per_sm < 1)
+        per_sm = 4;
+    return c->sm_count * per_sm;
+#else
+    (void)kern;
+    return c->sm_count * 2;
+#endif
+}
+
 template <int MODE>
-static void launch_image(tess_ctx* c, const TessImgArgs& a, bool vec, int grid, cudaStream_t s) {
+static void launch_image(tess_ctx* c, const TessImgArgs& a, bool vec, long want, cudaStream_t s) {
+#define TESS_GO(KERN)                                                   \
+    do {                                                                \
+        long g_ = resident_ctas(c, KERN);                               \
+        if (g_ > want) g_ = want;                                       \
+        if (g_ < 1) g_ = 1;                                             \
+        TESS_LAUNCH((KERN), (int)g_, TESS_MAIN_THREADS, s, a);          \
+    } while (0)
     if (c->has_scale) {
-        if (vec) TESS_LAUNCH((k_image_main<MODE, true, true>), grid, TESS_MAIN_THREADS, s, a);
-        else TESS_LAUNCH((k_image_main<MODE, true, false>), grid, TESS_MAIN_THREADS, s, a);
+        if (vec) TESS_GO((k_image_main<MODE, true, true>));
+        else TESS_GO((k_image_main<MODE, true, false>));
     } else {
-        if (vec) TESS_LAUNCH((k_image_main<MODE, false, true>), grid, TESS_MAIN_THREADS, s, a);
-        else TESS_LAUNCH((k_image_main<MODE, false, false>), grid, TESS_MAIN_THREADS, s, a);
+        if (vec) TESS_GO((k_image_main<MODE, false, true>));
+        else TESS_GO((k_image_main<MODE, false, false>));
     }
+#undef TESS_GO
 }
 
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
@@ -513,12 +535,10 @@ static int run_image(tess_ctx* c, const Geometry& q, int mode, int honor, int32_
     // one warp per quadrant, strided: enough CTAs to fill every SM at the compiled occupancy
     const long nq = (long)c->ql.nqx * c->ql.nqy;
     const int nw = TESS_MAIN_THREADS / 32;
-    long want = (nq + nw - 1) / nw;
-    int grid = (int)(want < (long)c->sm_count * 16 ? want : (long)c->sm_count * 16);
-    if (grid < 1) grid = 1;
-    if (mode == 0) launch_image<0>(c, a, vec, grid, s);
-    else if (mode == 1) launch_image<1>(c, a, vec, grid, s);
-    else launch_image<2>(c, a, vec, grid, s);
+    const long want = (nq + nw - 1) / nw;
+    if (mode == 0) launch_image<0>(c, a, vec, want, s);
+    else if (mode == 1) launch_image<1>(c, a, vec, want, s);
+    else launch_image<2>(c, a, vec, want, s);
     CU_TRY(cudaGetLastError());
     return TESS_OK;
 }
