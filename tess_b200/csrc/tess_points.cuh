@@ -19,9 +19,10 @@ TESS_DEVFN int tess_nearest_ring(const TessGrid& g, const int* cell_start, const
     const int cj = tess_cell_coord(py, g.oy, g.inv_cs, g.gh);
     double bd = INFINITY;
     int bi = 0x7fffffff;
-    auto scan = [&](int i, int j) {
-        const long cell = (long)j * g.gw + i;
-        const int s = cell_start[cell], e = cell_start[cell + 1];
+    // generators of the cells i0..i1 of grid row j: one contiguous slot range (two index loads)
+    auto scan = [&](int i0, int i1, int j) {
+        const long row = (long)j * g.gw;
+        const int s = cell_start[row + i0], e = cell_start[row + i1 + 1];
         for (int q = s; q < e; ++q) {
             const double2 p = cell_xy[q];
             double d = tess_d2_pinned(px, py, p.x, p.y);
@@ -36,13 +37,15 @@ TESS_DEVFN int tess_nearest_ring(const TessGrid& g, const int* cell_start, const
         const int bi0 = ci - ring, bi1 = ci + ring, bj0 = cj - ring, bj1 = cj + ring;
         const int xi0 = max(bi0, 0), xi1 = min(bi1, g.gw - 1);
         if (ring == 0) {
-            scan(ci, cj);
+            scan(ci, ci, cj);
         } else {
-            if (bj0 >= 0) for (int i = xi0; i <= xi1; ++i) scan(i, bj0);
-            if (bj1 < g.gh) for (int i = xi0; i <= xi1; ++i) scan(i, bj1);
+            if (bj0 >= 0) scan(xi0, xi1, bj0);
+            if (bj1 < g.gh) scan(xi0, xi1, bj1);
             const int yj0 = max(bj0 + 1, 0), yj1 = min(bj1 - 1, g.gh - 1);
-            if (bi0 >= 0) for (int j = yj0; j <= yj1; ++j) scan(bi0, j);
-            if (bi1 < g.gw) for (int j = yj0; j <= yj1; ++j) scan(bi1, j);
+            for (int j = yj0; j <= yj1; ++j) {
+                if (bi0 >= 0) scan(bi0, bi0, j);
+                if (bi1 < g.gw) scan(bi1, bi1, j);
+            }
         }
         if (bi0 <= 0 && bj0 <= 0 && bi1 >= g.gw - 1 && bj1 >= g.gh - 1) break;
         const double lb = fmax(g.cs * (double)ring - g.tol, 0.0);
