@@ -503,14 +503,16 @@ static void launch_image(tess_ctx* c, const TessImgArgs& a, bool vec, long want,
         long g_ = resident_ctas(c, KERN);                               \
         if (g_ > want) g_ = want;                                       \
         if (g_ < 1) g_ = 1;                                             \
-        TESS_LAUNCH((KERN), (int)g_, TESS_MAIN_THREADS, s, a);          \
+        TESS_LAUNCH((KERN), (int)g_, TESS_MAIN_THREADS, s, a, vec ? 1 : 0); \
     } while (0)
+    // interior quadrants (aligned 128-bit accesses), then the ragged edge / unaligned remainder
+    const bool has_edge = !vec || (a.W % 32 != 0) || (a.H % 32 != 0);
     if (c->has_scale) {
-        if (vec) TESS_GO((k_image_main<MODE, true, true>));
-        else TESS_GO((k_image_main<MODE, true, false>));
+        if (vec) TESS_GO((k_image_main<MODE, true, false>));
+        if (has_edge) TESS_GO((k_image_main<MODE, true, true>));
     } else {
-        if (vec) TESS_GO((k_image_main<MODE, false, true>));
-        else TESS_GO((k_image_main<MODE, false, false>));
+        if (vec) TESS_GO((k_image_main<MODE, false, false>));
+        if (has_edge) TESS_GO((k_image_main<MODE, false, true>));
     }
 #undef TESS_GO
 }

@@ -332,7 +332,7 @@ TESS_DEVFN int tess_filter(const double2* qxy, const double* qinv, const unsigne
 
 // Loads the lane's 2x4 pixel patch whose first pixel is (px, py): weight (MODE 1) or signal and
 // noise (MODE 2).  Interior quadrants: four 128-bit loads; else guarded scalar loads, NaN outside.
-template <int MODE, bool VEC>
+template <int MODE>
 TESS_DEVFN void tess_load_patch(const TessImgArgs& a, const double* src, bool interior, long px, long py,
                                 double (&w)[4][2], double (&nz)[4][2]) {
     const long base0 = py * a.W + px;
@@ -374,10 +374,377 @@ struct TessWarpSmem {
     unsigned short claim[(MODE != 0) ? QC : 1];              // election of the lane that adds to a table entry
 };
 
-// MODE 0: labels only; 1: density map (4 moments); 2: signal + noise maps (6 moments)
-template <int MODE, bool HAS_SCALE, bool VEC>
+// One quadrant on the fast path (list of at most QCAP candidates staged in sm.q*[buf]).  INTERIOR:
+// every pixel access is in bounds and 16-byte aligned (128-bit loads, 64-bit label stores, constant
+// rectangle radii); the general variant guards every access and is kept out of line.
+template <int MODE, bool HAS_SCALE, bool INTERIOR>
+TESS_DEVFN void tess_quadrant_body(const TessImgArgs& a, TessWarpSmem<MODE, HAS_SCALE>& sm, int buf, int32_t* labels,
+                                   const double* src, int c_q, int qx0, int qy0, int lane) {
+    constexpr int NV = (MODE == 2) ? 5 : 3;
+    const int cx = lane & 15, ry = lane >> 4;          // patch: cols 2cx,2cx+1; rows 4ry..4ry+3
+    const int leaf = cx >> 2;                          // 8-px-wide leaf of the warp tile
+    const int blk = cx >> 3;                           // 16-px-wide block
+    double* const tab = sm.tab;
+    const int Wi = (int)a.W, Hi = (int)a.H;
+    TessRun<NV> cur;                 // the lane's running same-bin sum (registers)
+    cur.key = -1;
+    cur.n = 0;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) cur.v[i] = 0.0;
+    const double2* const qxy = sm.qxy[buf];
+    const double* const qinv = HAS_SCALE ? sm.qinv[buf] : nullptr;
+    const int* const gidv = sm.qgid[buf];
+    constexpr bool interior = INTERIOR;   // every pixel access in bounds and 16-byte aligned
+    const int px = qx0 + 2 * cx;                     // first column of this lane
+    const double X0 = a.x0 + (double)px, X1 = a.x0 + (double)(px + 1);
+
+    // ---- one-bin quadrant (a single candidate, interior, MODE 1): constant labels, closed-form
+    //      patch sums, one shuffle reduction and four global reductions for the whole quadrant
+    if (MODE == 1 && c_q == 1 && interior) {
+        const int gid = gidv[0];
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        bool clean = true;
+#pragma unroll
+        for (int step = 0; step < 4; ++step) {
+            const int py = qy0 + 8 * step + 4 * ry;
+            const long base0 = (long)py * a.W + px;
+            double2 v[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                v[r] = *reinterpret_cast<const double2*>(src + base0 + r * a.W);
+                *reinterpret_cast<int2*>(labels + base0 + r * a.W) = make_int2(gid, gid);
+            }
+            const double c0 = __dadd_rn(__dadd_rn(v[0].x, v[1].x), __dadd_rn(v[2].x, v[3].x));
+            const double c1 = __dadd_rn(__dadd_rn(v[0].y, v[1].y), __dadd_rn(v[2].y, v[3].y));
+            double sy = 0.0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) sy = __dadd_rn(sy, __dmul_rn(__dadd_rn(v[r].x, v[r].y), a.y0 + (double)(py + r)));
+            const double t = __dadd_rn(c0, c1);
+            clean = clean && (fabs(t) <= 1.7976931348623157e308);
+            s0 = __dadd_rn(s0, t);
+            s1 = __dadd_rn(s1, __dadd_rn(__dmul_rn(c0, X0), __dmul_rn(c1, X1)));
+            s2 = __dadd_rn(s2, sy);
+        }
+        if (__all_sync(TESS_FULL, clean)) {
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) {
+                s0 = __dadd_rn(s0, __shfl_xor_sync(TESS_FULL, s0, m));
+                s1 = __dadd_rn(s1, __shfl_xor_sync(TESS_FULL, s1, m));
+                s2 = __dadd_rn(s2, __shfl_xor_sync(TESS_FULL, s2, m));
+            }
+            if (lane < 4) {
+                double* m = a.mom + (long)gid * (NV + 1);
+                tess_gmem_add(m + lane, lane == 0 ? 1024.0 : (lane == 1 ? s0 : (lane == 2 ? s1 : s2)));
+            }
+            return;
+        }
+        // a masked pixel somewhere: fall through to the general path (labels are rewritten there)
+    }
+
+    // ---- request the pixels of the first warp tile (the accumulator table is all zero here: it
+    //      is cleared once at kernel start and every entry is zeroed again when it is flushed)
+#if TESS_PREFETCH
+    double wn_[4][2], nn_[4][2];
+    if (MODE != 0) tess_load_patch<MODE>(a, src, interior, px, qy0 + 4 * ry, wn_, nn_);
+#endif
+
+    const unsigned short* pl = nullptr;   // parent list of the leaf filter (quadrant-list positions)
+    bool p_ident = true;
+    int p_len = c_q;
+
+    for (int step = 0; step < 4; ++step) {
+        const int wy0 = qy0 + 8 * step;
+        if (wy0 >= a.H) break;                         // warp-uniform
+        const int py = wy0 + 4 * ry;                   // first row of this lane
+        const long base0 = (long)py * a.W + px;              // flat index of the patch's first pixel
+        double Y[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) Y[r] = a.y0 + (double)(py + r);
+
+        // ---- pixel data of this warp tile was requested one warp tile ahead (software pipeline).
+        //      Pixels outside the image read as NaN and drop out with the masked ones.
+        double w_[4][2], n_[4][2];                     // MODE 1: weight; MODE 2: signal, noise
+        if (MODE != 0) {
+#if TESS_PREFETCH
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) { w_[r][c] = wn_[r][c]; if (MODE == 2) n_[r][c] = nn_[r][c]; }
+            if (step < 3 && wy0 + 8 < a.H) tess_load_patch<MODE>(a, src, interior, px, py + 8, wn_, nn_);
+#else
+            tess_load_patch<MODE>(a, src, interior, px, py, w_, n_);
+            // cache prefetch of the next warp tile's rows (no registers held): its loads then hit
+            // in L2 / L1 instead of paying the full HBM latency
+            if (TESS_PREFETCH_CACHE && interior && step < 3) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    tess_prefetch(src + base0 + (8 + r) * a.W);
+                    if (MODE == 2) tess_prefetch(a.noise + base0 + (8 + r) * a.W);
+                }
+            }
+#endif
+        }
+
+        // ---- 16x16 block lists (every other step), only where the quadrant list is long
+        if ((step & 1) == 0) {
+            pl = nullptr; p_ident = true; p_len = c_q;
+            if (c_q > TESS_BLOCK_MIN) {
+                const int bx0 = qx0 + 16 * blk, bx1 = min(bx0 + 15, Wi - 1), by1 = min(wy0 + 15, Hi - 1);
+                const double hx = 0.5 * (double)(bx1 - bx0), hy = 0.5 * (double)(by1 - wy0);
+                const double rho = interior ? 10.606602778 : sqrt(hx * hx + hy * hy) * 1.0000001;   // 7.5 sqrt 2
+                const int n = tess_filter<16, HAS_SCALE, false>(qxy, qinv, nullptr, true, c_q, c_q,
+                                                                a.x0 + 0.5 * (double)(bx0 + bx1),
+                                                                a.y0 + 0.5 * (double)(wy0 + by1), rho, bx0 < a.W, lane,
+                                                                sm.bl[blk], nullptr, nullptr, TESS_BCAP);
+                // both blocks must fit for the (warp-uniform) parent switch
+                if (__all_sync(TESS_FULL, n <= TESS_BCAP)) { pl = sm.bl[blk]; p_ident = false; p_len = n; }
+            }
+        }
+
+        // ---- candidates of this lane's 8x8 leaf
+        double2* const lg = sm.lg[leaf];
+        unsigned short* const ls = sm.ls[leaf];
+        double* const li = HAS_SCALE ? sm.li[leaf] : nullptr;
+        int len = 0;
+        bool use_leaf = false;
+        bool uniform = (c_q == 1);                     // the whole warp tile belongs to one bin
+        int ukey = 0;
+        if (!uniform) {
+            const int p_max = __reduce_max_sync(TESS_FULL, p_len);    // the two blocks' lists differ in length
+            if (p_max > TESS_LEAF_MIN) {
+                const int lx0 = qx0 + 8 * leaf;
+                const int lx1 = min(lx0 + 7, Wi - 1), ly1 = min(wy0 + 7, Hi - 1);
+                const double hx = 0.5 * (double)(lx1 - lx0), hy = 0.5 * (double)(ly1 - wy0);
+                const double rho = interior ? 4.9497479632 : sqrt(hx * hx + hy * hy) * 1.0000001;   // 3.5 sqrt 2
+                len = tess_filter<8, HAS_SCALE, true>(qxy, qinv, pl, p_ident, p_len, p_max,
+                                                      a.x0 + 0.5 * (double)(lx0 + lx1),
+                                                      a.y0 + 0.5 * (double)(wy0 + ly1), rho, lx0 < a.W, lane, ls, lg, li,
+                                                      TESS_LEAF_CAP);
+                use_leaf = (len <= TESS_LEAF_CAP);
+                // all (in-image) leaves ended with the same single candidate?
+                const int one = (len == 1) ? (int)ls[0] : ((lx0 < a.W) ? -1 : -3);
+                const int ref = __reduce_max_sync(TESS_FULL, one);
+                uniform = (ref >= 0) && __all_sync(TESS_FULL, one == ref || one == -3);
+                ukey = ref;
+            }
+        }
+
+        int bs[4][2];                                  // winning quadrant-list position per pixel
+        if (uniform) {
+            // ---- one bin for all 256 pixels: constant labels
+            const int gid = gidv[ukey];
+            if (interior) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) *reinterpret_cast<int2*>(labels + base0 + r * a.W) = make_int2(gid, gid);
+            } else {
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+                        if ((py + r < a.H) && (px + c < a.W)) labels[base0 + r * a.W + c] = gid;
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { bs[r][0] = ukey; bs[r][1] = ukey; }
+        } else {
+            // ---- evaluate the surviving candidates with the pinned formula.  Lists are in no
+            //      particular order, so an exact tie (d == best so far) is only RECORDED here; the
+            //      rare warp that saw one re-evaluates with the full (distance, index) order below.
+            double bd[4][2];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) { bd[r][c] = INFINITY; bs[r][c] = 0; }
+            const int n_ev = use_leaf ? len : p_len;
+            bool tied = false;
+            for (int j = 0; j < n_ev; ++j) {
+                double2 g;
+                int e;
+                double inv = 1.0;
+                if (use_leaf) {
+                    g = lg[j];
+                    e = ls[j];
+                    if (HAS_SCALE) inv = li[j];
+                } else {
+                    e = p_ident ? j : (int)pl[j];
+                    g = qxy[e];
+                    if (HAS_SCALE) inv = qinv[e];
+                }
+                const double dx0 = __dsub_rn(X0, g.x), dx1 = __dsub_rn(X1, g.x);
+                const double dxx0 = __dmul_rn(dx0, dx0), dxx1 = __dmul_rn(dx1, dx1);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const double dy = __dsub_rn(Y[r], g.y);
+                    const double dyy = __dmul_rn(dy, dy);
+                    double d0 = __dadd_rn(dxx0, dyy), d1 = __dadd_rn(dxx1, dyy);
+                    if (HAS_SCALE) { d0 = __dmul_rn(d0, inv); d1 = __dmul_rn(d1, inv); }
+                    tied = tied || (d0 == bd[r][0]) || (d1 == bd[r][1]);
+                    if (d0 < bd[r][0]) { bd[r][0] = d0; bs[r][0] = e; }
+                    if (d1 < bd[r][1]) { bd[r][1] = d1; bs[r][1] = e; }
+                }
+            }
+            if (__any_sync(TESS_FULL, tied)) {
+                // exact ties: lowest generator index wins
+                int bg[4][2];
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) { bd[r][c] = INFINITY; bs[r][c] = 0; bg[r][c] = 0x7fffffff; }
+                for (int j = 0; j < n_ev; ++j) {
+                    int e;
+                    if (use_leaf) e = ls[j];
+                    else e = p_ident ? j : (int)pl[j];
+                    const double2 g = qxy[e];
+                    const double inv = HAS_SCALE ? qinv[e] : 1.0;
+                    const int gid = gidv[e];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            double d = tess_d2_pinned(c ? X1 : X0, Y[r], g.x, g.y);
+                            if (HAS_SCALE) d = __dmul_rn(d, inv);
+                            if ((d < bd[r][c]) || ((d == bd[r][c]) && (gid < bg[r][c]))) {
+                                bd[r][c] = d; bs[r][c] = e; bg[r][c] = gid;
+                            }
+                        }
+                }
+            }
+            __syncwarp();                              // the leaves' lists differ in length
+            // ---- labels out: 16 lanes x 8 B = one 128-byte line per row
+            if (interior) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    *reinterpret_cast<int2*>(labels + base0 + r * a.W) = make_int2(gidv[bs[r][0]], gidv[bs[r][1]]);
+            } else {
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+                        if ((py + r < a.H) && (px + c < a.W)) labels[base0 + r * a.W + c] = gidv[bs[r][c]];
+            }
+        }
+        if (MODE == 0) continue;
+
+        // ---- moments.  Weights first.  The sum of the patch's weights is finite iff all of them
+        //      are (up to a harmless false alarm on overflow), so one test per lane decides whether
+        //      any pixel of the warp tile is masked (non-finite weight, signal or noise; outside
+        //      the image); only then are the masked pixels marked consumed (key -2) one by one.
+        double wv[4][2];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                double w = w_[r][c];
+                if (MODE == 2) {
+                    const double S = w_[r][c], N = n_[r][c];
+                    w = 1.0;
+                    if (!a.uniform_weight) { const double qq = __ddiv_rn(S, N); w = __dmul_rn(qq, qq); }
+                    // a non-finite signal or noise poisons the weight
+                    if (!((fabs(S) <= 1.7976931348623157e308) && (fabs(N) <= 1.7976931348623157e308))) w = TESS_NAN;
+                }
+                wv[r][c] = w;
+            }
+        const double c0 = __dadd_rn(__dadd_rn(wv[0][0], wv[1][0]), __dadd_rn(wv[2][0], wv[3][0]));
+        const double c1 = __dadd_rn(__dadd_rn(wv[0][1], wv[1][1]), __dadd_rn(wv[2][1], wv[3][1]));
+        const double wtot = __dadd_rn(c0, c1);
+        const bool all_clean = __all_sync(TESS_FULL, fabs(wtot) <= 1.7976931348623157e308);
+        if (!all_clean) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+                    bs[r][c] = (fabs(wv[r][c]) <= 1.7976931348623157e308) ? bs[r][c] : -2;
+        }
+        if (uniform && all_clean) {
+            // closed form for a one-bin patch: sum w x = X0 col0 + X1 col1, sum w y = sum_r Y_r row_r
+            const bool sw = (cur.key != ukey);
+            if (__any_sync(TESS_FULL, sw)) {
+                tess_table_flush<NV>(sw && cur.n > 0, cur.key, cur.n, cur.v, tab, sm.claim, lane);
+                cur.key = ukey;
+                cur.n = sw ? 0 : cur.n;
+#pragma unroll
+                for (int i = 0; i < NV; ++i) cur.v[i] = sw ? 0.0 : cur.v[i];
+            }
+            double sy = 0.0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) sy = __dadd_rn(sy, __dmul_rn(__dadd_rn(wv[r][0], wv[r][1]), Y[r]));
+            cur.n += 8;
+            cur.v[0] = __dadd_rn(cur.v[0], wtot);
+            cur.v[1] = __dadd_rn(cur.v[1], __dadd_rn(__dmul_rn(c0, X0), __dmul_rn(c1, X1)));
+            cur.v[2] = __dadd_rn(cur.v[2], sy);
+            if (MODE == 2) {
+                double ss = 0.0, nn = 0.0;
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        ss = __dadd_rn(ss, w_[r][c]);
+                        nn = __dadd_rn(nn, __dmul_rn(n_[r][c], n_[r][c]));
+                    }
+                cur.v[NV - 2] = __dadd_rn(cur.v[NV - 2], ss);
+                cur.v[NV - 1] = __dadd_rn(cur.v[NV - 1], nn);
+            }
+        } else {
+            // Rounds (no lane-divergent branch): a lane whose run's bin is no longer among its
+            // unconsumed pixels ends the run and starts the run of one of the remaining bins;
+            // then every lane folds all its pixels of its run's bin.
+            for (;;) {
+                const int rest = max(max(max(bs[0][0], bs[0][1]), max(bs[1][0], bs[1][1])),
+                                     max(max(bs[2][0], bs[2][1]), max(bs[3][0], bs[3][1])));
+                if (!__any_sync(TESS_FULL, rest >= 0)) break;
+                bool present = false;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) present = present || (bs[r][0] == cur.key) || (bs[r][1] == cur.key);
+                const bool sw = (rest >= 0) && !present;
+                if (__any_sync(TESS_FULL, sw)) {
+                    tess_table_flush<NV>(sw && cur.n > 0, cur.key, cur.n, cur.v, tab, sm.claim, lane);
+                    cur.key = sw ? rest : cur.key;
+                    cur.n = sw ? 0 : cur.n;
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) cur.v[i] = sw ? 0.0 : cur.v[i];
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const bool hit = (bs[r][c] == cur.key);
+                        const double w = hit ? wv[r][c] : 0.0;
+                        cur.n += hit ? 1 : 0;
+                        cur.v[0] = __dadd_rn(cur.v[0], w);
+                        cur.v[1] = __dadd_rn(cur.v[1], __dmul_rn(w, c ? X1 : X0));
+                        cur.v[2] = __dadd_rn(cur.v[2], __dmul_rn(w, Y[r]));
+                        if (MODE == 2) {
+                            cur.v[NV - 2] = __dadd_rn(cur.v[NV - 2], hit ? w_[r][c] : 0.0);
+                            const double nz = hit ? n_[r][c] : 0.0;
+                            cur.v[NV - 1] = __dadd_rn(cur.v[NV - 1], __dmul_rn(nz, nz));
+                        }
+                        bs[r][c] = hit ? -2 : bs[r][c];
+                    }
+                }
+            }
+        }
+    }   // steps
+
+    // ---- end of the quadrant: retire the live runs (merged across the warp), table -> global
+    if (MODE != 0) {
+        tess_warp_retire<NV>(cur, tab, lane);
+        for (int e = lane; e < c_q; e += 32) {
+            const double* t = tab + e * (NV + 1);
+            if (t[0] != 0.0) {
+                double* m = a.mom + (long)gidv[e] * (NV + 1);
+#pragma unroll
+                for (int i = 0; i <= NV; ++i) { tess_gmem_add(m + i, t[i]); tab[e * (NV + 1) + i] = 0.0; }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// MODE 0: labels only; 1: density map (4 moments); 2: signal + noise maps (6 moments).
+// EDGE = false: the interior quadrants (every access in bounds and aligned; `vec` must hold);
+// EDGE = true: the remaining ones (image edges; all of them when vec == 0), with guarded accesses.
+template <int MODE, bool HAS_SCALE, bool EDGE>
 __global__ void __launch_bounds__(TESS_MAIN_THREADS, (MODE == 2) ? TESS_MAIN_MINBLOCKS_SN : TESS_MAIN_MINBLOCKS)
-k_image_main(TessImgArgs a) {
+k_image_main(TessImgArgs a, int vec) {
     constexpr int NV = (MODE == 2) ? 5 : 3;
     constexpr int NW = TESS_MAIN_THREADS / 32;
     constexpr int QC = TESS_QCAP(MODE);
@@ -387,25 +754,15 @@ k_image_main(TessImgArgs a) {
     __shared__ __align__(16) TessWarpSmem<MODE, HAS_SCALE> s_w[NW];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     TessWarpSmem<MODE, HAS_SCALE>& sm = s_w[wib];
-    const int cx = lane & 15, ry = lane >> 4;          // patch: cols 2cx,2cx+1; rows 4ry..4ry+3
-    const int leaf = cx >> 2;                          // 8-px-wide leaf of the warp tile
-    const int blk = cx >> 3;                           // 16-px-wide block
     double* const tab = sm.tab;
     const double* const src = (MODE == 2) ? a.sig : a.dens;   // MODE 1: weight map; MODE 2: signal map
     const int n_q = a.L.nqx * a.L.nqy;               // < 2^31 (checked by the host)
-    const int Wi = (int)a.W, Hi = (int)a.H;
     const int stride = (int)gridDim.x * NW;
 
     if (MODE != 0) {
         for (int i = lane; i < QC * (NV + 1); i += 32) tab[i] = 0.0;
         __syncwarp();
     }
-    TessRun<NV> cur;                 // the lane's running same-bin sum (registers)
-    cur.key = -1;
-    cur.n = 0;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) cur.v[i] = 0.0;
-
     // ---- software pipeline over this warp's quadrants q, q + stride, ...: the list of quadrant i+1 is
     //      copied to shared memory (cp.async) while quadrant i is processed; (offset, count) of
     //      quadrant i+2 are loaded at the same time.
@@ -433,9 +790,10 @@ k_image_main(TessImgArgs a) {
         tess_cp_async_wait();          // this quadrant's list has landed
         __syncwarp();
         if (q1 < n_q) stage(buf ^ 1, off1, cnt1);
-        const int cnt_cur = cnt, off_cur = off;
         const int qy = q / a.L.nqx, qx = q - qy * a.L.nqx;
         const int qx0 = 32 * qx, qy0 = 32 * qy;            // pixel coordinates fit 32 bits (host-checked)
+        const bool interior = vec && (qx0 + 32 <= a.W) && (qy0 + 32 <= a.H);
+        const int cnt_cur = (interior != EDGE) ? cnt : 0, off_cur = off;   // the other kernel's quadrants are skipped
         if (cnt_cur != 0) {
         if (cnt_cur < 0 || cnt_cur > QC) {
             // slow path: list too long for the fast path (scan it from global memory) or overflow of
@@ -447,357 +805,9 @@ k_image_main(TessImgArgs a) {
                 tess_quadrant_scan<MODE, HAS_SCALE>(a, labels, qx0, qy0, reinterpret_cast<const double2*>(a.node), nullptr,
                                                     a.inv_s2, a.k);
         } else {
-        const double2* const qxy = sm.qxy[buf];
-        const double* const qinv = HAS_SCALE ? sm.qinv[buf] : nullptr;
-        const int* const gidv = sm.qgid[buf];
-        const int c_q = cnt_cur;
-        // interior quadrant: every pixel access is in bounds (and 16-byte aligned: VEC)
-        const bool interior = VEC && (qx0 + 32 <= a.W) && (qy0 + 32 <= a.H);
-        const int px = qx0 + 2 * cx;                     // first column of this lane
-        const double X0 = a.x0 + (double)px, X1 = a.x0 + (double)(px + 1);
-
-        // ---- one-bin quadrant (a single candidate, interior, MODE 1): constant labels, closed-form
-        //      patch sums, one shuffle reduction and four global reductions for the whole quadrant
-        if (MODE == 1 && c_q == 1 && interior) {
-            const int gid = gidv[0];
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-            bool clean = true;
-#pragma unroll
-            for (int step = 0; step < 4; ++step) {
-                const int py = qy0 + 8 * step + 4 * ry;
-                const long base0 = (long)py * a.W + px;
-                double2 v[4];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    v[r] = *reinterpret_cast<const double2*>(src + base0 + r * a.W);
-                    *reinterpret_cast<int2*>(labels + base0 + r * a.W) = make_int2(gid, gid);
-                }
-                const double c0 = __dadd_rn(__dadd_rn(v[0].x, v[1].x), __dadd_rn(v[2].x, v[3].x));
-                const double c1 = __dadd_rn(__dadd_rn(v[0].y, v[1].y), __dadd_rn(v[2].y, v[3].y));
-                double sy = 0.0;
-#pragma unroll
-                for (int r = 0; r < 4; ++r) sy = __dadd_rn(sy, __dmul_rn(__dadd_rn(v[r].x, v[r].y), a.y0 + (double)(py + r)));
-                const double t = __dadd_rn(c0, c1);
-                clean = clean && (fabs(t) <= 1.7976931348623157e308);
-                s0 = __dadd_rn(s0, t);
-                s1 = __dadd_rn(s1, __dadd_rn(__dmul_rn(c0, X0), __dmul_rn(c1, X1)));
-                s2 = __dadd_rn(s2, sy);
-            }
-            if (__all_sync(TESS_FULL, clean)) {
-#pragma unroll
-                for (int m = 16; m >= 1; m >>= 1) {
-                    s0 = __dadd_rn(s0, __shfl_xor_sync(TESS_FULL, s0, m));
-                    s1 = __dadd_rn(s1, __shfl_xor_sync(TESS_FULL, s1, m));
-                    s2 = __dadd_rn(s2, __shfl_xor_sync(TESS_FULL, s2, m));
-                }
-                if (lane < 4) {
-                    double* m = a.mom + (long)gid * (NV + 1);
-                    tess_gmem_add(m + lane, lane == 0 ? 1024.0 : (lane == 1 ? s0 : (lane == 2 ? s1 : s2)));
-                }
-                goto quadrant_done;
-            }
-            // a masked pixel somewhere: fall through to the general path (labels are rewritten there)
-        }
-
-        // ---- request the pixels of the first warp tile (the accumulator table is all zero here: it
-        //      is cleared once at kernel start and every entry is zeroed again when it is flushed)
-#if TESS_PREFETCH
-        double wn_[4][2], nn_[4][2];
-        if (MODE != 0) tess_load_patch<MODE, VEC>(a, src, interior, px, qy0 + 4 * ry, wn_, nn_);
-#endif
-
-        const unsigned short* pl = nullptr;   // parent list of the leaf filter (quadrant-list positions)
-        bool p_ident = true;
-        int p_len = c_q;
-
-        for (int step = 0; step < 4; ++step) {
-            const int wy0 = qy0 + 8 * step;
-            if (wy0 >= a.H) break;                         // warp-uniform
-            const int py = wy0 + 4 * ry;                   // first row of this lane
-            const long base0 = (long)py * a.W + px;              // flat index of the patch's first pixel
-            double Y[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) Y[r] = a.y0 + (double)(py + r);
-
-            // ---- pixel data of this warp tile was requested one warp tile ahead (software pipeline).
-            //      Pixels outside the image read as NaN and drop out with the masked ones.
-            double w_[4][2], n_[4][2];                     // MODE 1: weight; MODE 2: signal, noise
-            if (MODE != 0) {
-#if TESS_PREFETCH
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) { w_[r][c] = wn_[r][c]; if (MODE == 2) n_[r][c] = nn_[r][c]; }
-                if (step < 3 && wy0 + 8 < a.H) tess_load_patch<MODE, VEC>(a, src, interior, px, py + 8, wn_, nn_);
-#else
-                tess_load_patch<MODE, VEC>(a, src, interior, px, py, w_, n_);
-                // cache prefetch of the next warp tile's rows (no registers held): its loads then hit
-                // in L2 / L1 instead of paying the full HBM latency
-                if (TESS_PREFETCH_CACHE && interior && step < 3) {
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        tess_prefetch(src + base0 + (8 + r) * a.W);
-                        if (MODE == 2) tess_prefetch(a.noise + base0 + (8 + r) * a.W);
-                    }
-                }
-#endif
-            }
-
-            // ---- 16x16 block lists (every other step), only where the quadrant list is long
-            if ((step & 1) == 0) {
-                pl = nullptr; p_ident = true; p_len = c_q;
-                if (c_q > TESS_BLOCK_MIN) {
-                    const int bx0 = qx0 + 16 * blk, bx1 = min(bx0 + 15, Wi - 1), by1 = min(wy0 + 15, Hi - 1);
-                    const double hx = 0.5 * (double)(bx1 - bx0), hy = 0.5 * (double)(by1 - wy0);
-                    const double rho = interior ? 10.606602778 : sqrt(hx * hx + hy * hy) * 1.0000001;   // 7.5 sqrt 2
-                    const int n = tess_filter<16, HAS_SCALE, false>(qxy, qinv, nullptr, true, c_q, c_q,
-                                                                    a.x0 + 0.5 * (double)(bx0 + bx1),
-                                                                    a.y0 + 0.5 * (double)(wy0 + by1), rho, bx0 < a.W, lane,
-                                                                    sm.bl[blk], nullptr, nullptr, TESS_BCAP);
-                    // both blocks must fit for the (warp-uniform) parent switch
-                    if (__all_sync(TESS_FULL, n <= TESS_BCAP)) { pl = sm.bl[blk]; p_ident = false; p_len = n; }
-                }
-            }
-
-            // ---- candidates of this lane's 8x8 leaf
-            double2* const lg = sm.lg[leaf];
-            unsigned short* const ls = sm.ls[leaf];
-            double* const li = HAS_SCALE ? sm.li[leaf] : nullptr;
-            int len = 0;
-            bool use_leaf = false;
-            bool uniform = (c_q == 1);                     // the whole warp tile belongs to one bin
-            int ukey = 0;
-            if (!uniform) {
-                const int p_max = __reduce_max_sync(TESS_FULL, p_len);    // the two blocks' lists differ in length
-                if (p_max > TESS_LEAF_MIN) {
-                    const int lx0 = qx0 + 8 * leaf;
-                    const int lx1 = min(lx0 + 7, Wi - 1), ly1 = min(wy0 + 7, Hi - 1);
-                    const double hx = 0.5 * (double)(lx1 - lx0), hy = 0.5 * (double)(ly1 - wy0);
-                    const double rho = interior ? 4.9497479632 : sqrt(hx * hx + hy * hy) * 1.0000001;   // 3.5 sqrt 2
-                    len = tess_filter<8, HAS_SCALE, true>(qxy, qinv, pl, p_ident, p_len, p_max,
-                                                          a.x0 + 0.5 * (double)(lx0 + lx1),
-                                                          a.y0 + 0.5 * (double)(wy0 + ly1), rho, lx0 < a.W, lane, ls, lg, li,
-                                                          TESS_LEAF_CAP);
-                    use_leaf = (len <= TESS_LEAF_CAP);
-                    // all (in-image) leaves ended with the same single candidate?
-                    const int one = (len == 1) ? (int)ls[0] : ((lx0 < a.W) ? -1 : -3);
-                    const int ref = __reduce_max_sync(TESS_FULL, one);
-                    uniform = (ref >= 0) && __all_sync(TESS_FULL, one == ref || one == -3);
-                    ukey = ref;
-                }
-            }
-
-            int bs[4][2];                                  // winning quadrant-list position per pixel
-            if (uniform) {
-                // ---- one bin for all 256 pixels: constant labels
-                const int gid = gidv[ukey];
-                if (interior) {
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) *reinterpret_cast<int2*>(labels + base0 + r * a.W) = make_int2(gid, gid);
-                } else {
-#pragma unroll
-                    for (int r = 0; r < 4; ++r)
-#pragma unroll
-                        for (int c = 0; c < 2; ++c)
-                            if ((py + r < a.H) && (px + c < a.W)) labels[base0 + r * a.W + c] = gid;
-                }
-#pragma unroll
-                for (int r = 0; r < 4; ++r) { bs[r][0] = ukey; bs[r][1] = ukey; }
-            } else {
-                // ---- evaluate the surviving candidates with the pinned formula.  Lists are in no
-                //      particular order, so an exact tie (d == best so far) is only RECORDED here; the
-                //      rare warp that saw one re-evaluates with the full (distance, index) order below.
-                double bd[4][2];
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) { bd[r][c] = INFINITY; bs[r][c] = 0; }
-                const int n_ev = use_leaf ? len : p_len;
-                bool tied = false;
-                for (int j = 0; j < n_ev; ++j) {
-                    double2 g;
-                    int e;
-                    double inv = 1.0;
-                    if (use_leaf) {
-                        g = lg[j];
-                        e = ls[j];
-                        if (HAS_SCALE) inv = li[j];
-                    } else {
-                        e = p_ident ? j : (int)pl[j];
-                        g = qxy[e];
-                        if (HAS_SCALE) inv = qinv[e];
-                    }
-                    const double dx0 = __dsub_rn(X0, g.x), dx1 = __dsub_rn(X1, g.x);
-                    const double dxx0 = __dmul_rn(dx0, dx0), dxx1 = __dmul_rn(dx1, dx1);
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const double dy = __dsub_rn(Y[r], g.y);
-                        const double dyy = __dmul_rn(dy, dy);
-                        double d0 = __dadd_rn(dxx0, dyy), d1 = __dadd_rn(dxx1, dyy);
-                        if (HAS_SCALE) { d0 = __dmul_rn(d0, inv); d1 = __dmul_rn(d1, inv); }
-                        tied = tied || (d0 == bd[r][0]) || (d1 == bd[r][1]);
-                        if (d0 < bd[r][0]) { bd[r][0] = d0; bs[r][0] = e; }
-                        if (d1 < bd[r][1]) { bd[r][1] = d1; bs[r][1] = e; }
-                    }
-                }
-                if (__any_sync(TESS_FULL, tied)) {
-                    // exact ties: lowest generator index wins
-                    int bg[4][2];
-#pragma unroll
-                    for (int r = 0; r < 4; ++r)
-#pragma unroll
-                        for (int c = 0; c < 2; ++c) { bd[r][c] = INFINITY; bs[r][c] = 0; bg[r][c] = 0x7fffffff; }
-                    for (int j = 0; j < n_ev; ++j) {
-                        int e;
-                        if (use_leaf) e = ls[j];
-                        else e = p_ident ? j : (int)pl[j];
-                        const double2 g = qxy[e];
-                        const double inv = HAS_SCALE ? qinv[e] : 1.0;
-                        const int gid = gidv[e];
-#pragma unroll
-                        for (int r = 0; r < 4; ++r)
-#pragma unroll
-                            for (int c = 0; c < 2; ++c) {
-                                double d = tess_d2_pinned(c ? X1 : X0, Y[r], g.x, g.y);
-                                if (HAS_SCALE) d = __dmul_rn(d, inv);
-                                if ((d < bd[r][c]) || ((d == bd[r][c]) && (gid < bg[r][c]))) {
-                                    bd[r][c] = d; bs[r][c] = e; bg[r][c] = gid;
-                                }
-                            }
-                    }
-                }
-                __syncwarp();                              // the leaves' lists differ in length
-                // ---- labels out: 16 lanes x 8 B = one 128-byte line per row
-                if (interior) {
-#pragma unroll
-                    for (int r = 0; r < 4; ++r)
-                        *reinterpret_cast<int2*>(labels + base0 + r * a.W) = make_int2(gidv[bs[r][0]], gidv[bs[r][1]]);
-                } else {
-#pragma unroll
-                    for (int r = 0; r < 4; ++r)
-#pragma unroll
-                        for (int c = 0; c < 2; ++c)
-                            if ((py + r < a.H) && (px + c < a.W)) labels[base0 + r * a.W + c] = gidv[bs[r][c]];
-                }
-            }
-            if (MODE == 0) continue;
-
-            // ---- moments.  Weights first.  The sum of the patch's weights is finite iff all of them
-            //      are (up to a harmless false alarm on overflow), so one test per lane decides whether
-            //      any pixel of the warp tile is masked (non-finite weight, signal or noise; outside
-            //      the image); only then are the masked pixels marked consumed (key -2) one by one.
-            double wv[4][2];
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    double w = w_[r][c];
-                    if (MODE == 2) {
-                        const double S = w_[r][c], N = n_[r][c];
-                        w = 1.0;
-                        if (!a.uniform_weight) { const double qq = __ddiv_rn(S, N); w = __dmul_rn(qq, qq); }
-                        // a non-finite signal or noise poisons the weight
-                        if (!((fabs(S) <= 1.7976931348623157e308) && (fabs(N) <= 1.7976931348623157e308))) w = TESS_NAN;
-                    }
-                    wv[r][c] = w;
-                }
-            const double c0 = __dadd_rn(__dadd_rn(wv[0][0], wv[1][0]), __dadd_rn(wv[2][0], wv[3][0]));
-            const double c1 = __dadd_rn(__dadd_rn(wv[0][1], wv[1][1]), __dadd_rn(wv[2][1], wv[3][1]));
-            const double wtot = __dadd_rn(c0, c1);
-            const bool all_clean = __all_sync(TESS_FULL, fabs(wtot) <= 1.7976931348623157e308);
-            if (!all_clean) {
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-#pragma unroll
-                    for (int c = 0; c < 2; ++c)
-                        bs[r][c] = (fabs(wv[r][c]) <= 1.7976931348623157e308) ? bs[r][c] : -2;
-            }
-            if (uniform && all_clean) {
-                // closed form for a one-bin patch: sum w x = X0 col0 + X1 col1, sum w y = sum_r Y_r row_r
-                const bool sw = (cur.key != ukey);
-                if (__any_sync(TESS_FULL, sw)) {
-                    tess_table_flush<NV>(sw && cur.n > 0, cur.key, cur.n, cur.v, tab, sm.claim, lane);
-                    cur.key = ukey;
-                    cur.n = sw ? 0 : cur.n;
-#pragma unroll
-                    for (int i = 0; i < NV; ++i) cur.v[i] = sw ? 0.0 : cur.v[i];
-                }
-                double sy = 0.0;
-#pragma unroll
-                for (int r = 0; r < 4; ++r) sy = __dadd_rn(sy, __dmul_rn(__dadd_rn(wv[r][0], wv[r][1]), Y[r]));
-                cur.n += 8;
-                cur.v[0] = __dadd_rn(cur.v[0], wtot);
-                cur.v[1] = __dadd_rn(cur.v[1], __dadd_rn(__dmul_rn(c0, X0), __dmul_rn(c1, X1)));
-                cur.v[2] = __dadd_rn(cur.v[2], sy);
-                if (MODE == 2) {
-                    double ss = 0.0, nn = 0.0;
-#pragma unroll
-                    for (int r = 0; r < 4; ++r)
-#pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            ss = __dadd_rn(ss, w_[r][c]);
-                            nn = __dadd_rn(nn, __dmul_rn(n_[r][c], n_[r][c]));
-                        }
-                    cur.v[NV - 2] = __dadd_rn(cur.v[NV - 2], ss);
-                    cur.v[NV - 1] = __dadd_rn(cur.v[NV - 1], nn);
-                }
-            } else {
-                // Rounds (no lane-divergent branch): a lane whose run's bin is no longer among its
-                // unconsumed pixels ends the run and starts the run of one of the remaining bins;
-                // then every lane folds all its pixels of its run's bin.
-                for (;;) {
-                    const int rest = max(max(max(bs[0][0], bs[0][1]), max(bs[1][0], bs[1][1])),
-                                         max(max(bs[2][0], bs[2][1]), max(bs[3][0], bs[3][1])));
-                    if (!__any_sync(TESS_FULL, rest >= 0)) break;
-                    bool present = false;
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) present = present || (bs[r][0] == cur.key) || (bs[r][1] == cur.key);
-                    const bool sw = (rest >= 0) && !present;
-                    if (__any_sync(TESS_FULL, sw)) {
-                        tess_table_flush<NV>(sw && cur.n > 0, cur.key, cur.n, cur.v, tab, sm.claim, lane);
-                        cur.key = sw ? rest : cur.key;
-                        cur.n = sw ? 0 : cur.n;
-#pragma unroll
-                        for (int i = 0; i < NV; ++i) cur.v[i] = sw ? 0.0 : cur.v[i];
-                    }
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-#pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            const bool hit = (bs[r][c] == cur.key);
-                            const double w = hit ? wv[r][c] : 0.0;
-                            cur.n += hit ? 1 : 0;
-                            cur.v[0] = __dadd_rn(cur.v[0], w);
-                            cur.v[1] = __dadd_rn(cur.v[1], __dmul_rn(w, c ? X1 : X0));
-                            cur.v[2] = __dadd_rn(cur.v[2], __dmul_rn(w, Y[r]));
-                            if (MODE == 2) {
-                                cur.v[NV - 2] = __dadd_rn(cur.v[NV - 2], hit ? w_[r][c] : 0.0);
-                                const double nz = hit ? n_[r][c] : 0.0;
-                                cur.v[NV - 1] = __dadd_rn(cur.v[NV - 1], __dmul_rn(nz, nz));
-                            }
-                            bs[r][c] = hit ? -2 : bs[r][c];
-                        }
-                    }
-                }
-            }
-        }   // steps
-
-        // ---- end of the quadrant: retire the live runs (merged across the warp), table -> global
-        if (MODE != 0) {
-            tess_warp_retire<NV>(cur, tab, lane);
-            for (int e = lane; e < c_q; e += 32) {
-                const double* t = tab + e * (NV + 1);
-                if (t[0] != 0.0) {
-                    double* m = a.mom + (long)gidv[e] * (NV + 1);
-#pragma unroll
-                    for (int i = 0; i <= NV; ++i) { tess_gmem_add(m + i, t[i]); tab[e * (NV + 1) + i] = 0.0; }
-                }
-            }
-            __syncwarp();
-        }
+        tess_quadrant_body<MODE, HAS_SCALE, !EDGE>(a, sm, buf, labels, src, cnt_cur, qx0, qy0, lane);
         }   // fast path
         }   // cnt != 0
-    quadrant_done:
         // ---- rotate the pipeline
         q = q1; cnt = cnt1; off = off1;
         q1 = q2; cnt1 = cnt2; off1 = off2;
