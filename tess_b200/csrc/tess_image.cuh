@@ -123,7 +123,7 @@ TESS_DEVFN void tess_table_flush(bool flush, int key, int n, const double (&v)[N
     bool pending = flush;
     while (__any_sync(TESS_FULL, pending)) {
         if (pending) claim[key] = (unsigned short)lane;
-        __syncwarp();
+        __syncwarp();     // orders the previous turn's table writes before this turn's, publishes the claims
         if (pending && claim[key] == (unsigned short)lane) {
             double* t = tab + key * (NV + 1);
             t[0] += (double)n;
@@ -131,8 +131,8 @@ TESS_DEVFN void tess_table_flush(bool flush, int key, int n, const double (&v)[N
             for (int i = 0; i < NV; ++i) t[1 + i] = __dadd_rn(t[1 + i], v[i]);
             pending = false;
         }
-        __syncwarp();
     }
+    __syncwarp();
 }
 
 // End of a quadrant: every lane retires its live run.  Lanes that hold the same bin are merged with
@@ -454,7 +454,7 @@ TESS_DEVFN void tess_quadrant_body(const TessImgArgs& a, TessWarpSmem<MODE, HAS_
 
     for (int step = 0; step < 4; ++step) {
         const int wy0 = qy0 + 8 * step;
-        if (wy0 >= a.H) break;                         // warp-uniform
+        if (!interior && wy0 >= a.H) break;            // warp-uniform
         const int py = wy0 + 4 * ry;                   // first row of this lane
         const long base0 = (long)py * a.W + px;              // flat index of the patch's first pixel
         double Y[4];
@@ -489,12 +489,13 @@ TESS_DEVFN void tess_quadrant_body(const TessImgArgs& a, TessWarpSmem<MODE, HAS_
         if ((step & 1) == 0) {
             pl = nullptr; p_ident = true; p_len = c_q;
             if (c_q > TESS_BLOCK_MIN) {
-                const int bx0 = qx0 + 16 * blk, bx1 = min(bx0 + 15, Wi - 1), by1 = min(wy0 + 15, Hi - 1);
+                const int bx0 = qx0 + 16 * blk;
+                const int bx1 = interior ? bx0 + 15 : min(bx0 + 15, Wi - 1), by1 = interior ? wy0 + 15 : min(wy0 + 15, Hi - 1);
                 const double hx = 0.5 * (double)(bx1 - bx0), hy = 0.5 * (double)(by1 - wy0);
                 const double rho = interior ? 10.606602778 : sqrt(hx * hx + hy * hy) * 1.0000001;   // 7.5 sqrt 2
                 const int n = tess_filter<16, HAS_SCALE, false>(qxy, qinv, nullptr, true, c_q, c_q,
                                                                 a.x0 + 0.5 * (double)(bx0 + bx1),
-                                                                a.y0 + 0.5 * (double)(wy0 + by1), rho, bx0 < a.W, lane,
+                                                                a.y0 + 0.5 * (double)(wy0 + by1), rho, interior || bx0 < a.W, lane,
                                                                 sm.bl[blk], nullptr, nullptr, TESS_BCAP);
                 // both blocks must fit for the (warp-uniform) parent switch
                 if (__all_sync(TESS_FULL, n <= TESS_BCAP)) { pl = sm.bl[blk]; p_ident = false; p_len = n; }
@@ -513,16 +514,16 @@ TESS_DEVFN void tess_quadrant_body(const TessImgArgs& a, TessWarpSmem<MODE, HAS_
             const int p_max = __reduce_max_sync(TESS_FULL, p_len);    // the two blocks' lists differ in length
             if (p_max > TESS_LEAF_MIN) {
                 const int lx0 = qx0 + 8 * leaf;
-                const int lx1 = min(lx0 + 7, Wi - 1), ly1 = min(wy0 + 7, Hi - 1);
+                const int lx1 = interior ? lx0 + 7 : min(lx0 + 7, Wi - 1), ly1 = interior ? wy0 + 7 : min(wy0 + 7, Hi - 1);
                 const double hx = 0.5 * (double)(lx1 - lx0), hy = 0.5 * (double)(ly1 - wy0);
                 const double rho = interior ? 4.9497479632 : sqrt(hx * hx + hy * hy) * 1.0000001;   // 3.5 sqrt 2
                 len = tess_filter<8, HAS_SCALE, true>(qxy, qinv, pl, p_ident, p_len, p_max,
                                                       a.x0 + 0.5 * (double)(lx0 + lx1),
-                                                      a.y0 + 0.5 * (double)(wy0 + ly1), rho, lx0 < a.W, lane, ls, lg, li,
+                                                      a.y0 + 0.5 * (double)(wy0 + ly1), rho, interior || lx0 < a.W, lane, ls, lg, li,
                                                       TESS_LEAF_CAP);
                 use_leaf = (len <= TESS_LEAF_CAP);
                 // all (in-image) leaves ended with the same single candidate?
-                const int one = (len == 1) ? (int)ls[0] : ((lx0 < a.W) ? -1 : -3);
+                const int one = (len == 1) ? (int)ls[0] : ((interior || lx0 < a.W) ? -1 : -3);
                 const int ref = __reduce_max_sync(TESS_FULL, one);
                 uniform = (ref >= 0) && __all_sync(TESS_FULL, one == ref || one == -3);
                 ukey = ref;
