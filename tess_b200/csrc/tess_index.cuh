@@ -206,13 +206,31 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
         // ---- 1. box search for R.  Box rows are walked 32 at a time, one row per lane; a chunk whose
         //      rows hold few generators is walked row-parallel (every lane its own row), a dense one
         //      row by row with all lanes.  The ring starts near the one that sufficed last time.
+        //      While walking, the box generators are also staged in shared memory (if they fit), so
+        //      that step 2 needs no second pass over global memory.
         double rbest;
         int ring = max(1, (tile_ring[t] * 3) / 4);
         int xi0, xi1, xj0, xj1;
+        int n_box;
         for (;;) {
             xi0 = max(ci0 - ring, 0); xi1 = min(ci1 + ring, g.gw - 1);
             xj0 = max(cj0 - ring, 0); xj1 = min(cj1 + ring, g.gh - 1);
             rbest = INFINITY;
+            if (lane == 0) s_cnt[wib] = 0;
+            __syncwarp();
+            auto look = [&](int i) {
+                const double2 p = cell_xy[i];
+                double pv = 1.0;
+                double d = tess_maxd2(r, p.x, p.y);
+                if (HAS_SCALE) { pv = cell_inv[i]; d *= pv; }
+                rbest = fmin(rbest, d);
+                const int pos = atomicAdd(&s_cnt[wib], 1);
+                if (pos < TESS_CAP) {
+                    xy[pos] = p;
+                    if (HAS_SCALE) iv[pos] = pv;
+                    key[pos] = (unsigned long long)(unsigned)i;      // slot for now
+                }
+            };
             for (int j0 = xj0; j0 <= xj1; j0 += 32) {
                 const int j = j0 + lane;
                 int s = 0, e = 0;
@@ -223,26 +241,19 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
                 const int rows = min(32, xj1 - j0 + 1);
                 const int tot = __reduce_add_sync(TESS_FULL, e - s);
                 if (tot <= 6 * rows) {
-                    for (int i = s; i < e; ++i) {
-                        const double2 p = cell_xy[i];
-                        double d = tess_maxd2(r, p.x, p.y);
-                        if (HAS_SCALE) d *= cell_inv[i];
-                        rbest = fmin(rbest, d);
-                    }
+                    for (int i = s; i < e; ++i) look(i);
                     __syncwarp();
                 } else {
                     for (int src = 0; src < rows; ++src) {
                         const int ss = __shfl_sync(TESS_FULL, s, src), ee = __shfl_sync(TESS_FULL, e, src);
-                        for (int i = ss + lane; i < ee; i += 32) {
-                            const double2 p = cell_xy[i];
-                            double d = tess_maxd2(r, p.x, p.y);
-                            if (HAS_SCALE) d *= cell_inv[i];
-                            rbest = fmin(rbest, d);
-                        }
+                        for (int i = ss + lane; i < ee; i += 32) look(i);
                     }
+                    __syncwarp();
                 }
             }
             rbest = tess_warp_min(rbest);
+            n_box = s_cnt[wib];
+            __syncwarp();     // every lane has read the count before lane 0 resets it for the next ring
             const bool whole = (ci0 - ring <= 0 && cj0 - ring <= 0 && ci1 + ring >= g.gw - 1 && cj1 + ring >= g.gh - 1);
             if (whole) break;
             // every generator outside the box is at least `ring` whole cells away from the tile
@@ -253,45 +264,76 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
         if (lane == 0) tile_ring[t] = ring;
         const double thr = rbest * TESS_SLACK;
 
-        // ---- 2. stage every generator of the box with mind2 [* inv_s2] <= R (any order: sorted below)
-        if (lane == 0) s_cnt[wib] = 0;
-        __syncwarp();
-        for (int j0 = xj0; j0 <= xj1; j0 += 32) {
-            const int j = j0 + lane;
-            int s = 0, e = 0;
-            if (j <= xj1) {
-                s = cell_start[(long)j * g.gw + xi0];
-                e = cell_start[(long)j * g.gw + xi1 + 1];
-            }
-            const int rows = min(32, xj1 - j0 + 1);
-            const int tot = __reduce_add_sync(TESS_FULL, e - s);
-            auto take = [&](int i) {
-                const double2 p = cell_xy[i];
-                double d = tess_mind2(r, p.x, p.y);
+        // ---- 2. keep every generator of the box with mind2 [* inv_s2] <= R (any order)
+        int cnt;   // warp-uniform
+        if (n_box <= TESS_CAP) {
+            // in shared memory: order-free compaction in place (write position <= read position)
+            cnt = 0;
+            for (int b0 = 0; b0 < n_box; b0 += 32) {
+                const int i = b0 + lane;
+                double2 p = make_double2(0.0, 0.0);
                 double pv = 1.0;
-                if (HAS_SCALE) { pv = cell_inv[i]; d *= pv; }
-                if (d <= thr) {
-                    const int pos = atomicAdd(&s_cnt[wib], 1);
-                    if (pos < TESS_CAP) {
-                        xy[pos] = p;
-                        if (HAS_SCALE) iv[pos] = pv;
-                        key[pos] = (unsigned long long)(unsigned)i;      // slot for now
-                    }
+                unsigned long long kv = 0ull;
+                bool keep = false;
+                if (i < n_box) {
+                    p = xy[i];
+                    kv = key[i];
+                    double d = tess_mind2(r, p.x, p.y);
+                    if (HAS_SCALE) { pv = iv[i]; d *= pv; }
+                    keep = d <= thr;
                 }
-            };
-            if (tot <= 6 * rows) {
-                for (int i = s; i < e; ++i) take(i);
+                const unsigned bb = __ballot_sync(TESS_FULL, keep);
                 __syncwarp();
-            } else {
-                for (int src = 0; src < rows; ++src) {
-                    const int ss = __shfl_sync(TESS_FULL, s, src), ee = __shfl_sync(TESS_FULL, e, src);
-                    for (int i = ss + lane; i < ee; i += 32) take(i);
+                if (keep) {
+                    const int pos = cnt + __popc(bb & tess_lanemask_lt(lane));
+                    xy[pos] = p;
+                    key[pos] = kv;
+                    if (HAS_SCALE) iv[pos] = pv;
+                }
+                cnt += __popc(bb);
+                __syncwarp();
+            }
+        } else {
+            // the box does not fit: second pass over the grid cells
+            if (lane == 0) s_cnt[wib] = 0;
+            __syncwarp();
+            for (int j0 = xj0; j0 <= xj1; j0 += 32) {
+                const int j = j0 + lane;
+                int s = 0, e = 0;
+                if (j <= xj1) {
+                    s = cell_start[(long)j * g.gw + xi0];
+                    e = cell_start[(long)j * g.gw + xi1 + 1];
+                }
+                const int rows = min(32, xj1 - j0 + 1);
+                const int tot = __reduce_add_sync(TESS_FULL, e - s);
+                auto take = [&](int i) {
+                    const double2 p = cell_xy[i];
+                    double d = tess_mind2(r, p.x, p.y);
+                    double pv = 1.0;
+                    if (HAS_SCALE) { pv = cell_inv[i]; d *= pv; }
+                    if (d <= thr) {
+                        const int pos = atomicAdd(&s_cnt[wib], 1);
+                        if (pos < TESS_CAP) {
+                            xy[pos] = p;
+                            if (HAS_SCALE) iv[pos] = pv;
+                            key[pos] = (unsigned long long)(unsigned)i;      // slot for now
+                        }
+                    }
+                };
+                if (tot <= 6 * rows) {
+                    for (int i = s; i < e; ++i) take(i);
+                    __syncwarp();
+                } else {
+                    for (int src = 0; src < rows; ++src) {
+                        const int ss = __shfl_sync(TESS_FULL, s, src), ee = __shfl_sync(TESS_FULL, e, src);
+                        for (int i = ss + lane; i < ee; i += 32) take(i);
+                    }
                     __syncwarp();
                 }
             }
+            __syncwarp();
+            cnt = s_cnt[wib];
         }
-        __syncwarp();
-        const int cnt = s_cnt[wib];   // warp-uniform
         const bool overflow = cnt > TESS_CAP;
 
         // ---- 3. generator indices of the staged candidates
