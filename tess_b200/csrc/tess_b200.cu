@@ -695,7 +695,8 @@ extern "C" int tess_lloyd_update(tess_ctx* c, void* stream) {
     if (!c->mom) return tess_fail(TESS_ERR_STATE, "tess_lloyd_update: no accumulate has run");
     cudaStream_t s = S(stream);
     const int M = n_moments(c);
-    const int nb = (c->k + 255) / 256;
+    int nb = (c->k + 255) / 256;
+    if (nb > c->sm_count * 4) nb = c->sm_count * 4;
     double* tail = c->mom + (long)c->k * M;
     if (M == 6)
         TESS_LAUNCH((k_update_nodes<6>), nb, 256, s, c->st, 1, c->mom, tail, c->k, c->node, c->has_scale ? c->scale : nullptr,

@@ -186,7 +186,7 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
     if (TESS_STOPPED(st, honor)) return;
     __shared__ __align__(16) double2 s_xy[TESS_LIST_WARPS][TESS_CAP];
     __shared__ double s_iv[HAS_SCALE ? TESS_LIST_WARPS : 1][HAS_SCALE ? TESS_CAP : 1];
-    __shared__ unsigned long long s_key[TESS_LIST_WARPS][TESS_CAP];
+    __shared__ unsigned s_key[TESS_LIST_WARPS][TESS_CAP];
     __shared__ int s_cnt[TESS_LIST_WARPS];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int warp = blockIdx.x * TESS_LIST_WARPS + wib;
@@ -194,7 +194,7 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
     const double min_inv = HAS_SCALE ? st->min_inv_s2 : 1.0;
     double2* const xy = s_xy[wib];
     double* const iv = HAS_SCALE ? s_iv[wib] : nullptr;
-    unsigned long long* const key = s_key[wib];
+    unsigned* const key = s_key[wib];       // grid slot, later generator index
 
     for (int t = warp; t < T.n_tiles; t += n_warps) {
         const TessRect r = tess_tile_rect(T, t);
@@ -228,7 +228,7 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
                 if (pos < TESS_CAP) {
                     xy[pos] = p;
                     if (HAS_SCALE) iv[pos] = pv;
-                    key[pos] = (unsigned long long)(unsigned)i;      // slot for now
+                    key[pos] = (unsigned)i;      // slot for now
                 }
             };
             for (int j0 = xj0; j0 <= xj1; j0 += 32) {
@@ -273,7 +273,7 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
                 const int i = b0 + lane;
                 double2 p = make_double2(0.0, 0.0);
                 double pv = 1.0;
-                unsigned long long kv = 0ull;
+                unsigned kv = 0u;
                 bool keep = false;
                 if (i < n_box) {
                     p = xy[i];
@@ -316,7 +316,7 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
                         if (pos < TESS_CAP) {
                             xy[pos] = p;
                             if (HAS_SCALE) iv[pos] = pv;
-                            key[pos] = (unsigned long long)(unsigned)i;      // slot for now
+                            key[pos] = (unsigned)i;      // slot for now
                         }
                     }
                 };
@@ -338,7 +338,7 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
 
         // ---- 3. generator indices of the staged candidates
         if (!overflow)
-            for (int i = lane; i < cnt; i += 32) key[i] = (unsigned long long)(unsigned)cell_items[(int)key[i]];
+            for (int i = lane; i < cnt; i += 32) key[i] = (unsigned)cell_items[(int)key[i]];
         __syncwarp();
 
         // ---- 4. the four quadrants: one pass for the four centre minima, one for the keep flags
@@ -434,7 +434,7 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
                         const int i = 32 * b + lane;
                         const unsigned o = off + wpos + __popc(bb & tess_lanemask_lt(lane));
                         L.xy[o] = xy[i];
-                        L.gid[o] = (int)(unsigned)key[i];
+                        L.gid[o] = (int)key[i];
                         if (HAS_SCALE) L.inv[o] = iv[i];
                     }
                     wpos += __popc(bb);

@@ -88,27 +88,30 @@ k_update_nodes(TessState* st, int honor, const double* mom, const double* mom_ta
     __shared__ double s_red[8];
     __shared__ int s_last;
     const bool changed = mom_tail[TESS_TAIL_CHANGED] != 0.0;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (changed) {
         double d = 0.0;
-        if (j < k) {
+        // grid-stride: a few hundred CTAs whatever k is, so the per-CTA atomics (delta, ticket) stay few
+        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < k; j += gridDim.x * blockDim.x) {
             const double* m = mom + (long)j * M;
+            // the moment row as 128-bit loads (rows are 32 or 48 bytes, 16-byte aligned)
+            const double2 m01 = *reinterpret_cast<const double2*>(m), m23 = *reinterpret_cast<const double2*>(m + 2);
             double nx = 0.0, ny = 0.0;
-            if (m[0] > 0.0) {   // population test, not weight (lloyd.pyx:68)
-                nx = __ddiv_rn(m[2], m[1]);
-                ny = __ddiv_rn(m[3], m[1]);
+            if (m01.x > 0.0) {   // population test, not weight (lloyd.pyx:68)
+                nx = __ddiv_rn(m23.x, m01.y);
+                ny = __ddiv_rn(m23.y, m01.y);
             }
             if (!(isfinite(nx) && isfinite(ny))) atomicOr(&st->flags, TESS_FLAG_NONFINITE);
-            const double dx = __dsub_rn(node[2 * (long)j], nx), dy = __dsub_rn(node[2 * (long)j + 1], ny);
-            d = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-            node[2 * (long)j] = nx;
-            node[2 * (long)j + 1] = ny;
+            double2* np = reinterpret_cast<double2*>(node) + j;
+            const double2 old = *np;
+            const double dx = __dsub_rn(old.x, nx), dy = __dsub_rn(old.y, ny);
+            d = __dadd_rn(d, __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+            *np = make_double2(nx, ny);
             if (M == 6 && wvt_update && scale) {
                 // WVT scale length (Diehl & Statler 2006 eq. 4, as in vorbin): sqrt(area / (S/N));
                 // bins with no pixels or no signal keep their scale.
                 const double sn = __ddiv_rn(m[4], __dsqrt_rn(m[5]));
-                if (m[0] > 0.0 && sn > 0.0 && isfinite(sn)) {
-                    const double sc = __dsqrt_rn(__ddiv_rn(m[0], sn));
+                if (m01.x > 0.0 && sn > 0.0 && isfinite(sn)) {
+                    const double sc = __dsqrt_rn(__ddiv_rn(m01.x, sn));
                     scale[j] = sc;
                     inv_s2[j] = __ddiv_rn(1.0, __dmul_rn(sc, sc));
                 }
