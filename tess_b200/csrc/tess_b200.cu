@@ -696,7 +696,7 @@ extern "C" int tess_lloyd_update(tess_ctx* c, void* stream) {
     cudaStream_t s = S(stream);
     const int M = n_moments(c);
     int nb = (c->k + 255) / 256;
-    if (nb > c->sm_count * 4) nb = c->sm_count * 4;
+    if (nb > c->sm_count * 16) nb = c->sm_count * 16;
     double* tail = c->mom + (long)c->k * M;
     if (M == 6)
         TESS_LAUNCH((k_update_nodes<6>), nb, 256, s, c->st, 1, c->mom, tail, c->k, c->node, c->has_scale ? c->scale : nullptr,

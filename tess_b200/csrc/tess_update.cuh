@@ -25,11 +25,15 @@
 __global__ void __launch_bounds__(256)
 k_count_prefilter(TessState* st, int honor, const double* mom, int M, int k, double* prev_count) {
     if (TESS_STOPPED(st, honor)) return;
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= k) return;
-    double c = mom[(long)j * M];
-    if (c != prev_count[j]) st->count_changed = 1;   // benign race: every writer stores 1
-    prev_count[j] = c;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    bool diff = false;
+    if (j < k) {
+        const double c = mom[(long)j * M];
+        diff = (c != prev_count[j]);
+        prev_count[j] = c;
+    }
+    // one store per warp at most (every writer stores 1; a store per thread would serialise in L2)
+    if (__any_sync(TESS_FULL, diff) && (threadIdx.x & 31) == 0) st->count_changed = 1;
 }
 
 // Compares the two label buffers on the pixels/points that take part in the sums.
@@ -128,9 +132,14 @@ k_update_nodes(TessState* st, int honor, const double* mom, const double* mom_ta
             if (threadIdx.x == 0) atomicAdd(&st->delta, v);
         }
     }
-    __threadfence();
+    // last-block-done: this CTA's reductions (delta by thread 0, min 1/scale^2 by every thread in WVT
+    // mode) must be performed before its ticket; the node stores need no fence (kernel boundary)
+    if (M == 6 && wvt_update && scale) __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&st->ticket2, 1u) == gridDim.x - 1) ? 1 : 0;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(&st->ticket2, 1u) == gridDim.x - 1) ? 1 : 0;
+    }
     __syncthreads();
     if (s_last && threadIdx.x == 0) {
         __threadfence();
