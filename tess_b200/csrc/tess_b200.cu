@@ -87,6 +87,7 @@ struct tess_ctx {
     long mom_cap;
     double* prev_count;
     double* scratch;   // 8 doubles (bounding-box reduction)
+    double* delta_part; // per-CTA partial deltas of k_update_nodes
     int timing;        // TESS_OPT_KERNEL_TIMING
 #ifndef TESS_EMU
     cudaEvent_t ev[2 * 512];
@@ -126,6 +127,8 @@ extern "C" int tess_ctx_create(int device, tess_ctx** out) {
         cudaMemset(c->st, 0, sizeof(TessState));
         e = cudaMalloc((void**)&c->scratch, 8 * sizeof(double));
         if (e != cudaSuccess) { r = tess_fail(TESS_ERR_NOMEM, "cudaMalloc(scratch): %s", cudaGetErrorString(e)); break; }
+        e = cudaMalloc((void**)&c->delta_part, sizeof(double) * (size_t)(c->sm_count * 16 + 16));
+        if (e != cudaSuccess) { r = tess_fail(TESS_ERR_NOMEM, "cudaMalloc(delta_part): %s", cudaGetErrorString(e)); break; }
         e = cudaMallocHost((void**)&c->h_st, sizeof(TessState) + 8 * sizeof(double));
         if (e != cudaSuccess) { r = tess_fail(TESS_ERR_NOMEM, "cudaMallocHost: %s", cudaGetErrorString(e)); break; }
     } while (0);
@@ -143,7 +146,7 @@ extern "C" int tess_ctx_destroy(tess_ctx* c) {
     cudaDeviceSynchronize();
     void* ptrs[] = {c->node, c->scale, c->inv_s2, c->st, c->cell_cnt, c->cell_start, c->block_sum, c->cell_of, c->cell_items,
                     c->cell_xy, c->cell_inv, c->ql.q_off, c->ql.q_cnt, c->ql.xy, c->ql.gid, c->ql.inv, c->tile_ring, c->lab[0], c->lab[1],
-                    c->mom, c->prev_count, c->scratch};
+                    c->mom, c->prev_count, c->scratch, c->delta_part};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (c->h_st) cudaFreeHost(c->h_st);
@@ -665,10 +668,10 @@ extern "C" int tess_lloyd_accumulate(tess_ctx* c, void* stream) {
         n = c->n_pts;
     }
     const int nb = (c->k + 255) / 256;
-    TESS_LAUNCH((k_count_prefilter), nb, 256, s, c->st, 1, c->mom, M, c->k, c->prev_count);
+    double* tail = c->mom + (long)c->k * M;
+    TESS_LAUNCH((k_count_prefilter), nb, 256, s, c->st, 1, c->mom, M, c->k, c->prev_count, tail);
     long want = (n + 256L * 8 - 1) / (256L * 8);
     int grid = (int)(want < 1 ? 1 : (want > c->sm_count * 8 ? c->sm_count * 8 : want));
-    double* tail = c->mom + (long)c->k * M;
     if (c->source == SRC_IMAGE && c->img_mode == 1)
         TESS_LAUNCH((k_compare_labels<1>), grid, 256, s, c->st, 1, c->lab[0], c->lab[1], n, c->dens, nullptr, nullptr, 0, tail);
     else if (c->source == SRC_IMAGE)
@@ -696,13 +699,15 @@ extern "C" int tess_lloyd_update(tess_ctx* c, void* stream) {
     cudaStream_t s = S(stream);
     const int M = n_moments(c);
     int nb = (c->k + 255) / 256;
-    if (nb > c->sm_count * 16) nb = c->sm_count * 16;
+    if (nb > c->sm_count * 8) nb = c->sm_count * 8;
     double* tail = c->mom + (long)c->k * M;
     if (M == 6)
         TESS_LAUNCH((k_update_nodes<6>), nb, 256, s, c->st, 1, c->mom, tail, c->k, c->node, c->has_scale ? c->scale : nullptr,
-                                            c->inv_s2, c->wvt_update);
+                                            c->inv_s2, c->wvt_update, c->delta_part);
     else
-        TESS_LAUNCH((k_update_nodes<4>), nb, 256, s, c->st, 1, c->mom, tail, c->k, c->node, nullptr, c->inv_s2, 0);
+        TESS_LAUNCH((k_update_nodes<4>), nb, 256, s, c->st, 1, c->mom, tail, c->k, c->node, nullptr, c->inv_s2, 0,
+                    c->delta_part);
+    TESS_LAUNCH((k_update_finish), 1, 256, s, c->st, tail, c->delta_part, nb, (M == 6 && c->wvt_update && c->has_scale) ? 1 : 0);
     CU_TRY(cudaGetLastError());
     return TESS_OK;
 }

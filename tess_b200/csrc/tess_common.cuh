@@ -74,8 +74,8 @@ struct TessState {
     int have_prev;                   // previous-iteration labels exist
     int n_brute;                     // tiles that fell back to the exhaustive scan (diagnostic)
     unsigned list_cursor;            // bump allocator of the candidate-list arena
-    unsigned ticket;                 // "last block done" counters of the fused tail kernels
-    unsigned ticket2;
+    unsigned spare_;
+    unsigned update_ran;             // k_update_nodes did work this iteration (read by k_update_finish)
     int last_parity;                 // label buffer (0/1) written by the most recent accumulate
     int pad_;
 };

@@ -23,7 +23,7 @@
 #define TESS_TAIL_SPARE 1
 
 __global__ void __launch_bounds__(256)
-k_count_prefilter(TessState* st, int honor, const double* mom, int M, int k, double* prev_count) {
+k_count_prefilter(TessState* st, int honor, const double* mom, int M, int k, double* prev_count, double* mom_tail) {
     if (TESS_STOPPED(st, honor)) return;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     bool diff = false;
@@ -32,54 +32,63 @@ k_count_prefilter(TessState* st, int honor, const double* mom, int M, int k, dou
         diff = (c != prev_count[j]);
         prev_count[j] = c;
     }
-    // one store per warp at most (every writer stores 1; a store per thread would serialise in L2)
-    if (__any_sync(TESS_FULL, diff) && (threadIdx.x & 31) == 0) st->count_changed = 1;
+    // one store per warp at most (every writer stores the same value; a store per thread would
+    // serialise in L2).  The tail slot was zeroed together with the moments.
+    if (__any_sync(TESS_FULL, diff) && (threadIdx.x & 31) == 0) {
+        st->count_changed = 1;
+        mom_tail[TESS_TAIL_CHANGED] = 1.0;
+    }
+    if (j == 0) {
+        st->last_parity = (int)(st->iters_done & 1);
+        if (!st->have_prev) mom_tail[TESS_TAIL_CHANGED] = 1.0;   // nothing to compare with yet
+    }
 }
 
 // Compares the two label buffers on the pixels/points that take part in the sums.
 // MASK_MODE 0: all; 1: finite density; 2: finite signal, noise and weight
+// No fences, no "last block" tail: the flag is an idempotent store, ordering comes from the
+// kernel boundaries (a device-wide fence in a streaming kernel drains the SM's memory pipeline
+// and costs far more than an extra launch).
 template <int MASK_MODE>
 __global__ void __launch_bounds__(256)
 k_compare_labels(TessState* st, int honor, int32_t* lab0, int32_t* lab1, long n, const double* dens,
                  const double* sig, const double* noise, int uniform_weight, double* mom_tail) {
     if (TESS_STOPPED(st, honor)) return;
-    __shared__ int s_last;
     const bool need = (!st->count_changed) && st->have_prev;
-    if (need) {
-        const int32_t* cur = (st->iters_done & 1) ? lab1 : lab0;
-        const int32_t* prev = (st->iters_done & 1) ? lab0 : lab1;
-        long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-        const long stride = (long)gridDim.x * blockDim.x;
-        unsigned long long diff = 0;
-        for (; i < n; i += stride) {
-            bool ok = true;
-            if (MASK_MODE == 1) ok = isfinite(dens[i]);
-            if (MASK_MODE == 2) {
-                const double S = sig[i], N = noise[i];
-                double wv = 1.0;
-                if (!uniform_weight) { const double q = __ddiv_rn(S, N); wv = __dmul_rn(q, q); }
-                ok = isfinite(S) && isfinite(N) && isfinite(wv);
-            }
-            if (ok && cur[i] != prev[i]) ++diff;
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->counted = need ? 1 : 0;
+    if (!need) return;
+    const int32_t* cur = (st->iters_done & 1) ? lab1 : lab0;
+    const int32_t* prev = (st->iters_done & 1) ? lab0 : lab1;
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long stride = (long)gridDim.x * blockDim.x;
+    unsigned long long diff = 0;
+    for (; i < n; i += stride) {
+        bool ok = true;
+        if (MASK_MODE == 1) ok = isfinite(dens[i]);
+        if (MASK_MODE == 2) {
+            const double S = sig[i], N = noise[i];
+            double wv = 1.0;
+            if (!uniform_weight) { const double q = __ddiv_rn(S, N); wv = __dmul_rn(q, q); }
+            ok = isfinite(S) && isfinite(N) && isfinite(wv);
         }
-        for (int m = 16; m >= 1; m >>= 1) diff += __shfl_xor_sync(TESS_FULL, diff, m);
-        if ((threadIdx.x & 31) == 0 && diff) atomicAdd(&st->n_changed, diff);
+        if (ok && cur[i] != prev[i]) ++diff;
     }
-    // last block done: publish the flag
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1) ? 1 : 0;
-    __syncthreads();
-    if (s_last && threadIdx.x == 0) {
-        __threadfence();
-        const unsigned long long nch = *((volatile unsigned long long*)&st->n_changed);
-        const bool changed = !need || nch != 0ull;
-        st->counted = need ? 1 : 0;
-        mom_tail[TESS_TAIL_CHANGED] = changed ? 1.0 : 0.0;
-        mom_tail[TESS_TAIL_SPARE] = 0.0;
-        st->last_parity = (int)(st->iters_done & 1);
-        st->ticket = 0u;
+    for (int m = 16; m >= 1; m >>= 1) diff += __shfl_xor_sync(TESS_FULL, diff, m);
+    if ((threadIdx.x & 31) == 0 && diff) {
+        atomicAdd(&st->n_changed, diff);
+        mom_tail[TESS_TAIL_CHANGED] = 1.0;
     }
+}
+
+// 128-bit global load the compiler may not split or sink below a dependent branch
+TESS_DEVFN double2 tess_ld2(const double* p) {
+#ifndef TESS_EMU
+    double2 v;
+    asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+#else
+    return *reinterpret_cast<const double2*>(p);
+#endif
 }
 
 // One thread per generator.  `mom` holds the (globally reduced) moments, `mom_tail` the summed
@@ -87,26 +96,26 @@ k_compare_labels(TessState* st, int honor, int32_t* lab0, int32_t* lab1, long n,
 template <int M>
 __global__ void __launch_bounds__(256)
 k_update_nodes(TessState* st, int honor, const double* mom, const double* mom_tail, int k, double* node,
-               double* scale, double* inv_s2, int wvt_update) {
+               double* scale, double* inv_s2, int wvt_update, double* delta_part) {
     if (TESS_STOPPED(st, honor)) return;
     __shared__ double s_red[8];
-    __shared__ int s_last;
     const bool changed = mom_tail[TESS_TAIL_CHANGED] != 0.0;
     if (changed) {
         double d = 0.0;
-        // grid-stride: a few hundred CTAs whatever k is, so the per-CTA atomics (delta, ticket) stay few
         for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < k; j += gridDim.x * blockDim.x) {
             const double* m = mom + (long)j * M;
             // the moment row as 128-bit loads (rows are 32 or 48 bytes, 16-byte aligned)
-            const double2 m01 = *reinterpret_cast<const double2*>(m), m23 = *reinterpret_cast<const double2*>(m + 2);
+            const double2 m01 = tess_ld2(m), m23 = tess_ld2(m + 2);
+            // the old node is loaded together with the moments: issued after the divide (one more
+            // dependent DRAM round trip, interleaved with the node stores) the kernel measured 5x slower
+            double2* np = reinterpret_cast<double2*>(node) + j;
+            const double2 old = tess_ld2(node + 2 * (long)j);
             double nx = 0.0, ny = 0.0;
             if (m01.x > 0.0) {   // population test, not weight (lloyd.pyx:68)
                 nx = __ddiv_rn(m23.x, m01.y);
                 ny = __ddiv_rn(m23.y, m01.y);
             }
             if (!(isfinite(nx) && isfinite(ny))) atomicOr(&st->flags, TESS_FLAG_NONFINITE);
-            double2* np = reinterpret_cast<double2*>(node) + j;
-            const double2 old = *np;
             const double dx = __dsub_rn(old.x, nx), dy = __dsub_rn(old.y, ny);
             d = __dadd_rn(d, __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
             *np = make_double2(nx, ny);
@@ -129,30 +138,45 @@ k_update_nodes(TessState* st, int honor, const double* mom, const double* mom_ta
         if (threadIdx.x < 32) {
             double v = (threadIdx.x < (blockDim.x >> 5)) ? s_red[threadIdx.x] : 0.0;
             v = tess_warp_sum(v);
-            if (threadIdx.x == 0) atomicAdd(&st->delta, v);
+            // one partial per CTA, summed by k_update_finish
+            if (threadIdx.x == 0) delta_part[blockIdx.x] = v;
         }
     }
-    // last-block-done: this CTA's reductions (delta by thread 0, min 1/scale^2 by every thread in WVT
-    // mode) must be performed before its ticket; the node stores need no fence (kernel boundary)
-    if (M == 6 && wvt_update && scale) __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        s_last = (atomicAdd(&st->ticket2, 1u) == gridDim.x - 1) ? 1 : 0;
+    // "this update ran" marker for k_update_finish (a flag raised in the loop above must not make
+    // the finish kernel skip the bookkeeping of this iteration)
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->update_ran = 1u;
+}
+
+// Single CTA, launched right after k_update_nodes: sums the per-CTA deltas and advances the
+// iteration state (latch lloyd.pyx:85-86).  A separate launch instead of a "last block done"
+// tail: the device-wide fences that pattern needs cost ~90 us per update at k = 1e6 on cold
+// lines, an extra launch costs ~2 us.
+__global__ void __launch_bounds__(256)
+k_update_finish(TessState* st, const double* mom_tail, const double* delta_part, int n_part, int wvt_scales) {
+    if (st->update_ran != 1u) return;   // k_update_nodes was a no-op (latch closed or error flag up)
+    __shared__ double s_red[8];
+    const bool changed = mom_tail[TESS_TAIL_CHANGED] != 0.0;
+    double tot = 0.0;
+    if (changed) {
+        for (int i = threadIdx.x; i < n_part; i += blockDim.x) tot += delta_part[i];
+        tot = tess_warp_sum(tot);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = tot;
     }
     __syncthreads();
-    if (s_last && threadIdx.x == 0) {
-        __threadfence();
+    if (threadIdx.x == 0) {
         if (!changed) {
             st->converged = 1;
             st->conv_iter = st->iters_done;
             st->delta = 0.0;
-        } else if (M == 6 && wvt_update && scale) {
-            st->min_inv_s2 = __longlong_as_double((long long)*((volatile unsigned long long*)&st->min_inv_next));
+        } else {
+            tot = 0.0;
+            for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += s_red[i];
+            st->delta = tot;
+            if (wvt_scales) st->min_inv_s2 = __longlong_as_double((long long)st->min_inv_next);
         }
         st->iters_done += 1;
         st->have_prev = 1;
-        st->ticket2 = 0u;
+        st->update_ran = 0u;
     }
 }
 
