@@ -90,6 +90,7 @@ class ClockSampler(object):
         self.p = None
         self.th = None
         self.stop_flag = False
+        self.active = False      # samples are kept only while the timed region runs
         self.sm, self.mx, self.reasons, self.power = [], [], set(), []
 
     def _nvml_loop(self):
@@ -102,6 +103,9 @@ class ClockSampler(object):
         get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
             getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
         while not self.stop_flag:
+            if not self.active:
+                time.sleep(0.0005)
+                continue
             try:
                 self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
                 r = int(get_reasons(h))
@@ -272,6 +276,8 @@ def main():
     ap.add_argument("--no-single", action="store_true", help="N>1: skip rank 0's one-GPU run of the same map")
     ap.add_argument("--no-balance", dest="balance", action="store_false",
                     help="N>1: equal-height row shards instead of cost-balanced ones")
+    ap.add_argument("--trace-steps", action="store_true",
+                    help="diagnostic: after the timed region, time a second run of --steps steps one by one (stderr)")
     ap.add_argument("--fake-shard", default=None, metavar="R/N",
                     help="profiling aid on ONE GPU: process only the rows of rank R of N (no collective)")
     args = ap.parse_args()
@@ -346,11 +352,21 @@ def main():
 
     setup(eng, r0, r1)
     launches0 = eng.api.launch_count()
+    if drv is not None:
+        # communicator set-up is not a step: let NCCL finish its lazy channel/buffer initialisation on
+        # the real message (the moment vector) before the W warm-up steps
+        mv0 = drv._moments()
+        for _ in range(10):
+            dist.all_reduce(mv0, op=dist.ReduceOp.SUM)
+        barrier()
     step(args.warmup)
-    barrier()
+    # NVML set-up (nvmlInit enumerates every GPU of the box: milliseconds) happens before the barrier,
+    # otherwise the other ranks' timed regions would include rank 0's set-up through the first all-reduce
     sampler = ClockSampler(local)
     if rank == 0 and not args.no_clocks:
         sampler.start()
+    barrier()
+    sampler.active = True
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = eng.api.launch_count()
     ev0.record()
@@ -371,6 +387,17 @@ def main():
     if fake is not None:
         value = (float(r1 - r0) * N) / (ms_step * 1e-3) / 1e9
     conv, _ = eng.status()
+
+    if args.trace_steps:
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+        barrier()
+        evs[0].record()
+        for i in range(args.steps):
+            step(1)
+            evs[i + 1].record()
+        barrier()
+        per = [round(evs[i].elapsed_time(evs[i + 1]), 3) for i in range(args.steps)]
+        sys.stderr.write("rank %d per-step ms: %s\n" % (rank, per))
 
     # ---- dominant kernel, timed live with CUDA events on its own stream (second pass)
     eng.set_option(_capi.OPT_KERNEL_TIMING, 1)
