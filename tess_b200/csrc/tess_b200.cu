@@ -347,8 +347,21 @@ static Geometry window_geometry(const tess_ctx* c, double x0, double y0, long H,
     q.T.tiles_x = (int)((W + TESS_TS - 1) / TESS_TS);
     q.T.tiles_y = (int)((H + TESS_TS - 1) / TESS_TS);
     q.T.n_tiles = q.T.tiles_x * q.T.tiles_y;
-    const double cs = (double)TESS_TS;
     double gx0 = x0, gy0 = y0, gx1 = x0 + (double)W, gy1 = y0 + (double)H;
+    // Cell size: one tile (64 px) unless the table is dense.  With more than ~80 generators per tile
+    // on average (bins below ~50 px) most tiles overflow the list builder and their pixels run the
+    // per-pixel ring search, which wants a few generators per cell: halve the cell until the mean
+    // occupancy is <= 4 (cells stay power-of-two fractions of a tile, so tiles remain unions of cells).
+    // Sparser tables keep the coarse grid: the list builder walks it faster (measured 13-24 % on the
+    // whole iteration at 60-100 px per bin).
+    double cs = (double)TESS_TS;
+    {
+        const double dw = c->has_domain ? fmax(c->dom[2], gx1) - fmin(c->dom[0], gx0) : (double)W;
+        const double dh = c->has_domain ? fmax(c->dom[3], gy1) - fmin(c->dom[1], gy0) : (double)H;
+        double occ = (double)c->k * cs * cs / fmax(dw * dh, 1.0);
+        if (occ > 80.0)
+            while (occ > 4.0 && cs > 2.0 && (dw / cs) * (dh / cs) < 1.6e7) { cs *= 0.5; occ *= 0.25; }
+    }
     if (c->has_domain) {
         // extend by whole cells so that tiles stay aligned with cells
         if (c->dom[0] < gx0) gx0 -= cs * ceil((gx0 - c->dom[0]) / cs);
@@ -529,6 +542,7 @@ static int run_image(tess_ctx* c, const Geometry& q, int mode, int honor, int32_
     a.labels_ext = labels_ext; a.lab0 = c->lab[0]; a.lab1 = c->lab[1];
     a.mom = c->mom; a.node = c->node; a.inv_s2 = c->inv_s2;
     a.L = c->ql;
+    a.g = q.g; a.cell_start = c->cell_start; a.cell_items = c->cell_items; a.cell_xy = c->cell_xy; a.cell_inv = c->cell_inv;
     a.st = c->st;
     a.H = q.T.H; a.W = q.T.W; a.x0 = q.T.x0; a.y0 = q.T.y0;
     a.k = c->k;

@@ -30,6 +30,7 @@
 #pragma once
 #include "tess_common.cuh"
 #include "tess_index.cuh"
+#include "tess_points.cuh"
 
 #define TESS_BCAP 64        // 16x16 block list capacity
 #define TESS_BLOCK_MIN 20   // quadrant lists longer than this get the intermediate 16x16 level
@@ -48,6 +49,11 @@ struct TessImgArgs {
     const double* node;    // [k][2]
     const double* inv_s2;  // [k] or null
     TessQLists L;          // per-quadrant candidate lists
+    TessGrid g;            // generator grid (ring-search fallback of overflowed tiles)
+    const int* cell_start;
+    const int* cell_items;
+    const double2* cell_xy;
+    const double* cell_inv;
     TessState* st;
     long H, W;
     double x0, y0;
@@ -237,6 +243,51 @@ TESS_NOINLINE void tess_quadrant_scan(const TessImgArgs& a, int32_t* labels, lon
                 }
                 if (ok) {
                     double* m = a.mom + (long)bi[j] * (NV + 1);
+                    tess_gmem_add(m, 1.0);
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) tess_gmem_add(m + 1 + i, val[i]);
+                }
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// Fallback of a quadrant whose tile overflowed the list builder (bins of a few pixels): every pixel
+// runs the exact ring search of the point-set path over the generator grid (tess_points.cuh), so the
+// cost follows the LOCAL generator density, not k.  Moments go straight to the global vector.
+template <int MODE, bool HAS_SCALE>
+TESS_NOINLINE void tess_quadrant_ring(const TessImgArgs& a, int32_t* labels, long qx0, long qy0) {
+    constexpr int NV = (MODE == 2) ? 5 : 3;
+    const int lane = threadIdx.x & 31;
+    const long c = qx0 + lane;
+    const double X = a.x0 + (double)c;
+    const double min_inv = HAS_SCALE ? a.st->min_inv_s2 : 1.0;
+    if (c < a.W) {
+        for (int j = 0; j < 32; ++j) {
+            const long r = qy0 + j;
+            if (r >= a.H) break;
+            const double Y = a.y0 + (double)r;
+            const int bi = tess_nearest_ring<HAS_SCALE>(a.g, a.cell_start, a.cell_items, a.cell_xy, a.cell_inv, min_inv, X, Y);
+            const long idx = r * a.W + c;
+            labels[idx] = bi;
+            if (MODE != 0) {
+                double val[NV];
+                bool ok;
+                if (MODE == 1) {
+                    const double w = a.dens[idx];
+                    ok = isfinite(w);
+                    val[0] = w; val[1] = __dmul_rn(w, X); val[2] = __dmul_rn(w, Y);
+                } else {
+                    const double S = a.sig[idx], N = a.noise[idx];
+                    double w = 1.0;
+                    if (!a.uniform_weight) { const double q = __ddiv_rn(S, N); w = __dmul_rn(q, q); }
+                    ok = isfinite(w) && isfinite(S) && isfinite(N);
+                    val[0] = w; val[1] = __dmul_rn(w, X); val[2] = __dmul_rn(w, Y);
+                    val[NV - 2] = S; val[NV - 1] = __dmul_rn(N, N);
+                }
+                if (ok) {
+                    double* m = a.mom + (long)bi * (NV + 1);
                     tess_gmem_add(m, 1.0);
 #pragma unroll
                     for (int i = 0; i < NV; ++i) tess_gmem_add(m + 1 + i, val[i]);
@@ -803,8 +854,7 @@ k_image_main(TessImgArgs a, int vec) {
                 tess_quadrant_scan<MODE, HAS_SCALE>(a, labels, qx0, qy0, a.L.xy + off_cur, a.L.gid + off_cur,
                                                     HAS_SCALE ? a.L.inv + off_cur : nullptr, cnt_cur);
             else
-                tess_quadrant_scan<MODE, HAS_SCALE>(a, labels, qx0, qy0, reinterpret_cast<const double2*>(a.node), nullptr,
-                                                    a.inv_s2, a.k);
+                tess_quadrant_ring<MODE, HAS_SCALE>(a, labels, qx0, qy0);
         } else {
         tess_quadrant_body<MODE, HAS_SCALE, !EDGE>(a, sm, buf, labels, src, cnt_cur, qx0, qy0, lane);
         }   // fast path

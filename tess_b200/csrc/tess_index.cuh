@@ -203,6 +203,28 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
         const int ci0 = tess_cell_coord(r.x0, g.ox, g.inv_cs, g.gw), ci1 = tess_cell_coord(r.x1, g.ox, g.inv_cs, g.gw);
         const int cj0 = tess_cell_coord(r.y0, g.oy, g.inv_cs, g.gh), cj1 = tess_cell_coord(r.y1, g.oy, g.inv_cs, g.gh);
 
+        // ---- 0. a tile that holds more generators than a list can (bins of a few pixels): every one
+        //      of them is a candidate, so the tile overflows whatever R is -- hand its quadrants to the
+        //      per-pixel ring search of the image kernel without walking any box
+        {
+            int tot0 = 0;
+            for (int j = cj0 + lane; j <= cj1; j += 32)
+                tot0 += cell_start[(long)j * g.gw + ci1 + 1] - cell_start[(long)j * g.gw + ci0];
+            tot0 = __reduce_add_sync(TESS_FULL, tot0);
+            if (tot0 > TESS_CAP) {
+                if (lane < 4) {
+                    const int q = lane;
+                    const long px0 = (long)tx * TESS_TS + 32 * (q & 1), py0 = (long)ty * TESS_TS + 32 * (q >> 1);
+                    const bool in = (px0 < T.W) && (py0 < T.H);
+                    const long qid = (long)(2 * ty + (q >> 1)) * L.nqx + (2 * tx + (q & 1));
+                    L.q_off[qid] = 0;
+                    L.q_cnt[qid] = in ? -1 : 0;
+                    if (in) atomicAdd(&st->n_brute, 1);
+                }
+                continue;
+            }
+        }
+
         // ---- 1. box search for R.  Box rows are walked 32 at a time, one row per lane; a chunk whose
         //      rows hold few generators is walked row-parallel (every lane its own row), a dense one
         //      row by row with all lanes.  The ring starts near the one that sufficed last time.

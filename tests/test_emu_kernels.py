@@ -198,3 +198,30 @@ def test_options_and_dense_fallbacks(eng):
     np.testing.assert_allclose(eng.moments()[:, :4], rm[:, :4], rtol=1e-12, atol=0)
     st = eng.list_stats()
     assert st["scan_all"] + st["scan_list"] > 0
+
+
+def test_every_pixel_its_own_generator_and_dense_scaled(eng):
+    """Bins of one pixel (the reference's default when no node_xy is given, voronoi.py:298-299) and a
+    dense scaled table: every tile overflows the list builder and runs the per-pixel ring search over
+    a refined generator grid."""
+    H, W = 70, 45
+    x, y = np.meshgrid(np.arange(W, dtype=float), np.arange(H, dtype=float))
+    xy = np.column_stack((x.ravel(), y.ravel()))
+    w = np.random.default_rng(0).uniform(0.5, 1.5, (H, W))
+    eng.set_image(density=w)
+    eng.set_generators(xy)
+    eng.accumulate()
+    assert np.array_equal(eng.labels().ravel(), np.arange(H * W, dtype=np.int32))
+    m = eng.moments()
+    np.testing.assert_allclose(m[:, 0], 1.0)
+    np.testing.assert_allclose(m[:, 1], w.ravel(), rtol=1e-15)
+    assert eng.list_stats()["scan_all"] > 0
+    eng.update()
+    np.testing.assert_allclose(eng.generators(), xy, rtol=0, atol=1e-12)
+    # dense + scaled metric
+    rng = np.random.default_rng(1)
+    node = rng.uniform(0, 45, (700, 2))
+    scale = rng.uniform(0.7, 1.6, 700)
+    eng.set_generators(node, scale=scale)
+    eng.accumulate()
+    assert np.array_equal(eng.labels(), O.c_assign_grid(H, W, node, scale=scale))

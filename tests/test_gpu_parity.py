@@ -400,3 +400,32 @@ def test_list_diagnostics_and_dense_fallbacks(eng):
                                rtol=1e-12, atol=0)
     st = eng.list_stats()
     assert st["scan_all"] + st["scan_list"] > 0 and st["arena_used"] <= st["arena_capacity"]
+
+
+@pytest.mark.parametrize("area", [40.0, 10.0, 2.0, 1.0])
+def test_small_bins_ring_fallback(eng, area):
+    """Bins of a few pixels: tiles overflow the list builder and run the per-pixel ring search over a
+    refined generator grid.  Labels bit-exact against the exhaustive GPU scan (itself checked against
+    the oracle on a corner), moments against NumPy sums of the same labels."""
+    rng = np.random.default_rng(int(area))
+    N = 256
+    k = int(N * N / area)
+    node = rng.uniform(-0.5, N - 0.5, (k, 2))
+    node[: k // 50] = np.round(node[: k // 50])           # some generators exactly on pixel centres
+    node[5] = node[4]                                     # an exact duplicate: lowest index wins
+    w = rng.uniform(0.5, 1.5, (N, N))
+    eng.set_image(density=w)
+    eng.set_generators(node)
+    eng.accumulate()
+    lab = h(eng.labels())
+    ref = h(eng.assign_grid(0.0, 0.0, N, N, exhaustive=True))
+    assert np.array_equal(lab, ref)
+    assert np.array_equal(ref[:24, :24], O.c_assign_grid(N, N, node)[:24, :24])
+    assert not np.any(lab == 5)
+    x, y = np.meshgrid(np.arange(N, dtype=float), np.arange(N, dtype=float))
+    rm = O.np_moments(np.column_stack((x.ravel(), y.ravel())), w.ravel(), ref.ravel(), k)
+    np.testing.assert_allclose(h(eng.moments())[:, :4], rm[:, :4], rtol=1e-12, atol=0)
+    st = eng.list_stats()
+    assert st["scan_all"] > 0
+    # the segmap query takes the same path
+    assert np.array_equal(h(eng.assign_grid(0.0, 0.0, N, N)), ref)
