@@ -88,6 +88,8 @@ struct tess_ctx {
     double* prev_count;
     double* scratch;   // 8 doubles (bounding-box reduction)
     double* delta_part; // per-CTA partial deltas of k_update_nodes
+    int cell_shift;     // image grids: cell = 64 px >> cell_shift; -1 = not decided for geo_key yet
+    double geo_key[4];  // window (x0, y0, H, W) the shift was decided for
     int timing;        // TESS_OPT_KERNEL_TIMING
 #ifndef TESS_EMU
     cudaEvent_t ev[2 * 512];
@@ -145,7 +147,7 @@ extern "C" int tess_ctx_destroy(tess_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     void* ptrs[] = {c->node, c->scale, c->inv_s2, c->st, c->cell_cnt, c->cell_start, c->block_sum, c->cell_of, c->cell_items,
-                    c->cell_xy, c->cell_inv, c->ql.q_off, c->ql.q_cnt, c->ql.xy, c->ql.gid, c->ql.inv, c->tile_ring, c->lab[0], c->lab[1],
+                    c->cell_xy, c->cell_inv, c->ql.q_off, c->ql.q_cnt, c->ql.ring_q, c->ql.xy, c->ql.gid, c->ql.inv, c->tile_ring, c->lab[0], c->lab[1],
                     c->mom, c->prev_count, c->scratch, c->delta_part};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -235,10 +237,11 @@ extern "C" int tess_set_image(tess_ctx* c, long H, long W, double x0, double y0,
 
 extern "C" int tess_set_domain(tess_ctx* c, double x0, double y0, double x1, double y1) {
     TRY(bind(c));
-    if (!(x1 >= x0) || !(y1 >= y0)) { c->has_domain = 0; return TESS_OK; }
+    if (!(x1 >= x0) || !(y1 >= y0)) { c->has_domain = 0; c->cell_shift = -1; return TESS_OK; }
     if (!isfinite(x0) || !isfinite(y0) || !isfinite(x1) || !isfinite(y1))
         return tess_fail(TESS_ERR_ARG, "tess_set_domain: non-finite rectangle");
     c->has_domain = 1;
+    c->cell_shift = -1;
     c->dom[0] = x0; c->dom[1] = y0; c->dom[2] = x1; c->dom[3] = y1;
     return TESS_OK;
 }
@@ -315,6 +318,7 @@ extern "C" int tess_set_generators(tess_ctx* c, long k, const double* node_xy, c
         c->k_cap = (int)k;
     }
     c->k = (int)k;
+    c->cell_shift = -1;
     // WVT scale updates need a scale table: start from unit scales when none is given
     c->has_scale = (scale || c->wvt_update) ? 1 : 0;
     const int nb = (int)((k + 255) / 256);
@@ -339,29 +343,16 @@ struct Geometry {
     int n_cells;
 };
 
-// Grid for an H x W pixel window at (x0, y0): 64-px cells over the window (united with the generator
-// domain if one was given); generators outside are clamped into the border cells.
-static Geometry window_geometry(const tess_ctx* c, double x0, double y0, long H, long W) {
+// Grid for an H x W pixel window at (x0, y0): cells of 64 >> shift px over the window (united with
+// the generator domain if one was given); generators outside are clamped into the border cells.
+static Geometry window_geometry(const tess_ctx* c, double x0, double y0, long H, long W, int shift) {
     Geometry q;
     q.T.x0 = x0; q.T.y0 = y0; q.T.W = W; q.T.H = H;
     q.T.tiles_x = (int)((W + TESS_TS - 1) / TESS_TS);
     q.T.tiles_y = (int)((H + TESS_TS - 1) / TESS_TS);
     q.T.n_tiles = q.T.tiles_x * q.T.tiles_y;
     double gx0 = x0, gy0 = y0, gx1 = x0 + (double)W, gy1 = y0 + (double)H;
-    // Cell size: one tile (64 px) unless the table is dense.  With more than ~80 generators per tile
-    // on average (bins below ~50 px) most tiles overflow the list builder and their pixels run the
-    // per-pixel ring search, which wants a few generators per cell: halve the cell until the mean
-    // occupancy is <= 4 (cells stay power-of-two fractions of a tile, so tiles remain unions of cells).
-    // Sparser tables keep the coarse grid: the list builder walks it faster (measured 13-24 % on the
-    // whole iteration at 60-100 px per bin).
-    double cs = (double)TESS_TS;
-    {
-        const double dw = c->has_domain ? fmax(c->dom[2], gx1) - fmin(c->dom[0], gx0) : (double)W;
-        const double dh = c->has_domain ? fmax(c->dom[3], gy1) - fmin(c->dom[1], gy0) : (double)H;
-        double occ = (double)c->k * cs * cs / fmax(dw * dh, 1.0);
-        if (occ > 80.0)
-            while (occ > 4.0 && cs > 2.0 && (dw / cs) * (dh / cs) < 1.6e7) { cs *= 0.5; occ *= 0.25; }
-    }
+    const double cs = (double)TESS_TS / (double)(1 << shift);
     if (c->has_domain) {
         // extend by whole cells so that tiles stay aligned with cells
         if (c->dom[0] < gx0) gx0 -= cs * ceil((gx0 - c->dom[0]) / cs);
@@ -414,20 +405,59 @@ static int ensure_cells(tess_ctx* c, int n_cells) {
     return TESS_OK;
 }
 
+// Geometry of an image query, with the cell size decided once per (generator table, window):
+// one tile (64 px) per cell unless some tile holds more than ~110 generators (bins below ~40 px).
+// Such tiles overflow the list builder and their pixels run the per-pixel ring search, which wants a
+// few generators per cell: the cell is halved until the fullest one holds <= 16 and -- for tables
+// that are dense everywhere -- the mean occupancy is <= 4.  Cells stay power-of-two fractions of a
+// tile, so tiles remain unions of cells.  Sparser tables keep the coarse grid: the list builder walks
+// it faster (13-24 % of the whole iteration at 60-100 px per bin).  Costs one small kernel and one
+// host read-back after tess_set_generators / tess_set_image / tess_set_domain, never per iteration.
+static int image_geometry(tess_ctx* c, double x0, double y0, long H, long W, cudaStream_t s, Geometry* out) {
+    const double key[4] = {x0, y0, (double)H, (double)W};
+    if (c->cell_shift < 0 || memcmp(key, c->geo_key, sizeof(key)) != 0) {
+        int shift = 0;
+        if (c->k > 80) {
+            const Geometry q0 = window_geometry(c, x0, y0, H, W, 0);
+            TRY(ensure_cells(c, q0.n_cells));
+            CU_TRY(cudaMemsetAsync(&c->st->tile_counter, 0, sizeof(int), s));
+            int nb = (c->k + 255) / 256;
+            if (nb > c->sm_count * 16) nb = c->sm_count * 16;
+            TESS_LAUNCH((k_cell_occupancy_max), nb, 256, s, c->st, q0.g, c->node, c->k, c->cell_cnt);
+            CU_TRY(cudaMemsetAsync(c->cell_cnt, 0, sizeof(int) * (size_t)(q0.n_cells + 1), s));
+            CU_TRY(cudaMemcpyAsync(c->h_st, c->st, sizeof(TessState), cudaMemcpyDeviceToHost, s));
+            CU_TRY(cudaStreamSynchronize(s));
+            double occ_max = (double)c->h_st->tile_counter;
+            double occ_mean = (double)c->k / fmax((double)q0.n_cells, 1.0);
+            double cells = (double)q0.n_cells;
+            if (occ_max > 110.0)
+                while ((occ_max > 16.0 || occ_mean > 4.0) && shift < 5 && cells * 4.0 <= 3.2e7) {
+                    ++shift; occ_max *= 0.25; occ_mean *= 0.25; cells *= 4.0;
+                }
+        }
+        c->cell_shift = shift;
+        memcpy(c->geo_key, key, sizeof(key));
+    }
+    *out = window_geometry(c, x0, y0, H, W, c->cell_shift);
+    return TESS_OK;
+}
+
 static int ensure_lists(tess_ctx* c, const TessTiles& T) {
     const int nqx = 2 * T.tiles_x, nqy = 2 * T.tiles_y;
     const long nq = (long)nqx * nqy;
     if (nq > c->quads_cap) {
         if (c->ql.q_off) cudaFree(c->ql.q_off);
         if (c->ql.q_cnt) cudaFree(c->ql.q_cnt);
+        if (c->ql.ring_q) cudaFree(c->ql.ring_q);
         if (c->tile_ring) cudaFree(c->tile_ring);
-        c->ql.q_off = c->ql.q_cnt = nullptr;
+        c->ql.q_off = c->ql.q_cnt = c->ql.ring_q = nullptr;
         c->tile_ring = nullptr;
         c->quads_cap = 0;
         CU_TRY(cudaMalloc((void**)&c->tile_ring, sizeof(int) * (size_t)nq));      // >= n_tiles
         CU_TRY(cudaMemset(c->tile_ring, 0, sizeof(int) * (size_t)nq));
         CU_TRY(cudaMalloc((void**)&c->ql.q_off, sizeof(int) * (size_t)nq));
         CU_TRY(cudaMalloc((void**)&c->ql.q_cnt, sizeof(int) * (size_t)nq));
+        CU_TRY(cudaMalloc((void**)&c->ql.ring_q, sizeof(int) * (size_t)nq));
         c->quads_cap = nq;
     }
     // arena: a generator is listed by every quadrant it can win in -- its own bin plus a margin
@@ -666,7 +696,8 @@ extern "C" int tess_lloyd_accumulate(tess_ctx* c, void* stream) {
     const long n_mom = (long)c->k * M + TESS_TAIL;
     long n;
     if (c->source == SRC_IMAGE) {
-        Geometry q = window_geometry(c, c->x0, c->y0, c->H, c->W);
+        Geometry q;
+        TRY(image_geometry(c, c->x0, c->y0, c->H, c->W, s, &q));
         TRY(build_index(c, q, 1, c->mom, n_mom, s));
         TRY(build_lists(c, q, 1, s));
         timing_mark(c, s, 0);
@@ -838,7 +869,8 @@ extern "C" int tess_assign_grid(tess_ctx* c, double x0, double y0, long H, long 
     if (c->k <= 0) return tess_fail(TESS_ERR_STATE, "tess_assign_grid: call tess_set_generators first");
     if (H <= 0 || W <= 0 || !labels_out) return tess_fail(TESS_ERR_ARG, "tess_assign_grid: bad arguments");
     cudaStream_t s = S(stream);
-    Geometry q = window_geometry(c, x0, y0, H, W);
+    Geometry q;
+    TRY(image_geometry(c, x0, y0, H, W, s, &q));
     TRY(build_index(c, q, 0, nullptr, 0, s));
     TRY(build_lists(c, q, 0, s));
     TRY(run_image(c, q, 0, 0, labels_out, s));

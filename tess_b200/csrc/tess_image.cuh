@@ -253,47 +253,51 @@ TESS_NOINLINE void tess_quadrant_scan(const TessImgArgs& a, int32_t* labels, lon
     __syncwarp();
 }
 
-// Fallback of a quadrant whose tile overflowed the list builder (bins of a few pixels): every pixel
-// runs the exact ring search of the point-set path over the generator grid (tess_points.cuh), so the
-// cost follows the LOCAL generator density, not k.  Moments go straight to the global vector.
+// Fallback for the quadrants whose tile overflowed the list builder (bins of a few pixels): every
+// pixel runs the exact ring search of the point-set path over the generator grid (tess_points.cuh),
+// so the cost follows the LOCAL generator density, not k.  The builder collects those quadrants in
+// L.ring_q; after its own quadrants every warp of the grid takes strips of them (TESS_RING_ROWS rows of
+// 32 pixels per warp and turn, one column per lane: walking down a column keeps the cells in L1), so
+// that a few slow quadrants do not become the kernel's tail.
+// Moments go straight to the global vector.
+#ifndef TESS_RING_ROWS
+#define TESS_RING_ROWS 2
+#endif
 template <int MODE, bool HAS_SCALE>
-TESS_NOINLINE void tess_quadrant_ring(const TessImgArgs& a, int32_t* labels, long qx0, long qy0) {
+TESS_NOINLINE void tess_rows_ring(const TessImgArgs& a, int32_t* labels, long qx0, long r0) {
     constexpr int NV = (MODE == 2) ? 5 : 3;
     const int lane = threadIdx.x & 31;
     const long c = qx0 + lane;
-    const double X = a.x0 + (double)c;
     const double min_inv = HAS_SCALE ? a.st->min_inv_s2 : 1.0;
-    if (c < a.W) {
-        for (int j = 0; j < 32; ++j) {
-            const long r = qy0 + j;
-            if (r >= a.H) break;
-            const double Y = a.y0 + (double)r;
-            const int bi = tess_nearest_ring<HAS_SCALE>(a.g, a.cell_start, a.cell_items, a.cell_xy, a.cell_inv, min_inv, X, Y);
-            const long idx = r * a.W + c;
-            labels[idx] = bi;
-            if (MODE != 0) {
-                double val[NV];
-                bool ok;
-                if (MODE == 1) {
-                    const double w = a.dens[idx];
-                    ok = isfinite(w);
-                    val[0] = w; val[1] = __dmul_rn(w, X); val[2] = __dmul_rn(w, Y);
-                } else {
-                    const double S = a.sig[idx], N = a.noise[idx];
-                    double w = 1.0;
-                    if (!a.uniform_weight) { const double q = __ddiv_rn(S, N); w = __dmul_rn(q, q); }
-                    ok = isfinite(w) && isfinite(S) && isfinite(N);
-                    val[0] = w; val[1] = __dmul_rn(w, X); val[2] = __dmul_rn(w, Y);
-                    val[NV - 2] = S; val[NV - 1] = __dmul_rn(N, N);
-                }
-                if (ok) {
-                    double* m = a.mom + (long)bi * (NV + 1);
-                    tess_gmem_add(m, 1.0);
+    for (long r = r0; r < r0 + TESS_RING_ROWS; ++r) {
+    if (c < a.W && r < a.H) {
+        const double X = a.x0 + (double)c, Y = a.y0 + (double)r;
+        const int bi = tess_nearest_ring<HAS_SCALE>(a.g, a.cell_start, a.cell_items, a.cell_xy, a.cell_inv, min_inv, X, Y);
+        const long idx = r * a.W + c;
+        labels[idx] = bi;
+        if (MODE != 0) {
+            double val[NV];
+            bool ok;
+            if (MODE == 1) {
+                const double w = a.dens[idx];
+                ok = isfinite(w);
+                val[0] = w; val[1] = __dmul_rn(w, X); val[2] = __dmul_rn(w, Y);
+            } else {
+                const double S = a.sig[idx], N = a.noise[idx];
+                double w = 1.0;
+                if (!a.uniform_weight) { const double q = __ddiv_rn(S, N); w = __dmul_rn(q, q); }
+                ok = isfinite(w) && isfinite(S) && isfinite(N);
+                val[0] = w; val[1] = __dmul_rn(w, X); val[2] = __dmul_rn(w, Y);
+                val[NV - 2] = S; val[NV - 1] = __dmul_rn(N, N);
+            }
+            if (ok) {
+                double* m = a.mom + (long)bi * (NV + 1);
+                tess_gmem_add(m, 1.0);
 #pragma unroll
-                    for (int i = 0; i < NV; ++i) tess_gmem_add(m + 1 + i, val[i]);
-                }
+                for (int i = 0; i < NV; ++i) tess_gmem_add(m + 1 + i, val[i]);
             }
         }
+    }
     }
     __syncwarp();
 }
@@ -846,23 +850,30 @@ k_image_main(TessImgArgs a, int vec) {
         const int qx0 = 32 * qx, qy0 = 32 * qy;            // pixel coordinates fit 32 bits (host-checked)
         const bool interior = vec && (qx0 + 32 <= a.W) && (qy0 + 32 <= a.H);
         const int cnt_cur = (interior != EDGE) ? cnt : 0, off_cur = off;   // the other kernel's quadrants are skipped
-        if (cnt_cur != 0) {
-        if (cnt_cur < 0 || cnt_cur > QC) {
-            // slow path: list too long for the fast path (scan it from global memory) or overflow of
-            // the builder (scan the complete generator table)
-            if (cnt_cur > 0)
-                tess_quadrant_scan<MODE, HAS_SCALE>(a, labels, qx0, qy0, a.L.xy + off_cur, a.L.gid + off_cur,
-                                                    HAS_SCALE ? a.L.inv + off_cur : nullptr, cnt_cur);
-            else
-                tess_quadrant_ring<MODE, HAS_SCALE>(a, labels, qx0, qy0);
+        if (cnt_cur > 0) {                                 // < 0: builder overflow, done in the tail below
+        if (cnt_cur > QC) {
+            // slow path: list too long for the fast path (scan it from global memory)
+            tess_quadrant_scan<MODE, HAS_SCALE>(a, labels, qx0, qy0, a.L.xy + off_cur, a.L.gid + off_cur,
+                                                HAS_SCALE ? a.L.inv + off_cur : nullptr, cnt_cur);
         } else {
         tess_quadrant_body<MODE, HAS_SCALE, !EDGE>(a, sm, buf, labels, src, cnt_cur, qx0, qy0, lane);
         }   // fast path
-        }   // cnt != 0
+        }   // cnt > 0
         // ---- rotate the pipeline
         q = q1; cnt = cnt1; off = off1;
         q1 = q2; cnt1 = cnt2; off1 = off2;
         buf ^= 1;
+    }
+    // ---- tail: rows of the overflowed quadrants, spread over all warps of the grid (only in the
+    //      instantiation that is always launched: the interior one for vector-friendly images)
+    if (EDGE != (vec != 0)) {
+        constexpr int PER_Q = 32 / TESS_RING_ROWS;
+        const int n_items = a.st->n_brute * PER_Q;
+        for (int item = (int)blockIdx.x * NW + wib; item < n_items; item += stride) {
+            const int qq = a.L.ring_q[item / PER_Q];
+            const int qy = qq / a.L.nqx, qx = qq - qy * a.L.nqx;
+            tess_rows_ring<MODE, HAS_SCALE>(a, labels, 32L * qx, 32L * qy + TESS_RING_ROWS * (item % PER_Q));
+        }
     }
 }
 

@@ -30,6 +30,20 @@ k_cell_count(const TessState* st, int honor, TessGrid g, const double* node, int
     }
 }
 
+// Largest number of generators in one cell of grid g (set-up only: decides how far the grid is
+// refined, tess_b200.cu::image_geometry).  cell_cnt is all-zero on entry; the caller clears it again.
+__global__ void __launch_bounds__(256)
+k_cell_occupancy_max(TessState* st, TessGrid g, const double* node, int k, int* cell_cnt) {
+    int m = 0;
+    for (long j = (long)blockIdx.x * blockDim.x + threadIdx.x; j < k; j += (long)gridDim.x * blockDim.x) {
+        const int ci = tess_cell_coord(node[2 * j], g.ox, g.inv_cs, g.gw);
+        const int cj = tess_cell_coord(node[2 * j + 1], g.oy, g.inv_cs, g.gh);
+        m = max(m, atomicAdd(&cell_cnt[cj * g.gw + ci], 1) + 1);
+    }
+    m = __reduce_max_sync(TESS_FULL, m);
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(&st->tile_counter, m);
+}
+
 // Exclusive scan of cell_cnt[0..n_cells) -> cell_start[0..n_cells], reduce-then-scan over blocks of
 // TESS_SCAN_BLOCK cells: k_cell_blocksum writes one total per block, k_cell_scan adds the totals of
 // the preceding blocks to a register/shuffle scan of its own block (16 consecutive cells per thread).
@@ -164,6 +178,7 @@ struct TessQLists {
     double2* xy;       // arena
     int* gid;
     double* inv;       // arena (scaled metric only)
+    int* ring_q;       // [nqx*nqy] the overflowed quadrants (st->n_brute of them), any order
     unsigned capacity; // arena records
     int nqx, nqy;      // quadrant grid (2 tiles_x, 2 tiles_y)
 };
@@ -219,7 +234,7 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
                     const long qid = (long)(2 * ty + (q >> 1)) * L.nqx + (2 * tx + (q & 1));
                     L.q_off[qid] = 0;
                     L.q_cnt[qid] = in ? -1 : 0;
-                    if (in) atomicAdd(&st->n_brute, 1);
+                    if (in) L.ring_q[atomicAdd(&st->n_brute, 1)] = (int)qid;
                 }
                 continue;
             }
@@ -445,7 +460,7 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
             if (lane == 0) {
                 L.q_off[qid] = ok ? (int)off : 0;
                 L.q_cnt[qid] = !qin[q] ? 0 : (ok ? nq_[q] : -1);
-                if (!ok && qin[q]) atomicAdd(&st->n_brute, 1);
+                if (!ok && qin[q]) L.ring_q[atomicAdd(&st->n_brute, 1)] = (int)qid;
             }
             if (ok && qin[q]) {
                 int wpos = 0;

@@ -19,32 +19,64 @@ TESS_DEVFN int tess_nearest_ring(const TessGrid& g, const int* cell_start, const
     const int cj = tess_cell_coord(py, g.oy, g.inv_cs, g.gh);
     double bd = INFINITY;
     int bi = 0x7fffffff;
-    // generators of the cells i0..i1 of grid row j: one contiguous slot range (two index loads)
-    auto scan = [&](int i0, int i1, int j) {
-        const long row = (long)j * g.gw;
-        const int s = cell_start[row + i0], e = cell_start[row + i1 + 1];
-        for (int q = s; q < e; ++q) {
-            const double2 p = cell_xy[q];
-            double d = tess_d2_pinned(px, py, p.x, p.y);
-            if (HAS_SCALE) d = __dmul_rn(d, cell_inv[q]);
-            if (d <= bd) {
-                const int gid = cell_items[q];
-                if ((d < bd) | (gid < bi)) { bd = d; bi = gid; }
+    // records [s, e) of the cell-ordered table; four per trip: the loads are independent, only the
+    // compares are serial
+    auto scan = [&](int s, int e) {
+        for (int q = s; q < e; q += 4) {
+            double d[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int qq = min(q + u, e - 1);
+                const double2 p = cell_xy[qq];
+                d[u] = tess_d2_pinned(px, py, p.x, p.y);
+                if (HAS_SCALE) d[u] = __dmul_rn(d[u], cell_inv[qq]);
+                if (q + u >= e) d[u] = INFINITY;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (d[u] <= bd && q + u < e) {
+                    const int gid = cell_items[q + u];
+                    if ((d[u] < bd) | (gid < bi)) { bd = d[u]; bi = gid; }
+                }
             }
         }
     };
-    for (int ring = 0;; ++ring) {
+    // The cells i0..i1 of one grid row are one contiguous record range (two index loads).
+    // Rings 0 and 1 together (three row ranges, their index loads issued up front): in a grid with a
+    // few generators per cell most queries end here, and the loads of a ring no longer wait for the
+    // scan of the previous one.
+    {
+        const int xi0 = max(ci - 1, 0), xi1 = min(ci + 1, g.gw - 1);
+        int rs[3], re[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int j = cj - 1 + r;
+            const bool in = (j >= 0) && (j < g.gh);
+            const long row = (long)(in ? j : cj) * g.gw;
+            rs[r] = cell_start[row + xi0];
+            re[r] = in ? cell_start[row + xi1 + 1] : rs[r];
+        }
+        scan(rs[1], re[1]);
+        scan(rs[0], re[0]);
+        scan(rs[2], re[2]);
+    }
+    for (int ring = 1;; ++ring) {
         const int bi0 = ci - ring, bi1 = ci + ring, bj0 = cj - ring, bj1 = cj + ring;
-        const int xi0 = max(bi0, 0), xi1 = min(bi1, g.gw - 1);
-        if (ring == 0) {
-            scan(ci, ci, cj);
-        } else {
-            if (bj0 >= 0) scan(xi0, xi1, bj0);
-            if (bj1 < g.gh) scan(xi0, xi1, bj1);
+        if (ring > 1) {
+            const int xi0 = max(bi0, 0), xi1 = min(bi1, g.gw - 1);
+            int s0 = 0, e0 = 0, s1 = 0, e1 = 0;
+            if (bj0 >= 0) { s0 = cell_start[(long)bj0 * g.gw + xi0]; e0 = cell_start[(long)bj0 * g.gw + xi1 + 1]; }
+            if (bj1 < g.gh) { s1 = cell_start[(long)bj1 * g.gw + xi0]; e1 = cell_start[(long)bj1 * g.gw + xi1 + 1]; }
+            scan(s0, e0);
+            scan(s1, e1);
             const int yj0 = max(bj0 + 1, 0), yj1 = min(bj1 - 1, g.gh - 1);
             for (int j = yj0; j <= yj1; ++j) {
-                if (bi0 >= 0) scan(bi0, bi0, j);
-                if (bi1 < g.gw) scan(bi1, bi1, j);
+                const long row = (long)j * g.gw;
+                int sl = 0, el = 0, sr = 0, er = 0;
+                if (bi0 >= 0) { sl = cell_start[row + bi0]; el = cell_start[row + bi0 + 1]; }
+                if (bi1 < g.gw) { sr = cell_start[row + bi1]; er = cell_start[row + bi1 + 1]; }
+                scan(sl, el);
+                scan(sr, er);
             }
         }
         if (bi0 <= 0 && bj0 <= 0 && bi1 >= g.gw - 1 && bj1 >= g.gh - 1) break;

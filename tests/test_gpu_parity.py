@@ -429,3 +429,27 @@ def test_small_bins_ring_fallback(eng, area):
     assert st["scan_all"] > 0
     # the segmap query takes the same path
     assert np.array_equal(h(eng.assign_grid(0.0, 0.0, N, N)), ref)
+
+
+def test_dense_centre_sparse_outskirts(eng):
+    """Unbinned pixels in the centre (one generator per pixel), large bins outside: the grid is refined
+    from the fullest tile, not the mean occupancy; labels stay bit-exact everywhere."""
+    rng = np.random.default_rng(11)
+    N = 512
+    c0, c1 = 200, 312
+    yy, xx = np.mgrid[c0:c1, c0:c1]
+    centre = np.column_stack((xx.ravel(), yy.ravel())).astype(np.float64)
+    outer = rng.uniform(-0.5, N - 0.5, (300, 2))
+    outer = outer[(np.abs(outer - 255.5) > 70).any(axis=1)]
+    node = np.vstack((outer, centre))
+    w = rng.uniform(0.5, 1.5, (N, N))
+    eng.set_image(density=w)
+    eng.set_generators(node)
+    eng.accumulate()
+    lab = h(eng.labels())
+    ref = h(eng.assign_grid(0.0, 0.0, N, N, exhaustive=True))
+    assert np.array_equal(lab, ref)
+    assert np.array_equal(lab[c0:c1, c0:c1].ravel(), outer.shape[0] + np.arange(centre.shape[0]))
+    x, y = np.meshgrid(np.arange(N, dtype=float), np.arange(N, dtype=float))
+    rm = O.np_moments(np.column_stack((x.ravel(), y.ravel())), w.ravel(), ref.ravel(), node.shape[0])
+    np.testing.assert_allclose(h(eng.moments())[:, :4], rm[:, :4], rtol=1e-12, atol=0)
