@@ -5,6 +5,9 @@ jonathansick/tess behind tess's own Python API:
     tess_b200.lloyd.lloyd                 <->  tess.lloyd.lloyd              (tess/lloyd.pyx:10-90)
     tess_b200.voronoi.VoronoiTessellation <->  tess.voronoi.VoronoiTessellation (tess/voronoi.py:31-223)
     tess_b200.voronoi.CVTessellation      <->  tess.voronoi.CVTessellation      (tess/voronoi.py:226-321)
+    tess_b200.accretion                   <->  accretor centroids / bin_sn / cleanup (tess/pixel_accretion.py:212-240,485-517)
+    tess_b200.wvt.wvt_binning                  Lloyd/WVT to a target S/N on the device
+    tess_b200.fitsio                           single-HDU FITS maps in / segmaps out (astropy is absent)
 
 Everything numeric runs in hand-written CUDA kernels inside libtess_b200.so (built by
 `python -m tess_b200.build`, C ABI in include/tess_b200.h); Python is a thin ctypes host layer.
@@ -18,7 +21,7 @@ from ._capi import TessError, TessNonFinite  # noqa: F401
 
 def __getattr__(name):
     # lazy: importing the package must work on a GPU-less box (build checks, CPU tests)
-    if name in ("lloyd", "voronoi", "engine", "sharded"):
+    if name in ("lloyd", "voronoi", "engine", "sharded", "accretion", "wvt", "fitsio"):
         import importlib
         return importlib.import_module("." + name, __name__)
     if name in ("VoronoiTessellation", "CVTessellation"):

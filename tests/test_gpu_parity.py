@@ -5,9 +5,13 @@ Parity of the CUDA path (through the C ABI, via tess_b200.engine / lloyd / voron
  (iii) size-independent properties at BASELINE.json's full sizes.
 Bars: labels bit-exact; per-bin moments <= 1e-12 relative; converged nodes <= 1e-6 px.
 """
+import os
+import sys
+
 import numpy as np
 import pytest
 
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from conftest import golden, gaussian_image, sampled_seeds
 from oracle import oracle as O
 
@@ -453,3 +457,15 @@ def test_dense_centre_sparse_outskirts(eng):
     x, y = np.meshgrid(np.arange(N, dtype=float), np.arange(N, dtype=float))
     rm = O.np_moments(np.column_stack((x.ravel(), y.ravel())), w.ravel(), ref.ravel(), node.shape[0])
     np.testing.assert_allclose(h(eng.moments())[:, :4], rm[:, :4], rtol=1e-12, atol=0)
+
+
+# ---------------------------------------------------------------- SURVEY.md section 8f rows
+def test_accretion_helpers_gpu(engine_cls):
+    import frow_checks
+    frow_checks.check_accretion_helpers(lambda: engine_cls(0))
+
+
+def test_wvt_binning_to_target_sn_gpu(engine_cls):
+    import frow_checks
+    r = frow_checks.check_wvt_binning(lambda: engine_cls(0), N=256, k=120)
+    assert r["labels"].shape == (256, 256)
