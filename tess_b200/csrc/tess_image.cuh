@@ -634,6 +634,7 @@ TESS_DEVFN void tess_quadrant_body(const TessImgArgs& a, TessWarpSmem<MODE, HAS_
                     double d0 = __dadd_rn(dxx0, dyy), d1 = __dadd_rn(dxx1, dyy);
                     if (HAS_SCALE) { d0 = __dmul_rn(d0, inv); d1 = __dmul_rn(d1, inv); }
                     tied = tied || (d0 == bd[r][0]) || (d1 == bd[r][1]);
+                    // (select pairs, not fmin: DMNMX measured 9 % slower on the whole kernel)
                     if (d0 < bd[r][0]) { bd[r][0] = d0; bs[r][0] = e; }
                     if (d1 < bd[r][1]) { bd[r][1] = d1; bs[r][1] = e; }
                 }
@@ -758,24 +759,32 @@ TESS_DEVFN void tess_quadrant_body(const TessImgArgs& a, TessWarpSmem<MODE, HAS_
 #pragma unroll
                     for (int i = 0; i < NV; ++i) cur.v[i] = sw ? 0.0 : cur.v[i];
                 }
+                // the lane's pixels of this bin, summed in patch-local coordinates (column offset
+                // 0/1, row offset 0..3) and shifted once: sum w x = X0 sum w + sum_{col 1} w,
+                // sum w y = Y0 sum w + sum_r r (w_r0 + w_r1)
+                double t[4], c1 = 0.0;
+                int nh = 0;
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const bool hit = (bs[r][c] == cur.key);
-                        const double w = hit ? wv[r][c] : 0.0;
-                        cur.n += hit ? 1 : 0;
-                        cur.v[0] = __dadd_rn(cur.v[0], w);
-                        cur.v[1] = __dadd_rn(cur.v[1], __dmul_rn(w, c ? X1 : X0));
-                        cur.v[2] = __dadd_rn(cur.v[2], __dmul_rn(w, Y[r]));
-                        if (MODE == 2) {
-                            cur.v[NV - 2] = __dadd_rn(cur.v[NV - 2], hit ? w_[r][c] : 0.0);
-                            const double nz = hit ? n_[r][c] : 0.0;
-                            cur.v[NV - 1] = __dadd_rn(cur.v[NV - 1], __dmul_rn(nz, nz));
-                        }
-                        bs[r][c] = hit ? -2 : bs[r][c];
+                    const bool h0 = (bs[r][0] == cur.key), h1 = (bs[r][1] == cur.key);
+                    const double w0 = h0 ? wv[r][0] : 0.0, w1 = h1 ? wv[r][1] : 0.0;
+                    nh += (h0 ? 1 : 0) + (h1 ? 1 : 0);
+                    t[r] = __dadd_rn(w0, w1);
+                    c1 = __dadd_rn(c1, w1);
+                    if (MODE == 2) {
+                        cur.v[NV - 2] = __dadd_rn(cur.v[NV - 2], __dadd_rn(h0 ? w_[r][0] : 0.0, h1 ? w_[r][1] : 0.0));
+                        const double z0 = h0 ? n_[r][0] : 0.0, z1 = h1 ? n_[r][1] : 0.0;
+                        cur.v[NV - 1] = __dadd_rn(cur.v[NV - 1], __dadd_rn(__dmul_rn(z0, z0), __dmul_rn(z1, z1)));
                     }
+                    bs[r][0] = h0 ? -2 : bs[r][0];
+                    bs[r][1] = h1 ? -2 : bs[r][1];
                 }
+                const double wsum = __dadd_rn(__dadd_rn(t[0], t[1]), __dadd_rn(t[2], t[3]));
+                const double sy = __fma_rn(3.0, t[3], __fma_rn(2.0, t[2], t[1]));
+                cur.n += nh;
+                cur.v[0] = __dadd_rn(cur.v[0], wsum);
+                cur.v[1] = __dadd_rn(cur.v[1], __fma_rn(X0, wsum, c1));
+                cur.v[2] = __dadd_rn(cur.v[2], __fma_rn(Y[0], wsum, sy));
             }
         }
     }   // steps

@@ -195,6 +195,7 @@ static inline double __dsub_rn(double a, double b) { return a - b; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
 static inline double __dsqrt_rn(double a) { return std::sqrt(a); }
+static inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 static inline long long __double_as_longlong(double d) { long long r; std::memcpy(&r, &d, 8); return r; }
 static inline double __longlong_as_double(long long l) { double r; std::memcpy(&r, &l, 8); return r; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
