@@ -180,8 +180,8 @@ int tess_get_status(tess_ctx* ctx, int* converged, int* nonfinite, void* stream)
  * tess_launch_count returns how many kernels this library has launched in this process.
  */
 int tess_get_kernel_timing(tess_ctx* ctx, double* ms_total, long* launches);
-/* Diagnostics of the last list build: out[0] = quadrants that fell back to scanning the complete
- * generator table, out[1] = arena records used, out[2] = arena capacity, out[3] = quadrants whose
+/* Diagnostics of the last list build: out[0] = quadrants handed to the per-pixel ring search (their
+ * tile overflowed the list builder: bins of a few pixels), out[1] = arena records used, out[2] = arena capacity, out[3] = quadrants whose
  * list exceeded the fast path (scan of the list).  Synchronises the device. */
 int tess_get_list_stats(tess_ctx* ctx, long* out4);
 long tess_launch_count(void);

@@ -139,4 +139,4 @@ class CApi(object):
     def list_stats(self, ctx):
         out = (_l * 4)()
         self.call("tess_get_list_stats", ctx, out)
-        return dict(scan_all=out[0], arena_used=out[1], arena_capacity=out[2], scan_list=out[3])
+        return dict(ring_fallback=out[0], arena_used=out[1], arena_capacity=out[2], scan_list=out[3])

@@ -1,14 +1,18 @@
 // tess_common.cuh -- shared definitions for the sm_100a kernels of libtess_b200.so.
 //
 // Geometry of the pruning hierarchy (image mode):
-//   super-tile  64 x 64 px   one CTA work unit; candidate list built by k_build_lists
+//   tile        64 x 64 px   one warp of k_build_qlists: box search over the generator grid, then
+//                            the candidate lists of its four quadrants
+//   quadrant    32 x 32 px   one warp of k_image_main: list staged in shared memory (cp.async)
+//   block       16 x 16 px   16 lanes; intermediate filter for long quadrant lists
 //   warp tile   32 x  8 px   one warp step; each lane owns a 2-column x 4-row patch (8 px),
 //                            so every row of a warp tile is 16 lanes x 16 B = 256 B contiguous
 //   leaf         8 x  8 px   8 lanes (4 across x 2 down); shortest candidate list
 // A generator g can be the nearest one somewhere in a rectangle T only if
-//   mind2(g,T) <= min_h maxd2(h,T)        (times the scale weights in WVT mode)
-// so each level keeps exactly those (plus a 2^-39 relative slack that covers every fp64
-// rounding difference between these bounds and the pinned per-pixel formula).
+//   mind2(g,T) <= min_h maxd2(h,T)        (times the scale weights in WVT mode);
+// for a disc of radius rho around c the sharper form is |c-g| <= min_h |c-h| + 2 rho.
+// Each level keeps exactly those (plus a 2^-39 relative slack that covers every fp64 rounding
+// difference between these bounds and the pinned per-pixel formula).
 #pragma once
 #include <stdint.h>
 #include <math.h>
@@ -22,27 +26,18 @@ static long g_tess_launches = 0;   // kernels launched by the library (host-side
 #define TESS_LAUNCH(kern, grid, block, stream, ...) (++g_tess_launches, kern<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__))
 #endif
 
-#define TESS_TS 64            // super-tile edge, px
-#define TESS_WT_W 32          // warp-tile width, px
-#define TESS_WT_H 8           // warp-tile height, px
+#define TESS_TS 64            // tile edge, px
 #define TESS_CAP 512           // candidates of one tile staged in shared memory
 #define TESS_LEAF_CAP 24      // candidates of one 8x8 leaf
 #define TESS_MAIN_THREADS 64  // image main kernel: 2 independent warps per CTA
 #ifndef TESS_MAIN_MINBLOCKS
 #define TESS_MAIN_MINBLOCKS 8 // CTAs per SM the main kernel is compiled for (<= 128 registers)
 #endif
-#ifndef TESS_PREFETCH
-#define TESS_PREFETCH 0         // request the pixels of warp tile s+1 while warp tile s is processed
-#endif
-#ifndef TESS_PREFETCH_CACHE
-#define TESS_PREFETCH_CACHE 0   // 0: none; 1: prefetch.global.L2 of the next warp tile's rows; 2: into L1
-#endif
 #ifndef TESS_MAIN_MINBLOCKS_SN
 #define TESS_MAIN_MINBLOCKS_SN 6 // same for the signal/noise mode (two maps in flight: <= 168 registers)
 #endif
 #define TESS_FULL 0xffffffffu
 #define TESS_NAN (__longlong_as_double(0x7ff8000000000000LL))
-#define TESS_BRUTE (-1)       // list_cnt marker: list did not fit, scan every generator
 
 // relative slack on bound comparisons, 1 + 2^-39
 #define TESS_SLACK 1.0000000000018189894035458564758300781250
@@ -70,9 +65,9 @@ struct TessState {
     int counted;                     // 1 if n_changed was actually counted this iteration
     int converged;                   // latch: once set every kernel of later iterations is a no-op
     int flags;                       // TESS_FLAG_*; non-zero also stops the iteration kernels
-    int tile_counter;                // dynamic tile scheduler of the main kernel
+    int tile_counter;                // scratch: fullest cell of the coarse grid (k_cell_occupancy_max)
     int have_prev;                   // previous-iteration labels exist
-    int n_brute;                     // tiles that fell back to the exhaustive scan (diagnostic)
+    int n_brute;                     // quadrants handed to the per-pixel ring search (entries of ring_q)
     unsigned list_cursor;            // bump allocator of the candidate-list arena
     unsigned spare_;
     unsigned update_ran;             // k_update_nodes did work this iteration (read by k_update_finish)
@@ -82,8 +77,6 @@ struct TessState {
 #define TESS_FLAG_NONFINITE 1
 // iteration kernels are no-ops once the latch closed or an error flag is up (unless forced)
 #define TESS_STOPPED(st, honor) ((honor) && ((st)->converged | (st)->flags))
-
-__host__ __device__ __forceinline__ double tess_sq(double a) { return a * a; }
 
 // max over the rectangle of the squared distance to (gx,gy) -- an upper bound (to rounding)
 __host__ __device__ __forceinline__ double tess_maxd2(const TessRect& r, double gx, double gy) {
@@ -131,12 +124,3 @@ TESS_DEVFN double tess_d2_pinned(double px, double py, double gx, double gy) {
     return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
 }
 
-// (distance, generator index) packed so that one unsigned compare is the lexicographic
-// "smaller distance, then lower index" order.  d2 >= +0 always, so its bit pattern orders
-// like the value; NaN/Inf patterns sort last.
-typedef unsigned __int128 tess_key_t;
-TESS_DEVFN tess_key_t tess_make_key(double d, int gid) {
-    return ((tess_key_t)(unsigned long long)__double_as_longlong(d) << 32) | (unsigned)gid;
-}
-#define TESS_KEY_MAX (~(tess_key_t)0)
-TESS_DEVFN int tess_key_gid(tess_key_t k) { return (int)(unsigned)k; }

@@ -101,18 +101,6 @@ TESS_DEVFN void tess_cp_async4(void* dst, const void* src) {
     memcpy(dst, src, 4);
 #endif
 }
-// prefetch of one global address into L2 (TESS_PREFETCH_CACHE 1) or L1 (2); nothing under the emulator
-TESS_DEVFN void tess_prefetch(const void* p) {
-#ifndef TESS_EMU
-#if TESS_PREFETCH_CACHE == 2
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#else
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#endif
-#else
-    (void)p;
-#endif
-}
 TESS_DEVFN void tess_cp_async_wait() {
 #ifndef TESS_EMU
     asm volatile("cp.async.wait_all;" ::: "memory");
@@ -496,12 +484,8 @@ TESS_DEVFN void tess_quadrant_body(const TessImgArgs& a, TessWarpSmem<MODE, HAS_
         // a masked pixel somewhere: fall through to the general path (labels are rewritten there)
     }
 
-    // ---- request the pixels of the first warp tile (the accumulator table is all zero here: it
-    //      is cleared once at kernel start and every entry is zeroed again when it is flushed)
-#if TESS_PREFETCH
-    double wn_[4][2], nn_[4][2];
-    if (MODE != 0) tess_load_patch<MODE>(a, src, interior, px, qy0 + 4 * ry, wn_, nn_);
-#endif
+    // (the accumulator table is all zero here: it is cleared once at kernel start and every entry is
+    //  zeroed again when it is flushed)
 
     const unsigned short* pl = nullptr;   // parent list of the leaf filter (quadrant-list positions)
     bool p_ident = true;
@@ -516,29 +500,11 @@ TESS_DEVFN void tess_quadrant_body(const TessImgArgs& a, TessWarpSmem<MODE, HAS_
 #pragma unroll
         for (int r = 0; r < 4; ++r) Y[r] = a.y0 + (double)(py + r);
 
-        // ---- pixel data of this warp tile was requested one warp tile ahead (software pipeline).
-        //      Pixels outside the image read as NaN and drop out with the masked ones.
+        // ---- pixel data of this warp tile.  Pixels outside the image read as NaN and drop out with
+        //      the masked ones.  (Requesting them one warp tile ahead -- in registers or as L2/L1
+        //      prefetches -- measured slower: 16 warps per SM already hide the latency.)
         double w_[4][2], n_[4][2];                     // MODE 1: weight; MODE 2: signal, noise
-        if (MODE != 0) {
-#if TESS_PREFETCH
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-                for (int c = 0; c < 2; ++c) { w_[r][c] = wn_[r][c]; if (MODE == 2) n_[r][c] = nn_[r][c]; }
-            if (step < 3 && wy0 + 8 < a.H) tess_load_patch<MODE>(a, src, interior, px, py + 8, wn_, nn_);
-#else
-            tess_load_patch<MODE>(a, src, interior, px, py, w_, n_);
-            // cache prefetch of the next warp tile's rows (no registers held): its loads then hit
-            // in L2 / L1 instead of paying the full HBM latency
-            if (TESS_PREFETCH_CACHE && interior && step < 3) {
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    tess_prefetch(src + base0 + (8 + r) * a.W);
-                    if (MODE == 2) tess_prefetch(a.noise + base0 + (8 + r) * a.W);
-                }
-            }
-#endif
-        }
+        if (MODE != 0) tess_load_patch<MODE>(a, src, interior, px, py, w_, n_);
 
         // ---- 16x16 block lists (every other step), only where the quadrant list is long
         if ((step & 1) == 0) {

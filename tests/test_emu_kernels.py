@@ -197,7 +197,7 @@ def test_options_and_dense_fallbacks(eng):
     rm = O.np_moments(np.column_stack((x.ravel(), y.ravel())), w.ravel(), ref.ravel(), dense.shape[0])
     np.testing.assert_allclose(eng.moments()[:, :4], rm[:, :4], rtol=1e-12, atol=0)
     st = eng.list_stats()
-    assert st["scan_all"] + st["scan_list"] > 0
+    assert st["ring_fallback"] + st["scan_list"] > 0
 
 
 def test_every_pixel_its_own_generator_and_dense_scaled(eng):
@@ -215,7 +215,7 @@ def test_every_pixel_its_own_generator_and_dense_scaled(eng):
     m = eng.moments()
     np.testing.assert_allclose(m[:, 0], 1.0)
     np.testing.assert_allclose(m[:, 1], w.ravel(), rtol=1e-15)
-    assert eng.list_stats()["scan_all"] > 0
+    assert eng.list_stats()["ring_fallback"] > 0
     eng.update()
     np.testing.assert_allclose(eng.generators(), xy, rtol=0, atol=1e-12)
     # dense + scaled metric

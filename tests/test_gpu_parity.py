@@ -403,7 +403,7 @@ def test_list_diagnostics_and_dense_fallbacks(eng):
     np.testing.assert_allclose(h(eng.moments())[:, :4], O.np_moments(xy, w.ravel(), ref.ravel(), dense.shape[0])[:, :4],
                                rtol=1e-12, atol=0)
     st = eng.list_stats()
-    assert st["scan_all"] + st["scan_list"] > 0 and st["arena_used"] <= st["arena_capacity"]
+    assert st["ring_fallback"] + st["scan_list"] > 0 and st["arena_used"] <= st["arena_capacity"]
 
 
 @pytest.mark.parametrize("area", [40.0, 10.0, 2.0, 1.0])
@@ -430,7 +430,7 @@ def test_small_bins_ring_fallback(eng, area):
     rm = O.np_moments(np.column_stack((x.ravel(), y.ravel())), w.ravel(), ref.ravel(), k)
     np.testing.assert_allclose(h(eng.moments())[:, :4], rm[:, :4], rtol=1e-12, atol=0)
     st = eng.list_stats()
-    assert st["scan_all"] > 0
+    assert st["ring_fallback"] > 0
     # the segmap query takes the same path
     assert np.array_equal(h(eng.assign_grid(0.0, 0.0, N, N)), ref)
 
