@@ -520,10 +520,10 @@ static int build_lists(tess_ctx* c, const Geometry& q, int honor, cudaStream_t s
     if (grid > c->sm_count * 32) grid = c->sm_count * 32;
     if (c->has_scale)
         TESS_LAUNCH((k_build_qlists<true>), grid, TESS_LIST_WARPS * 32, s, c->st, honor, q.T, q.g, c->cell_start,
-                    c->cell_items, c->cell_xy, c->cell_inv, c->ql, c->tile_ring);
+                    c->cell_items, c->cell_xy, c->cell_inv, c->ql, c->tile_ring, c->cell_shift > 0 ? 1 : 0);
     else
         TESS_LAUNCH((k_build_qlists<false>), grid, TESS_LIST_WARPS * 32, s, c->st, honor, q.T, q.g, c->cell_start,
-                    c->cell_items, c->cell_xy, c->cell_inv, c->ql, c->tile_ring);
+                    c->cell_items, c->cell_xy, c->cell_inv, c->ql, c->tile_ring, c->cell_shift > 0 ? 1 : 0);
     CU_TRY(cudaGetLastError());
     return TESS_OK;
 }

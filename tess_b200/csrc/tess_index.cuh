@@ -197,7 +197,7 @@ struct TessQLists {
 template <bool HAS_SCALE>
 __global__ void __launch_bounds__(TESS_LIST_WARPS * 32)
 k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cell_start, const int* cell_items,
-               const double2* cell_xy, const double* cell_inv, TessQLists L, int* tile_ring) {
+               const double2* cell_xy, const double* cell_inv, TessQLists L, int* tile_ring, int dense) {
     if (TESS_STOPPED(st, honor)) return;
     __shared__ __align__(16) double2 s_xy[TESS_LIST_WARPS][TESS_CAP];
     __shared__ double s_iv[HAS_SCALE ? TESS_LIST_WARPS : 1][HAS_SCALE ? TESS_CAP : 1];
@@ -209,7 +209,7 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
     const double min_inv = HAS_SCALE ? st->min_inv_s2 : 1.0;
     double2* const xy = s_xy[wib];
     double* const iv = HAS_SCALE ? s_iv[wib] : nullptr;
-    unsigned* const key = s_key[wib];       // grid slot, later generator index
+    unsigned* const key = s_key[wib];       // generator index
 
     for (int t = warp; t < T.n_tiles; t += n_warps) {
         const TessRect r = tess_tile_rect(T, t);
@@ -218,10 +218,13 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
         const int ci0 = tess_cell_coord(r.x0, g.ox, g.inv_cs, g.gw), ci1 = tess_cell_coord(r.x1, g.ox, g.inv_cs, g.gw);
         const int cj0 = tess_cell_coord(r.y0, g.oy, g.inv_cs, g.gh), cj1 = tess_cell_coord(r.y1, g.oy, g.inv_cs, g.gh);
 
+        const int ring_hint = tile_ring[t];     // requested before step 0 so that its latency overlaps
         // ---- 0. a tile that holds more generators than a list can (bins of a few pixels): every one
         //      of them is a candidate, so the tile overflows whatever R is -- hand its quadrants to the
-        //      per-pixel ring search of the image kernel without walking any box
-        {
+        //      per-pixel ring search of the image kernel without walking any box.  Only asked on
+        //      refined grids (`dense`: some tile is known to be that full); on the coarse grid the
+        //      check would cost every tile a dependent load (7 us of 68 at C3) for nothing.
+        if (dense) {
             int tot0 = 0;
             for (int j = cj0 + lane; j <= cj1; j += 32)
                 tot0 += cell_start[(long)j * g.gw + ci1 + 1] - cell_start[(long)j * g.gw + ci0];
@@ -246,7 +249,7 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
         //      While walking, the box generators are also staged in shared memory (if they fit), so
         //      that step 2 needs no second pass over global memory.
         double rbest;
-        int ring = max(1, (tile_ring[t] * 3) / 4);
+        int ring = max(1, (ring_hint * 3) / 4);
         int xi0, xi1, xj0, xj1;
         int n_box;
         for (;;) {
@@ -265,7 +268,7 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
                 if (pos < TESS_CAP) {
                     xy[pos] = p;
                     if (HAS_SCALE) iv[pos] = pv;
-                    key[pos] = (unsigned)i;      // slot for now
+                    key[pos] = (unsigned)cell_items[i];      // generator index (independent, coalesced load)
                 }
             };
             for (int j0 = xj0; j0 <= xj1; j0 += 32) {
@@ -353,7 +356,7 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
                         if (pos < TESS_CAP) {
                             xy[pos] = p;
                             if (HAS_SCALE) iv[pos] = pv;
-                            key[pos] = (unsigned)i;      // slot for now
+                            key[pos] = (unsigned)cell_items[i];
                         }
                     }
                 };
@@ -372,11 +375,6 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
             cnt = s_cnt[wib];
         }
         const bool overflow = cnt > TESS_CAP;
-
-        // ---- 3. generator indices of the staged candidates
-        if (!overflow)
-            for (int i = lane; i < cnt; i += 32) key[i] = (unsigned)cell_items[(int)key[i]];
-        __syncwarp();
 
         // ---- 4. the four quadrants: one pass for the four centre minima, one for the keep flags
         //      (entry i = 32 b + lane -> bit b of the lane's flag word), one arena reservation for
@@ -403,10 +401,12 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
                 const double2 p = xy[i];
                 double v = 1.0;
                 if (HAS_SCALE) { v = iv[i]; imax = fmax(imax, v); }
+                // the centre's x depends on the quadrant's column only, its y on the row only
+                const double ax = qcx[0] - p.x, bx = qcx[1] - p.x, ay = qcy[0] - p.y, by = qcy[2] - p.y;
+                const double axx = ax * ax, bxx = bx * bx, ayy = ay * ay, byy = by * by;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const double dx = qcx[q] - p.x, dy = qcy[q] - p.y;
-                    double d = dx * dx + dy * dy;
+                    double d = ((q & 1) ? bxx : axx) + ((q >> 1) ? byy : ayy);
                     if (HAS_SCALE) d *= v;
                     umin[q] = fmin(umin[q], d);
                 }
@@ -428,10 +428,11 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
                 double2 p = make_double2(0.0, 0.0);
                 double v = 1.0;
                 if (i < cnt) { p = xy[i]; if (HAS_SCALE) v = iv[i]; }
+                const double ax = qcx[0] - p.x, bx = qcx[1] - p.x, ay = qcy[0] - p.y, by = qcy[2] - p.y;
+                const double axx = ax * ax, bxx = bx * bx, ayy = ay * ay, byy = by * by;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const double dx = qcx[q] - p.x, dy = qcy[q] - p.y;
-                    double d = dx * dx + dy * dy;
+                    double d = ((q & 1) ? bxx : axx) + ((q >> 1) ? byy : ayy);
                     if (HAS_SCALE) d *= v;
                     const bool keep = (i < cnt) && qin[q] && (d <= qthr[q]);
                     if (keep) bits[q] |= 1u << b;
