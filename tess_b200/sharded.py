@@ -28,10 +28,11 @@ def shard_rows(H, world, align=64):
 
 
 def balanced_row_shards(generators, H, W, world, x0=0.0, y0=0.0, align=64):
-    """Row ranges whose estimated cost is equal: the image kernel's time per pixel grows with the
-    local generator density rho roughly like c0 + c1 rho^0.4 (fit to measured shard times of the C4
-    map: 3.3 ps/px for empty regions plus 0.4 ps/px of list building, +90 ps/px at one generator per pixel), so equal-height shards
-    of a centrally concentrated map would leave the central ranks 2-3x slower than the outer ones.
+    """Row ranges whose estimated cost is equal: the time per pixel of one accumulate (list building +
+    image kernel) grows with the local generator density rho (generators per pixel) like
+    3.2 + 42 rho^0.256 ps/px -- a least-squares fit to the per-rank accumulate times of the C4 map on
+    8 GPUs (residuals <= 1 %), consistent with tools/regime_bench.py -- so equal-height shards of a
+    centrally concentrated map would leave the central ranks 2-3x slower than the outer ones.
     `generators` is the (k, 2) table (host array); boundaries fall on multiples of `align` rows."""
     import numpy as np
     g = np.asarray(generators, dtype=np.float64)
@@ -42,7 +43,7 @@ def balanced_row_shards(generators, H, W, world, x0=0.0, y0=0.0, align=64):
     iy = np.clip(((g[:, 1] - y0) // align).astype(np.int64), 0, nty - 1)
     cnt = np.bincount(iy * ntx + ix, minlength=nty * ntx).reshape(nty, ntx).astype(np.float64)
     tile_px = float(align * align)
-    cost = (tile_px * (3.7 + 90.0 * (cnt / tile_px) ** 0.4)).sum(axis=1)      # per tile row
+    cost = (tile_px * (3.2 + 42.0 * (cnt / tile_px) ** 0.256)).sum(axis=1)     # per tile row
     cum = np.concatenate(([0.0], np.cumsum(cost)))
     cuts = [0]
     for r in range(1, world):
