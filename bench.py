@@ -332,12 +332,12 @@ def main():
     eng = Engine(local)
     drv = ShardedLloyd(eng) if world > 1 else None
 
-    def setup(e, r0, r1):
+    def setup(e, r0, r1, d=None):
         m = maps(r0, r1)
         e.set_image(y0=float(r0), **m)
         if (r1 - r0) != N:
             e.set_domain(0.0, 0.0, float(N), float(N))      # the generator table spans the full image
-        e.set_generators(seeds)
+        (d.set_generators(seeds) if d is not None else e.set_generators(seeds))
 
     def step(n=1):
         if drv is not None:
@@ -350,14 +350,13 @@ def main():
         else:
             eng.step(n)
 
-    setup(eng, r0, r1)
+    setup(eng, r0, r1, drv)
     launches0 = eng.api.launch_count()
     if drv is not None:
         # communicator set-up is not a step: let NCCL finish its lazy channel/buffer initialisation on
         # the real message (the moment vector) before the W warm-up steps
-        mv0 = drv._moments()
         for _ in range(10):
-            dist.all_reduce(mv0, op=dist.ReduceOp.SUM)
+            drv.exchange_moments()
         barrier()
     step(args.warmup)
     # NVML set-up (nvmlInit enumerates every GPU of the box: milliseconds) happens before the barrier,
@@ -427,10 +426,9 @@ def main():
     breakdown = None
     if world > 1:
         ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(8)]
-        mv = drv._moments()
         for e4 in ev:
             e4[0].record(); eng.accumulate(); e4[1].record()
-            dist.all_reduce(mv, op=dist.ReduceOp.SUM); e4[2].record()
+            drv.exchange_moments(); e4[2].record()
             eng.update(); e4[3].record()
         torch.cuda.synchronize()
         acc = float(np.mean([e4[0].elapsed_time(e4[1]) for e4 in ev[2:]]))
@@ -461,7 +459,7 @@ def main():
             e2.set_image(y0=float(r0), **host_in)          # H2D of this step's maps (pinned -> device)
             if (r1 - r0) != N:
                 e2.set_domain(0.0, 0.0, float(N), float(N))
-            e2.set_generators(seeds_pin)                    # H2D of the generator table
+            (d2.set_generators(seeds_pin) if d2 is not None else e2.set_generators(seeds_pin))   # H2D of the generator table
             (d2.step(1) if d2 is not None else e2.step(1))
             lab_pin.copy_(e2.labels(), non_blocking=True)   # D2H of the results
             node_pin.copy_(e2.generators(), non_blocking=True)
@@ -521,6 +519,7 @@ def main():
                 "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": wl["name"], "pixels": N * N, "generators": k, "mode": mode,
                            "bytes_per_px": BYTES_PER_PX[mode], "parallelism": ("rows x%d (%s) + allreduce(moments)" % (world, "cost-balanced" if args.balance else "equal")) if world > 1 else "1 GPU",
+                           "exchange": drv.exchange if drv is not None else None,
                            "shard_rows": [list(x) for x in shards] if world > 1 or fake else None,
                            "l2": "inputs (%.0f MB per GPU) larger than L2 (126 MB); no flush needed" % (
                                (BYTES_PER_PX[mode] - 4) * (r1 - r0) * N / 1e6),

@@ -142,6 +142,23 @@ int tess_lloyd_accumulate(tess_ctx* ctx, void* stream);
 int tess_moments_ptr(tess_ctx* ctx, double** dev_ptr, long* n_doubles, int* n_moments);
 int tess_lloyd_update(tess_ctx* ctx, void* stream);
 
+/*
+ * The exchange step without NCCL (multi-GPU, one NVSwitch node).  tess_set_moment_buffer makes the
+ * context keep its moment vector in caller memory -- a SYMMETRIC allocation of the same size on
+ * every rank (>= 6 k + 2 doubles, 16-byte aligned; NULL returns to a library-owned vector).
+ * tess_peer_allreduce then sums that vector over the ranks in place, in one kernel of this
+ * library: with `multicast_ptr` (an NVLS multicast mapping of the allocation) the switch does the
+ * reduction (multimem.ld_reduce / multimem.st); otherwise `peer_ptrs[0..world-1]` (HOST array of
+ * the peer-mapped device addresses, own rank included) are read and written over NVLink.  All
+ * ranks end with bit-identical sums.  The caller provides the cross-rank ordering: a device-side
+ * barrier over all ranks before the call (stream-ordered after tess_lloyd_accumulate) and after it
+ * (before tess_lloyd_update).  Replaces: nothing in the reference (single process, lloyd.pyx:58-65
+ * sums in one loop); it is the collective of SURVEY.md section 8e.
+ */
+int tess_set_moment_buffer(tess_ctx* ctx, double* buf, long n_doubles);
+int tess_peer_allreduce(tess_ctx* ctx, int world, int rank, double* const* peer_ptrs, double* multicast_ptr,
+                        long n_doubles, void* stream);
+
 /* n_steps iterations back to back, no host synchronisation (benchmarks, fixed-step use). */
 int tess_lloyd_step(tess_ctx* ctx, long n_steps, void* stream);
 

@@ -39,6 +39,8 @@ SIGNATURES = {
     "tess_set_generators": (_i, [_vp, _l, _vp, _vp, _vp]),
     "tess_lloyd_accumulate": (_i, [_vp, _vp]),
     "tess_moments_ptr": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_l), ctypes.POINTER(_i)]),
+    "tess_set_moment_buffer": (_i, [_vp, _vp, _l]),
+    "tess_peer_allreduce": (_i, [_vp, _i, _i, ctypes.POINTER(_vp), _vp, _l, _vp]),
     "tess_lloyd_update": (_i, [_vp, _vp]),
     "tess_lloyd_step": (_i, [_vp, _l, _vp]),
     "tess_lloyd_run": (_i, [_vp, _l, ctypes.POINTER(_i), ctypes.POINTER(_l), _vp]),

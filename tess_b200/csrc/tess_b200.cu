@@ -16,6 +16,7 @@
 #include "tess_image.cuh"
 #include "tess_points.cuh"
 #include "tess_update.cuh"
+#include "tess_peer.cuh"
 
 #include <stdarg.h>
 #include <stdio.h>
@@ -85,6 +86,7 @@ struct tess_ctx {
     long lab_cap;
     double* mom;
     long mom_cap;
+    int mom_external;   // mom is caller memory (tess_set_moment_buffer): never freed or grown here
     double* prev_count;
     double* scratch;   // 8 doubles (bounding-box reduction)
     double* delta_part; // per-CTA partial deltas of k_update_nodes
@@ -148,7 +150,7 @@ extern "C" int tess_ctx_destroy(tess_ctx* c) {
     cudaDeviceSynchronize();
     void* ptrs[] = {c->node, c->scale, c->inv_s2, c->st, c->cell_cnt, c->cell_start, c->block_sum, c->cell_of, c->cell_items,
                     c->cell_xy, c->cell_inv, c->ql.q_off, c->ql.q_cnt, c->ql.ring_q, c->ql.xy, c->ql.gid, c->ql.inv, c->tile_ring, c->lab[0], c->lab[1],
-                    c->mom, c->prev_count, c->scratch, c->delta_part};
+                    c->mom_external ? nullptr : c->mom, c->prev_count, c->scratch, c->delta_part};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (c->h_st) cudaFreeHost(c->h_st);
@@ -487,6 +489,8 @@ static int ensure_lists(tess_ctx* c, const TessTiles& T) {
 static int ensure_moments(tess_ctx* c) {
     const long need = (long)c->k * 6 + TESS_TAIL;
     if (need <= c->mom_cap) return TESS_OK;
+    if (c->mom_external)
+        return tess_fail(TESS_ERR_ARG, "the moment buffer given to tess_set_moment_buffer holds %ld doubles, %ld needed", c->mom_cap, need);
     if (c->mom) cudaFree(c->mom);
     c->mom = nullptr;
     c->mom_cap = 0;
@@ -736,6 +740,59 @@ extern "C" int tess_moments_ptr(tess_ctx* c, double** dev_ptr, long* n_doubles, 
     if (n_doubles) *n_doubles = (long)c->k * M + TESS_TAIL;
     if (n_mom) *n_mom = M;
     return TESS_OK;
+}
+
+extern "C" int tess_set_moment_buffer(tess_ctx* c, double* buf, long n_doubles) {
+    TRY(bind(c));
+    if (!buf) {                       // back to a library-owned vector
+        if (c->mom_external) { c->mom = nullptr; c->mom_cap = 0; c->mom_external = 0; }
+        return TESS_OK;
+    }
+    if (n_doubles < TESS_TAIL + 6 || ((uintptr_t)buf & 15u))
+        return tess_fail(TESS_ERR_ARG, "tess_set_moment_buffer: need a 16-byte aligned buffer of at least 6 k + %d doubles", TESS_TAIL);
+    if (c->mom && !c->mom_external) cudaFree(c->mom);
+    c->mom = buf;
+    c->mom_cap = n_doubles;
+    c->mom_external = 1;
+    return TESS_OK;
+}
+
+extern "C" int tess_peer_allreduce(tess_ctx* c, int world, int rank, double* const* peer_ptrs, double* multicast_ptr,
+                                   long n_doubles, void* stream) {
+    TRY(bind(c));
+#ifdef TESS_EMU
+    (void)world; (void)rank; (void)peer_ptrs; (void)multicast_ptr; (void)n_doubles; (void)stream;
+    return tess_fail(TESS_ERR_STATE, "tess_peer_allreduce: no peer memory in the emulator build");
+#else
+    if (world < 1 || world > TESS_PEER_MAX || rank < 0 || rank >= world || n_doubles <= 0 || (!peer_ptrs && !multicast_ptr))
+        return tess_fail(TESS_ERR_ARG, "tess_peer_allreduce: bad arguments (world <= %d)", TESS_PEER_MAX);
+    // rank r owns [lo, hi); slices start on even elements (16-byte accesses), the vector is even
+    if (n_doubles & 1) return tess_fail(TESS_ERR_ARG, "tess_peer_allreduce: n_doubles must be even");
+    long per = (n_doubles + world - 1) / world;
+    per += per & 1;
+    const long lo = per * rank, hi = (lo + per < n_doubles) ? lo + per : n_doubles;
+    if (hi <= lo) return TESS_OK;
+    long nb = (hi - lo + 255) / 256;
+    if (nb > c->sm_count * 8) nb = c->sm_count * 8;
+    if (multicast_ptr) {
+        nb = (hi - lo + 4 * 256 - 1) / (4 * 256);           // four elements per thread and trip
+        if (nb > c->sm_count * 8) nb = c->sm_count * 8;
+        TESS_LAUNCH((k_peer_sum_multimem), (int)nb, 256, S(stream), multicast_ptr, lo, hi);
+    } else {
+        TessPeers P;
+        memset(&P, 0, sizeof(P));
+        P.world = world; P.rank = rank;
+        for (int r = 0; r < world; ++r) {
+            if (!peer_ptrs[r]) return tess_fail(TESS_ERR_ARG, "tess_peer_allreduce: null peer pointer for rank %d", r);
+            P.ptr[r] = peer_ptrs[r];
+        }
+        nb = ((hi - lo) / 2 + 255) / 256;
+        if (nb > c->sm_count * 8) nb = c->sm_count * 8;
+        TESS_LAUNCH((k_peer_sum_p2p), (int)nb, 256, S(stream), P, lo, hi);
+    }
+    CU_TRY(cudaGetLastError());
+    return TESS_OK;
+#endif
 }
 
 extern "C" int tess_lloyd_update(tess_ctx* c, void* stream) {

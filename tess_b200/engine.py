@@ -166,6 +166,18 @@ class Engine(object):
         """Reference loop and stop rule (tess/lloyd.pyx:47-90).  Returns (converged, n_iters)."""
         return self.api.lloyd_run(self.ctx, int(max_iters), self._stream())
 
+    def set_moment_buffer(self, t, n_doubles):
+        """Keep the packed moment vector in caller memory `t` (a symmetric allocation shared with the
+        peer ranks, see tess_b200.sharded); None returns to a library-owned vector."""
+        self.api.call("tess_set_moment_buffer", self.ctx, None if t is None else self._ptr(t), int(n_doubles))
+        self._keep["mom_ext"] = t
+
+    def peer_allreduce(self, world, rank, peer_ptrs, multicast_ptr, n_doubles):
+        """Sum the moment vector over the ranks in place with the library's own kernel
+        (tess_peer_allreduce): `peer_ptrs` a ctypes array of the peer-mapped addresses."""
+        self.api.call("tess_peer_allreduce", self.ctx, int(world), int(rank), peer_ptrs,
+                      multicast_ptr if multicast_ptr else None, int(n_doubles), self._stream())
+
     def moments_view(self):
         """The library's packed local moment vector [k*M | tail] as a tensor ALIASING device memory:
         what a multi-GPU driver all-reduces between accumulate() and update()."""

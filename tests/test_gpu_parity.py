@@ -469,3 +469,41 @@ def test_wvt_binning_to_target_sn_gpu(engine_cls):
     import frow_checks
     r = frow_checks.check_wvt_binning(lambda: engine_cls(0), N=256, k=120)
     assert r["labels"].shape == (256, 256)
+
+
+def test_external_moment_buffer_and_peer_allreduce_world1(eng, engine_cls):
+    """tess_set_moment_buffer + tess_peer_allreduce on one GPU: caller-owned moment vector gives the
+    same moments, and the (world = 1) two-shot kernel is the identity on it.  The multi-rank paths
+    are exercised by tools/peer_probe.py and bench.py --gpus N on the multi-GPU boxes."""
+    import ctypes
+    import torch
+    N, k = 192, 60
+    w = gaussian_image(N) + 0.5
+    seeds = sampled_seeds(w, k, seed=2)
+    eng.set_image(density=w)
+    eng.set_generators(seeds)
+    eng.step(2)
+    want_m, want_g = h(eng.moments()), h(eng.generators())
+    e2 = engine_cls(0)
+    buf = torch.full((6 * k + 2,), 7.0, dtype=torch.float64, device="cuda")
+    e2.set_image(density=w)
+    e2.set_generators(seeds)
+    e2.set_moment_buffer(buf, buf.numel())
+    ptr, n, m = e2.api.moments_ptr(e2.ctx)
+    assert ptr == buf.data_ptr() and m == 4 and n == 4 * k + 2
+    ptrs = (ctypes.c_void_p * 1)(buf.data_ptr())
+    for _ in range(2):
+        e2.accumulate()
+        before = buf[:n].clone()
+        e2.peer_allreduce(1, 0, ptrs, 0, n)
+        torch.cuda.synchronize()
+        assert torch.equal(before, buf[:n])
+        e2.update()
+    np.testing.assert_allclose(h(e2.moments()), want_m, rtol=1e-12, atol=0)
+    np.testing.assert_allclose(h(e2.generators()), want_g, rtol=0, atol=1e-9)
+    with pytest.raises(Exception):
+        e2.set_moment_buffer(torch.zeros(8, dtype=torch.float64, device="cuda"), 8)
+        e2.accumulate()
+    e2.set_moment_buffer(None, 0)
+    e2.accumulate()
+    e2.close()
