@@ -825,6 +825,9 @@ extern "C" int tess_lloyd_step(tess_ctx* c, long n_steps, void* stream) {
 static int fetch_state(tess_ctx* c, cudaStream_t s) {
     CU_TRY(cudaMemcpyAsync(c->h_st, c->st, sizeof(TessState), cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaStreamSynchronize(s));
+    // generators that drift into a dense clump overflow tiles the coarse grid was not refined for:
+    // the host is synchronised here anyway, so let the next accumulate decide the cell size again
+    if (c->source == SRC_IMAGE && c->cell_shift == 0 && c->h_st->n_brute > 0) c->cell_shift = -1;
     return TESS_OK;
 }
 

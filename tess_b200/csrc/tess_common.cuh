@@ -65,11 +65,11 @@ struct TessState {
     int counted;                     // 1 if n_changed was actually counted this iteration
     int converged;                   // latch: once set every kernel of later iterations is a no-op
     int flags;                       // TESS_FLAG_*; non-zero also stops the iteration kernels
-    int tile_counter;                // scratch: fullest cell of the coarse grid (k_cell_occupancy_max)
+    int tile_counter;                // quadrant queue of k_image_main (interior); also the scratch of k_cell_occupancy_max
     int have_prev;                   // previous-iteration labels exist
     int n_brute;                     // quadrants handed to the per-pixel ring search (entries of ring_q)
     unsigned list_cursor;            // bump allocator of the candidate-list arena
-    unsigned spare_;
+    unsigned spare_;                 // quadrant queue of k_image_main (edge instantiation)
     unsigned update_ran;             // k_update_nodes did work this iteration (read by k_update_finish)
     int last_parity;                 // label buffer (0/1) written by the most recent accumulate
     int pad_;

@@ -127,7 +127,8 @@ k_cell_scan(TessState* st, int honor, const int* cell_cnt, int* cell_start, int 
             st->min_inv_next = 0x7ff0000000000000ull;   // +inf
         }
         st->list_cursor = 0u;
-        st->tile_counter = 0;
+        st->tile_counter = 0;      // quadrant queues of the interior / edge image kernels
+        st->spare_ = 0u;
         st->n_brute = 0;
     }
 }
