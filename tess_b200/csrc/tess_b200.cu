@@ -518,16 +518,17 @@ static int build_index(tess_ctx* c, const Geometry& q, int honor, double* mom, l
     return TESS_OK;
 }
 
-static int build_lists(tess_ctx* c, const Geometry& q, int honor, cudaStream_t s) {
+static int build_lists(tess_ctx* c, const Geometry& q, int honor, int mode, cudaStream_t s) {
     TRY(ensure_lists(c, q.T));
+    const int qcap = TESS_QCAP(mode);          // longest list the image kernel of this mode stages
     int grid = (q.T.n_tiles + TESS_LIST_WARPS - 1) / TESS_LIST_WARPS;
     if (grid > c->sm_count * 32) grid = c->sm_count * 32;
     if (c->has_scale)
         TESS_LAUNCH((k_build_qlists<true>), grid, TESS_LIST_WARPS * 32, s, c->st, honor, q.T, q.g, c->cell_start,
-                    c->cell_items, c->cell_xy, c->cell_inv, c->ql, c->tile_ring, c->cell_shift > 0 ? 1 : 0);
+                    c->cell_items, c->cell_xy, c->cell_inv, c->ql, c->tile_ring, c->cell_shift > 0 ? 1 : 0, qcap);
     else
         TESS_LAUNCH((k_build_qlists<false>), grid, TESS_LIST_WARPS * 32, s, c->st, honor, q.T, q.g, c->cell_start,
-                    c->cell_items, c->cell_xy, c->cell_inv, c->ql, c->tile_ring, c->cell_shift > 0 ? 1 : 0);
+                    c->cell_items, c->cell_xy, c->cell_inv, c->ql, c->tile_ring, c->cell_shift > 0 ? 1 : 0, qcap);
     CU_TRY(cudaGetLastError());
     return TESS_OK;
 }
@@ -667,7 +668,7 @@ extern "C" int tess_get_list_stats(tess_ctx* c, long* out4) {
     TRY(bind(c));
     if (!out4) return tess_fail(TESS_ERR_ARG, "tess_get_list_stats: out is null");
     TRY(fetch_state(c, nullptr));
-    out4[0] = c->h_st->n_brute;
+    out4[0] = c->h_st->n_brute;      // ring-search quadrants + long lists; the latter are subtracted below
     out4[1] = c->h_st->list_cursor;
     out4[2] = c->ql.capacity;
     out4[3] = 0;
@@ -680,6 +681,7 @@ extern "C" int tess_get_list_stats(tess_ctx* c, long* out4) {
         unsigned long long h = 0;
         CU_TRY(cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost));
         out4[3] = (long)h;
+        out4[0] -= (long)h;
     }
     return TESS_OK;
 }
@@ -703,7 +705,7 @@ extern "C" int tess_lloyd_accumulate(tess_ctx* c, void* stream) {
         Geometry q;
         TRY(image_geometry(c, c->x0, c->y0, c->H, c->W, s, &q));
         TRY(build_index(c, q, 1, c->mom, n_mom, s));
-        TRY(build_lists(c, q, 1, s));
+        TRY(build_lists(c, q, 1, c->img_mode, s));
         timing_mark(c, s, 0);
         TRY(run_image(c, q, c->img_mode, 1, nullptr, s));
         timing_mark(c, s, 1);
@@ -932,7 +934,7 @@ extern "C" int tess_assign_grid(tess_ctx* c, double x0, double y0, long H, long 
     Geometry q;
     TRY(image_geometry(c, x0, y0, H, W, s, &q));
     TRY(build_index(c, q, 0, nullptr, 0, s));
-    TRY(build_lists(c, q, 0, s));
+    TRY(build_lists(c, q, 0, 0, s));
     TRY(run_image(c, q, 0, 0, labels_out, s));
     return TESS_OK;
 }

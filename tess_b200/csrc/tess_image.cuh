@@ -37,6 +37,12 @@
 #define TESS_LEAF_MIN 3     // parent lists up to this length are evaluated without a leaf filter
 // quadrant list capacity of the fast path = entries of a warp's accumulator table
 #define TESS_QCAP(MODE) ((MODE) == 2 ? 96 : 128)
+#ifndef TESS_DYNAMIC
+#define TESS_DYNAMIC 1
+#endif
+#ifndef TESS_RING_ROWS
+#define TESS_RING_ROWS 2
+#endif
 
 struct TessImgArgs {
     const double* dens;    // MODE 1: [H][W] weights
@@ -176,84 +182,88 @@ TESS_DEVFN double tess_center_thr(double umin, double c) {
     return (umin + 2.0 * c * tess_sqrt_up(umin) + c * c) * TESS_SLACK;
 }
 
-// Slow path for a quadrant whose candidate list does not fit the fast path: every pixel scans the
-// whole list (n records at gxy / gids / ginv in GLOBAL memory; gids == null: record j is generator
-// j, i.e. the complete generator table) and sends its moments straight to the global vector.
-// Correct for any density, but slow; kept out of line so that it does not bloat the hot loop.
+// A strip (TESS_RING_ROWS rows x 32 columns, one column per lane) of a quadrant whose candidate list
+// is longer than the fast path stages in shared memory: every pixel scans the whole list (n records
+// at gxy / gids / ginv in global memory, i.e. L2; four records per trip so that the loads overlap)
+// and sends its moments straight to the global vector.  Part of the tail phase of k_image_main.
 template <int MODE, bool HAS_SCALE>
-TESS_NOINLINE void tess_quadrant_scan(const TessImgArgs& a, int32_t* labels, long qx0, long qy0, const double2* gxy,
-                                      const int* gids, const double* ginv, int n) {
+TESS_NOINLINE void tess_rows_scan(const TessImgArgs& a, int32_t* labels, long qx0, long r0, const double2* gxy,
+                                  const int* gids, const double* ginv, int n) {
     constexpr int NV = (MODE == 2) ? 5 : 3;
+    constexpr int R = TESS_RING_ROWS;
     const int lane = threadIdx.x & 31;
-    // lane -> column qx0 + lane, all 32 rows in four passes of 8 rows
     const long c = qx0 + lane;
     const double X = a.x0 + (double)c;
-    for (int r0 = 0; r0 < 32; r0 += 8) {
-        double bd[8];
-        int bi[8];
+    double Y[R], bd[R];
+    int bi[R];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { bd[j] = INFINITY; bi[j] = 0x7fffffff; }
-        for (int i = 0; i < n; ++i) {
-            const double2 g = gxy[i];
-            const double iv = HAS_SCALE ? ginv[i] : 1.0;
-            const int gid = gids ? gids[i] : i;
-            const double dx = __dsub_rn(X, g.x);
-            const double dxx = __dmul_rn(dx, dx);
+    for (int j = 0; j < R; ++j) { Y[j] = a.y0 + (double)(r0 + j); bd[j] = INFINITY; bi[j] = 0x7fffffff; }
+    for (int i = 0; i < n; i += 4) {
+        double2 g[4];
+        double iv[4];
+        int gid[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const double dy = __dsub_rn(a.y0 + (double)(qy0 + r0 + j), g.y);
-                double d = __dadd_rn(dxx, __dmul_rn(dy, dy));
-                if (HAS_SCALE) d = __dmul_rn(d, iv);
-                if ((d < bd[j]) || ((d == bd[j]) && (gid < bi[j]))) { bd[j] = d; bi[j] = gid; }
-            }
+        for (int u = 0; u < 4; ++u) {
+            const int ii = min(i + u, n - 1);
+            g[u] = gxy[ii];
+            iv[u] = HAS_SCALE ? ginv[ii] : 1.0;
+            gid[u] = gids[ii];
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const long r = qy0 + r0 + j;
-            if (c >= a.W || r >= a.H) continue;
-            const long idx = r * a.W + c;
-            labels[idx] = bi[j];
-            if (MODE != 0) {
-                const double Y = a.y0 + (double)r;
-                double val[NV];
-                bool ok;
-                if (MODE == 1) {
-                    const double w = a.dens[idx];
-                    ok = isfinite(w);
-                    val[0] = w; val[1] = __dmul_rn(w, X); val[2] = __dmul_rn(w, Y);
-                } else {
-                    const double S = a.sig[idx], N = a.noise[idx];
-                    double w = 1.0;
-                    if (!a.uniform_weight) { const double q = __ddiv_rn(S, N); w = __dmul_rn(q, q); }
-                    ok = isfinite(w) && isfinite(S) && isfinite(N);
-                    val[0] = w; val[1] = __dmul_rn(w, X); val[2] = __dmul_rn(w, Y);
-                    val[NV - 2] = S; val[NV - 1] = __dmul_rn(N, N);
-                }
-                if (ok) {
-                    double* m = a.mom + (long)bi[j] * (NV + 1);
-                    tess_gmem_add(m, 1.0);
+        for (int u = 0; u < 4; ++u) {
+            if (i + u >= n) break;
+            const double dx = __dsub_rn(X, g[u].x);
+            const double dxx = __dmul_rn(dx, dx);
 #pragma unroll
-                    for (int i = 0; i < NV; ++i) tess_gmem_add(m + 1 + i, val[i]);
-                }
+            for (int j = 0; j < R; ++j) {
+                const double dy = __dsub_rn(Y[j], g[u].y);
+                double d = __dadd_rn(dxx, __dmul_rn(dy, dy));
+                if (HAS_SCALE) d = __dmul_rn(d, iv[u]);
+                if ((d < bd[j]) || ((d == bd[j]) && (gid[u] < bi[j]))) { bd[j] = d; bi[j] = gid[u]; }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        const long r = r0 + j;
+        if (c >= a.W || r >= a.H) continue;
+        const long idx = r * a.W + c;
+        labels[idx] = bi[j];
+        if (MODE != 0) {
+            double val[NV];
+            bool ok;
+            if (MODE == 1) {
+                const double w = a.dens[idx];
+                ok = isfinite(w);
+                val[0] = w; val[1] = __dmul_rn(w, X); val[2] = __dmul_rn(w, Y[j]);
+            } else {
+                const double S = a.sig[idx], N = a.noise[idx];
+                double w = 1.0;
+                if (!a.uniform_weight) { const double q = __ddiv_rn(S, N); w = __dmul_rn(q, q); }
+                ok = isfinite(w) && isfinite(S) && isfinite(N);
+                val[0] = w; val[1] = __dmul_rn(w, X); val[2] = __dmul_rn(w, Y[j]);
+                val[NV - 2] = S; val[NV - 1] = __dmul_rn(N, N);
+            }
+            if (ok) {
+                double* m = a.mom + (long)bi[j] * (NV + 1);
+                tess_gmem_add(m, 1.0);
+#pragma unroll
+                for (int i = 0; i < NV; ++i) tess_gmem_add(m + 1 + i, val[i]);
             }
         }
     }
     __syncwarp();
 }
 
-// Fallback for the quadrants whose tile overflowed the list builder (bins of a few pixels): every
+// Fallback for the quadrants off the fast path -- the tile overflowed the list builder (bins of a few
+// pixels, q_cnt = -1: ring search) or the quadrant's list is longer than the fast path stages
+// (q_cnt > QCAP: tess_rows_scan over that list).  Ring search: every
 // pixel runs the exact ring search of the point-set path over the generator grid (tess_points.cuh),
 // so the cost follows the LOCAL generator density, not k.  The builder collects those quadrants in
 // L.ring_q; after its own quadrants every warp of the grid takes strips of them (TESS_RING_ROWS rows of
 // 32 pixels per warp and turn, one column per lane: walking down a column keeps the cells in L1), so
 // that a few slow quadrants do not become the kernel's tail.
 // Moments go straight to the global vector.
-#ifndef TESS_DYNAMIC
-#define TESS_DYNAMIC 1
-#endif
-#ifndef TESS_RING_ROWS
-#define TESS_RING_ROWS 2
-#endif
 template <int MODE, bool HAS_SCALE>
 TESS_NOINLINE void tess_rows_ring(const TessImgArgs& a, int32_t* labels, long qx0, long r0) {
     constexpr int NV = (MODE == 2) ? 5 : 3;
@@ -842,15 +852,10 @@ k_image_main(TessImgArgs a, int vec) {
         const int qx0 = 32 * qx, qy0 = 32 * qy;            // pixel coordinates fit 32 bits (host-checked)
         const bool interior = vec && (qx0 + 32 <= a.W) && (qy0 + 32 <= a.H);
         const int cnt_cur = (interior != EDGE) ? cnt : 0, off_cur = off;   // the other kernel's quadrants are skipped
-        if (cnt_cur > 0) {                                 // < 0: builder overflow, done in the tail below
-        if (cnt_cur > QC) {
-            // slow path: list too long for the fast path (scan it from global memory)
-            tess_quadrant_scan<MODE, HAS_SCALE>(a, labels, qx0, qy0, a.L.xy + off_cur, a.L.gid + off_cur,
-                                                HAS_SCALE ? a.L.inv + off_cur : nullptr, cnt_cur);
-        } else {
-        tess_quadrant_body<MODE, HAS_SCALE, !EDGE>(a, sm, buf, labels, src, cnt_cur, qx0, qy0, lane);
-        }   // fast path
-        }   // cnt > 0
+        // cnt < 0 (builder overflow) and cnt > QC (list too long for the fast path) are done in the
+        // tail below, spread over all warps
+        if (cnt_cur > 0 && cnt_cur <= QC)
+            tess_quadrant_body<MODE, HAS_SCALE, !EDGE>(a, sm, buf, labels, src, cnt_cur, qx0, qy0, lane);
         // ---- rotate the pipeline
         q = q1; cnt = cnt1; off = off1;
         q1 = q2; cnt1 = cnt2; off1 = off2;
@@ -864,7 +869,15 @@ k_image_main(TessImgArgs a, int vec) {
         for (int item = (int)blockIdx.x * NW + wib; item < n_items; item += stride) {
             const int qq = a.L.ring_q[item / PER_Q];
             const int qy = qq / a.L.nqx, qx = qq - qy * a.L.nqx;
-            tess_rows_ring<MODE, HAS_SCALE>(a, labels, 32L * qx, 32L * qy + TESS_RING_ROWS * (item % PER_Q));
+            const long r0 = 32L * qy + TESS_RING_ROWS * (item % PER_Q);
+            const int cn = a.L.q_cnt[qq];
+            if (cn < 0) {
+                tess_rows_ring<MODE, HAS_SCALE>(a, labels, 32L * qx, r0);
+            } else {       // a list beyond the fast path: every pixel scans it (from L2)
+                const int o = a.L.q_off[qq];
+                tess_rows_scan<MODE, HAS_SCALE>(a, labels, 32L * qx, r0, a.L.xy + o, a.L.gid + o,
+                                                HAS_SCALE ? a.L.inv + o : nullptr, cn);
+            }
         }
     }
 }

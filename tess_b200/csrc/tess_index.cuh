@@ -179,7 +179,7 @@ struct TessQLists {
     double2* xy;       // arena
     int* gid;
     double* inv;       // arena (scaled metric only)
-    int* ring_q;       // [nqx*nqy] the overflowed quadrants (st->n_brute of them), any order
+    int* ring_q;       // [nqx*nqy] the quadrants off the fast path (st->n_brute of them), any order
     unsigned capacity; // arena records
     int nqx, nqy;      // quadrant grid (2 tiles_x, 2 tiles_y)
 };
@@ -198,7 +198,7 @@ struct TessQLists {
 template <bool HAS_SCALE>
 __global__ void __launch_bounds__(TESS_LIST_WARPS * 32)
 k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cell_start, const int* cell_items,
-               const double2* cell_xy, const double* cell_inv, TessQLists L, int* tile_ring, int dense) {
+               const double2* cell_xy, const double* cell_inv, TessQLists L, int* tile_ring, int dense, int qcap) {
     if (TESS_STOPPED(st, honor)) return;
     __shared__ __align__(16) double2 s_xy[TESS_LIST_WARPS][TESS_CAP];
     __shared__ double s_iv[HAS_SCALE ? TESS_LIST_WARPS : 1][HAS_SCALE ? TESS_CAP : 1];
@@ -462,7 +462,9 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
             if (lane == 0) {
                 L.q_off[qid] = ok ? (int)off : 0;
                 L.q_cnt[qid] = !qin[q] ? 0 : (ok ? nq_[q] : -1);
-                if (!ok && qin[q]) L.ring_q[atomicAdd(&st->n_brute, 1)] = (int)qid;
+                // off the fast path of the image kernel (overflow, or a list longer than it stages):
+                // queued for its tail phase
+                if (qin[q] && (!ok || nq_[q] > qcap)) L.ring_q[atomicAdd(&st->n_brute, 1)] = (int)qid;
             }
             if (ok && qin[q]) {
                 int wpos = 0;

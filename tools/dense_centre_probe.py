@@ -20,5 +20,8 @@ for D in (0, 64, 256, 512, 1024):
     eng.accumulate(); eng.accumulate()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(); eng.accumulate(); b.record(); torch.cuda.synchronize()
-    print(json.dumps(dict(D=D, k=int(node.shape[0]), ms_accumulate=a.elapsed_time(b), list_stats=eng.list_stats())), flush=True)
+    a.record()
+    for _ in range(5):
+        eng.accumulate()
+    b.record(); torch.cuda.synchronize()
+    print(json.dumps(dict(D=D, k=int(node.shape[0]), ms_accumulate=a.elapsed_time(b) / 5, list_stats=eng.list_stats())), flush=True)
