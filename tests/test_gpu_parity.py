@@ -507,3 +507,14 @@ def test_external_moment_buffer_and_peer_allreduce_world1(eng, engine_cls):
     e2.set_moment_buffer(None, 0)
     e2.accumulate()
     e2.close()
+
+
+def test_randomised_parity_short():
+    """tools/fuzz_parity.py for a few seconds: random shapes, origins, densities (thousands of px per
+    bin down to one), ties, duplicates, scales and modes against the exhaustive scan."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "8", "7"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " 0 failures" in r.stdout
