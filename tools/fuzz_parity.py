@@ -32,9 +32,34 @@ while time.time() - t0 < budget:
     if k > 3 and rng.random() < 0.3:
         g[k // 2] = g[1]                                      # exact duplicate
     scale = rng.uniform(0.6, 1.7, k) if rng.random() < 0.35 else None
-    mode = int(rng.integers(0, 3))
+    mode = int(rng.integers(0, 4))
     try:
         eng.set_option(_capi.OPT_UNIFORM_WEIGHT, 0)
+        if rng.random() < 0.3:      # a rank's window inside a larger generator domain (sharded use)
+            eng.set_domain(x0 - rng.uniform(0, 300), y0 - rng.uniform(0, 3000), x0 + W + rng.uniform(0, 300), y0 + H + rng.uniform(0, 3000))
+        else:
+            eng.set_domain(1.0, 1.0, 0.0, 0.0)      # none
+        if mode == 3:               # point set (C2-like): lloyd on arbitrary xy
+            n = int(rng.integers(1, 200000))
+            pts = np.column_stack((rng.normal(cx, W / 4 + 1, n), rng.normal(cy, H / 5 + 1, n)))
+            pw = rng.uniform(0.1, 1.0, n)
+            eng.set_points(pts, pw)
+            eng.set_generators(g, scale=scale)
+            eng.accumulate()
+            lab = eng.labels().cpu().numpy().ravel()
+            ref = eng.assign_points(pts, exhaustive=True).cpu().numpy()
+            ok = np.array_equal(lab, ref) and np.array_equal(eng.assign_points(pts).cpu().numpy(), ref)
+            why = "point labels"
+            if ok:
+                want = np.column_stack((np.bincount(ref, minlength=k), np.bincount(ref, weights=pw, minlength=k),
+                                        np.bincount(ref, weights=pw * pts[:, 0], minlength=k), np.bincount(ref, weights=pw * pts[:, 1], minlength=k)))
+                got = eng.moments().cpu().numpy()[:, :4]
+                ok = np.allclose(got, want, rtol=1e-11, atol=1e-9)
+                why = "point moments (max abs diff %.3e)" % np.abs(got - want).max()
+            if not ok:
+                n_fail += 1
+                print("FAIL case %d: %s n=%d k=%d scale=%s" % (n_case, why, n, k, scale is not None), flush=True)
+            continue
         if mode == 2:
             sig = rng.uniform(0.5, 3.0, (H, W)); noise = rng.uniform(0.5, 1.5, (H, W))
             if rng.random() < 0.5: sig[rng.integers(0, H), rng.integers(0, W)] = np.nan
