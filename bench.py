@@ -483,6 +483,38 @@ def main():
         e2e = {"value": (float(N) * N) / dt / 1e9, "unit": UNIT, "ms_per_step": dt * 1e3,
                "h2d_bytes_per_step": int(h2d * world), "d2h_bytes_per_step": int(d2h * world),
                "call": "Engine.set_image(pinned host maps) + set_generators + step(1) + labels()/generators() to pinned host"}
+        # One GPU: the same steps double-buffered -- two Engine contexts on two CUDA streams, so that the
+        # upload of step i+1 overlaps the download of step i (PCIe is full duplex).  Every step still
+        # uploads its inputs and downloads its results; this is the throughput a user gets when
+        # batches are pipelined.  (With N > 1 the two pipelines' collectives would interleave: serial.)
+        if world == 1:
+            eb = [e2, Engine(local)]
+            sb = [torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)]
+            lab_b = [lab_pin, torch.empty((r1 - r0, N), dtype=torch.int32).pin_memory()]
+            node_b = [node_pin, torch.empty((k, 2), dtype=torch.float64).pin_memory()]
+
+            def piped_step(i):
+                e, st = eb[i & 1], sb[i & 1]
+                with torch.cuda.stream(st):
+                    e.set_image(y0=float(r0), **host_in)
+                    e.set_generators(seeds_pin)
+                    e.step(1)
+                    lab_b[i & 1].copy_(e.labels(), non_blocking=True)
+                    node_b[i & 1].copy_(e.generators(), non_blocking=True)
+
+            for i in range(4):
+                piped_step(i)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(n_e2e):
+                piped_step(i)
+            torch.cuda.synchronize()
+            dtp = (time.perf_counter() - t0) / n_e2e
+            e2e["serial_value"], e2e["serial_ms_per_step"] = e2e["value"], e2e["ms_per_step"]
+            e2e["value"], e2e["ms_per_step"] = (float(N) * N) / dtp / 1e9, dtp * 1e3
+            e2e["call"] += "; double-buffered over two Engine contexts / CUDA streams (serial_* = one context, one stream)"
+            eb[1].close()
+            del lab_b, node_b
         e2.close()
         del host_in, lab_pin
 
