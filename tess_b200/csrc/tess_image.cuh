@@ -6,9 +6,11 @@
 // generator rasterisation behind VoronoiTessellation.segmap (tess/voronoi.py:75-114).
 //
 // Work unit: one WARP per 32x32-px quadrant, warps fully independent (no CTA barrier anywhere).
-// The quadrant's candidate list (k_build_qlists: arena records in ascending generator index) is
-// copied into the warp's shared-memory buffer with cp.async one quadrant AHEAD, so list latency is
-// hidden behind the previous quadrant's arithmetic; pixel data is requested one warp tile ahead.
+// A warp's first two quadrants are fixed (q, q + stride), the following ones are drawn from a device
+// queue (one atomic per quadrant, requested a whole quadrant before its value is needed), so no warp
+// idles while others still have work.  The quadrant's candidate list (k_build_qlists: arena records
+// in no particular order) is copied into the warp's shared-memory buffer with cp.async one quadrant
+// AHEAD, so list latency is hidden behind the previous quadrant's arithmetic.
 // For each of its four 32x8 warp tiles the warp narrows the list per 16x16 block (long lists only)
 // and per 8x8 leaf (8 lanes per leaf) with the centre + radius test
 //     keep g  iff  u(c,g) <= min_h u(c,h) + 2 rho / s_min        (u = distance / scale)
@@ -18,12 +20,17 @@
 //
 // Moments ("segmented reduction"): every lane owns a 2-column x 4-row pixel patch per warp tile and
 // keeps ONE running same-bin sum in registers across the warp tiles of the quadrant (labels are
-// spatially coherent, so most patches extend the current run).  When a lane's run ends, its sums go
-// to the warp's shared-memory table of per-candidate accumulators; lanes that retire the same bin in
-// the same round are serialised with match.any (warp-level aggregation, no atomics: the table is
-// private to the warp).  At the end of the quadrant the live runs are merged across the warp with
-// shuffles and the table goes to the global moment vector -- one fp64 reduction per
-// (quadrant, bin, moment).  The fold is written without lane-divergent branches.
+// spatially coherent, so most patches extend the current run); a patch is summed in patch-local
+// coordinates and shifted once.  When a lane's run ends, its sums go to the warp's shared-memory
+// table of per-candidate accumulators; lanes that retire the same bin in the same round take turns
+// through a claim slot (warp-level aggregation, no atomics: the table is private to the warp).  At
+// the end of the quadrant the live runs are merged across the warp with shuffles and the table goes
+// to the global moment vector -- one fp64 reduction per (quadrant, bin, moment).  The fold is written
+// without lane-divergent branches.
+//
+// Tail phase: quadrants off this fast path (list longer than the table, or a tile that overflowed
+// the builder) are queued by the builder; after their own quadrants all warps of the grid take
+// 2-row strips of them (list scan from L2, or the per-pixel ring search over the generator grid).
 //
 // Algorithmic HBM traffic per pixel: MODE 1: 8 B (density) + 4 B (label) = 12 B;
 // MODE 2: 8 + 8 B (signal, noise) + 4 B = 20 B; MODE 0: 4 B.  Pixel coordinates are implicit.
