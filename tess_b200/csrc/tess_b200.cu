@@ -575,12 +575,11 @@ static int run_image(tess_ctx* c, const Geometry& q, int mode, int honor, int32_
     memset(&a, 0, sizeof(a));
     a.dens = c->dens; a.sig = c->sig; a.noise = c->noise;
     a.labels_ext = labels_ext; a.lab0 = c->lab[0]; a.lab1 = c->lab[1];
-    a.mom = c->mom; a.node = c->node; a.inv_s2 = c->inv_s2;
+    a.mom = c->mom;
     a.L = c->ql;
     a.g = q.g; a.cell_start = c->cell_start; a.cell_items = c->cell_items; a.cell_xy = c->cell_xy; a.cell_inv = c->cell_inv;
     a.st = c->st;
     a.H = q.T.H; a.W = q.T.W; a.x0 = q.T.x0; a.y0 = q.T.y0;
-    a.k = c->k;
     a.uniform_weight = c->uniform_weight;
     a.honor = honor;
     bool vec = (q.T.W % 2 == 0);

@@ -59,8 +59,6 @@ struct TessImgArgs {
     int32_t* lab0;
     int32_t* lab1;
     double* mom;           // [k][M] global moment table (M = 4 or 6)
-    const double* node;    // [k][2]
-    const double* inv_s2;  // [k] or null
     TessQLists L;          // per-quadrant candidate lists
     TessGrid g;            // generator grid (ring-search fallback of overflowed tiles)
     const int* cell_start;
@@ -70,7 +68,6 @@ struct TessImgArgs {
     TessState* st;
     long H, W;
     double x0, y0;
-    int k;
     int uniform_weight;    // MODE 2: w = 1 instead of (S/N)^2
     int honor;             // honour the convergence latch (iteration kernels) or not (segmap)
 };
