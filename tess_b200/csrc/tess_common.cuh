@@ -28,7 +28,9 @@ static long g_tess_launches = 0;   // kernels launched by the library (host-side
 
 #define TESS_TS 64            // tile edge, px
 #define TESS_CAP 512           // candidates of one tile staged in shared memory
+#ifndef TESS_LEAF_CAP
 #define TESS_LEAF_CAP 24      // candidates of one 8x8 leaf
+#endif
 #define TESS_MAIN_THREADS 64  // image main kernel: 2 independent warps per CTA
 #ifndef TESS_MAIN_MINBLOCKS
 #define TESS_MAIN_MINBLOCKS 8 // CTAs per SM the main kernel is compiled for (<= 128 registers)

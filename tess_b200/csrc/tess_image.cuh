@@ -39,9 +39,15 @@
 #include "tess_index.cuh"
 #include "tess_points.cuh"
 
+#ifndef TESS_BCAP
 #define TESS_BCAP 64        // 16x16 block list capacity
+#endif
+#ifndef TESS_BLOCK_MIN
 #define TESS_BLOCK_MIN 20   // quadrant lists longer than this get the intermediate 16x16 level
+#endif
+#ifndef TESS_LEAF_MIN
 #define TESS_LEAF_MIN 3     // parent lists up to this length are evaluated without a leaf filter
+#endif
 // quadrant list capacity of the fast path = entries of a warp's accumulator table
 #define TESS_QCAP(MODE) ((MODE) == 2 ? 96 : 128)
 #ifndef TESS_DYNAMIC
