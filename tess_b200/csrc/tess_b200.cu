@@ -252,13 +252,20 @@ extern "C" int tess_set_domain(tess_ctx* c, double x0, double y0, double x1, dou
 // a single-CTA pass (n is at most a few million in point mode)
 __global__ void __launch_bounds__(1024) k_points_bbox(const double* xy, long n, double* out) {
     __shared__ double s_v[4][32];
+    __shared__ int s_bad;
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
     double x0 = INFINITY, x1 = -INFINITY, y0 = INFINITY, y1 = -INFINITY;
+    bool bad = false;
     for (long i = threadIdx.x; i < n; i += blockDim.x) {
         double x = xy[2 * i], y = xy[2 * i + 1];
         if (isfinite(x) && isfinite(y)) {
             x0 = fmin(x0, x); x1 = fmax(x1, x); y0 = fmin(y0, y); y1 = fmax(y1, y);
+        } else {
+            bad = true;
         }
     }
+    if (bad) s_bad = 1;
     x0 = tess_warp_min(x0); y0 = tess_warp_min(y0);
     x1 = -tess_warp_min(-x1); y1 = -tess_warp_min(-y1);
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -270,7 +277,7 @@ __global__ void __launch_bounds__(1024) k_points_bbox(const double* xy, long n, 
         y0 = l < nw ? s_v[2][l] : INFINITY; y1 = l < nw ? s_v[3][l] : -INFINITY;
         x0 = tess_warp_min(x0); y0 = tess_warp_min(y0);
         x1 = -tess_warp_min(-x1); y1 = -tess_warp_min(-y1);
-        if (l == 0) { out[0] = x0; out[1] = x1; out[2] = y0; out[3] = y1; }
+        if (l == 0) { out[0] = x0; out[1] = x1; out[2] = y0; out[3] = y1; out[4] = s_bad ? 1.0 : 0.0; }
     }
 }
 
@@ -278,8 +285,10 @@ static int points_bbox(tess_ctx* c, long n, const double* xy, double* box, cudaS
     TESS_LAUNCH((k_points_bbox), 1, 1024, s, xy, n, c->scratch);
     CU_TRY(cudaGetLastError());
     double* h = (double*)(c->h_st + 1);
-    CU_TRY(cudaMemcpyAsync(h, c->scratch, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(h, c->scratch, 5 * sizeof(double), cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaStreamSynchronize(s));
+    // the reference's cKDTree.query raises ValueError("'x' must be finite") here (lloyd.pyx:55)
+    if (h[4] != 0.0) return tess_fail(TESS_ERR_NONFINITE, "point coordinates must be finite (NaN or Inf found)");
     memcpy(box, h, 4 * sizeof(double));
     if (!(box[0] <= box[1]) || !(box[2] <= box[3])) { box[0] = box[2] = 0.0; box[1] = box[3] = 1.0; }
     return TESS_OK;

@@ -73,6 +73,24 @@ def lloyd(xy, w, node_xy, max_iters, verbose=False, device=None, engine=None):
     _check_f64("xy", xy, 2)
     _check_f64("w", w, 1)
     _check_f64("node_xy", node_xy, 2)
+    n, k = int(xy.shape[0]), int(node_xy.shape[0])
+    if k == 0:
+        raise ValueError("Invalid shape in axis 0: 0.")            # the reference's memoryview error
+    if int(xy.shape[1]) != 2 or int(node_xy.shape[1]) != 2:
+        raise ValueError("x must consist of vectors of length 2 but has shape %s"
+                         % (tuple(xy.shape) if int(xy.shape[1]) != 2 else tuple(node_xy.shape),))
+    # the reference indexes w[i] for i < n (lloyd.pyx:63): a longer w is read partially, a shorter
+    # one is an IndexError from its bounds check
+    if int(w.shape[0]) < n:
+        raise IndexError("Out of bounds on buffer access (axis 0)")
+    if int(w.shape[0]) > n:
+        w = w[:n]
+    if n == 0:
+        # no points: every bin is empty, nodes go to (0, 0) (lloyd.pyx:71-74) and the second
+        # iteration finds delta == 0 (lloyd.pyx:85-86); nothing to compute
+        if as_torch:
+            return xy.new_zeros((k, 2)), xy.new_zeros((0,), dtype=xy.long().dtype), True
+        return np.zeros((k, 2)), np.zeros((0,), dtype=np.int64), True
     eng = engine if engine is not None else shared_engine(device if device is not None else
                                                           (xy.device if as_torch else None))
     eng.set_points(xy, w)

@@ -225,3 +225,29 @@ def test_every_pixel_its_own_generator_and_dense_scaled(eng):
     eng.set_generators(node, scale=scale)
     eng.accumulate()
     assert np.array_equal(eng.labels(), O.c_assign_grid(H, W, node, scale=scale))
+
+
+def test_lloyd_edge_cases_follow_the_reference(eng):
+    """Probed on the compiled reference (oracle/_ref): n = 0 returns zero nodes and converged; a
+    longer w is read partially, a shorter one is an IndexError; k = 0, wrong widths, wrong dtypes and
+    non-finite point coordinates are ValueErrors (typed memoryviews / cKDTree)."""
+    from tess_b200.lloyd import lloyd
+    g = np.array([[1., 2.], [3., 4.]])
+    n, i, c = lloyd(np.empty((0, 2)), np.empty(0), g, 10, engine=eng)
+    assert np.array_equal(n, np.zeros((2, 2))) and i.shape == (0,) and i.dtype == np.int64 and c is True
+    xy = np.random.default_rng(0).uniform(0, 5, (10, 2))
+    with pytest.raises(IndexError):
+        lloyd(xy, np.ones(5), g, 10, engine=eng)
+    a = lloyd(xy, np.ones(15), g, 10, engine=eng)
+    b = O.c_lloyd(xy, np.ones(10), g, 10)
+    np.testing.assert_allclose(a[0], b[0], atol=1e-12)
+    assert np.array_equal(a[1], b[1]) and a[2] == b[2]
+    for bad in ((xy, np.ones(10), np.empty((0, 2))), (np.zeros((10, 3)), np.ones(10), g),
+                (xy, np.ones(10), np.zeros((2, 3))), (np.full((3, 2), np.nan), np.ones(3), g),
+                (xy, np.ones(10, dtype=int), g)):
+        with pytest.raises(ValueError):
+            lloyd(*bad, 10, engine=eng)
+    from tess_b200.voronoi import VoronoiTessellation
+    vt = VoronoiTessellation(g, engine=eng)
+    with pytest.raises(ValueError):                      # scipy's KDTree.query: 'x' must be finite
+        vt.partition_points(np.array([[0.5, np.inf]]))

@@ -518,3 +518,20 @@ def test_randomised_parity_short():
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " 0 failures" in r.stdout
+
+
+def test_nonfinite_points_raise_like_ckdtree(eng):
+    """lloyd.pyx:55 / voronoi.py:171-172: cKDTree.query raises ValueError("'x' must be finite")."""
+    from tess_b200.lloyd import lloyd
+    from tess_b200.voronoi import VoronoiTessellation
+    g = np.array([[1., 2.], [3., 4.]])
+    xy = np.random.default_rng(0).uniform(0, 5, (1000, 2))
+    xy[417, 1] = np.nan
+    with pytest.raises(ValueError):
+        lloyd(xy, np.ones(1000), g, 10, engine=eng)
+    vt = VoronoiTessellation(g, engine=eng)
+    with pytest.raises(ValueError):
+        vt.partition_points(np.array([[0.5, np.inf], [1.0, 1.0]]))
+    assert np.array_equal(vt.partition_points(np.array([[0.5, 2.0], [3.1, 4.2]])), [0, 1])
+    n, i, c = lloyd(np.empty((0, 2)), np.empty(0), g, 10, engine=eng)
+    assert np.array_equal(n, np.zeros((2, 2))) and i.shape == (0,) and c is True
