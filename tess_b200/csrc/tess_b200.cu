@@ -62,6 +62,8 @@ struct tess_ctx {
     long n_pts;
     const double *pts_xy, *pts_w;
     double pb[4];   // bounding box of the points (x0, x1, y0, y1)
+    double gb[4];   // bounding box of the generator table at tess_set_generators
+    int gb_valid;
     int has_domain;
     double dom[4];  // generator domain (x0, y0, x1, y1)
     // ---- generators (owned)
@@ -281,14 +283,15 @@ __global__ void __launch_bounds__(1024) k_points_bbox(const double* xy, long n, 
     }
 }
 
-static int points_bbox(tess_ctx* c, long n, const double* xy, double* box, cudaStream_t s) {
+static int points_bbox(tess_ctx* c, long n, const double* xy, double* box, cudaStream_t s, bool must_be_finite = true) {
     TESS_LAUNCH((k_points_bbox), 1, 1024, s, xy, n, c->scratch);
     CU_TRY(cudaGetLastError());
     double* h = (double*)(c->h_st + 1);
     CU_TRY(cudaMemcpyAsync(h, c->scratch, 5 * sizeof(double), cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaStreamSynchronize(s));
     // the reference's cKDTree.query raises ValueError("'x' must be finite") here (lloyd.pyx:55)
-    if (h[4] != 0.0) return tess_fail(TESS_ERR_NONFINITE, "point coordinates must be finite (NaN or Inf found)");
+    if (must_be_finite && h[4] != 0.0)
+        return tess_fail(TESS_ERR_NONFINITE, "point coordinates must be finite (NaN or Inf found)");
     memcpy(box, h, 4 * sizeof(double));
     if (!(box[0] <= box[1]) || !(box[2] <= box[3])) { box[0] = box[2] = 0.0; box[1] = box[3] = 1.0; }
     return TESS_OK;
@@ -330,6 +333,7 @@ extern "C" int tess_set_generators(tess_ctx* c, long k, const double* node_xy, c
     }
     c->k = (int)k;
     c->cell_shift = -1;
+    c->gb_valid = 0;
     // WVT scale updates need a scale table: start from unit scales when none is given
     c->has_scale = (scale || c->wvt_update) ? 1 : 0;
     const int nb = (int)((k + 255) / 256);
@@ -383,22 +387,46 @@ static Geometry window_geometry(const tess_ctx* c, double x0, double y0, long H,
     return q;
 }
 
-// Grid for a point query: covers the box, about 0.75 generators per cell on average (point sets are
-// rarely uniform: the dense cells then stay short, empty ones cost two index loads per ring row).
-static Geometry box_geometry(const double* box, int k) {
+// Grid for a point query.  It covers the part of the plane where both the query points and the
+// generators are (the intersection of the two bounding boxes; the generators' box if they do not
+// overlap), with about 0.75 generators per cell on average (point sets are rarely uniform: the dense
+// cells then stay short, empty ones cost two index loads per ring row).  Whatever lies outside --
+// query points or generators -- is clamped into the border cells; the ring bound stays exact because
+// clamping to a box is non-expansive.  Degenerate boxes (a single point, points on a line) get a
+// one-cell-wide grid in the flat direction instead of absurdly thin cells.
+static Geometry box_geometry(const tess_ctx* c, const double* pbox) {
     Geometry q;
     memset(&q, 0, sizeof(q));
-    const double w = fmax(box[1] - box[0], 1e-300), h = fmax(box[3] - box[2], 1e-300);
-    double cs = sqrt(w * h / fmax((double)k / 0.75, 1.0));
-    if (!(cs > 0.0) || !isfinite(cs)) cs = fmax(w, h);
+    double b[4] = {pbox[0], pbox[1], pbox[2], pbox[3]};
+    if (c->gb_valid) {
+        const double ix0 = fmax(b[0], c->gb[0]), ix1 = fmin(b[1], c->gb[1]);
+        const double iy0 = fmax(b[2], c->gb[2]), iy1 = fmin(b[3], c->gb[3]);
+        if (ix0 <= ix1 && iy0 <= iy1) { b[0] = ix0; b[1] = ix1; b[2] = iy0; b[3] = iy1; }
+        else { b[0] = c->gb[0]; b[1] = c->gb[1]; b[2] = c->gb[2]; b[3] = c->gb[3]; }
+    }
+    const double w = fmax(b[1] - b[0], 0.0), h = fmax(b[3] - b[2], 0.0);
+    const double cells = fmax((double)c->k / 0.75, 1.0);
+    double cs;
+    if (w > 0.0 && h > 0.0) cs = sqrt(w * h / cells);
+    else if (w > 0.0 || h > 0.0) cs = fmax(w, h) / fmin(cells, 4096.0);
+    else cs = 1.0;
+    if (!(cs > 0.0) || !isfinite(cs)) cs = 1.0;
     cs = fmax(cs, fmax(w, h) / 4096.0);
-    int gw = (int)fmin(floor(w / cs) + 1.0, 4097.0), gh = (int)fmin(floor(h / cs) + 1.0, 4097.0);
-    q.g.ox = box[0]; q.g.oy = box[2]; q.g.cs = cs; q.g.inv_cs = 1.0 / cs;
+    const int gw = (int)fmin(floor(w / cs) + 1.0, 4097.0), gh = (int)fmin(floor(h / cs) + 1.0, 4097.0);
+    q.g.ox = b[0]; q.g.oy = b[2]; q.g.cs = cs; q.g.inv_cs = 1.0 / cs;
     q.g.gw = gw < 1 ? 1 : gw; q.g.gh = gh < 1 ? 1 : gh;
-    const double ext = fmax(fmax(fabs(box[0]), fabs(box[1])), fmax(fabs(box[2]), fabs(box[3]))) + cs;
+    const double ext = fmax(fmax(fabs(b[0]), fabs(b[1])), fmax(fabs(b[2]), fabs(b[3]))) + cs;
     q.g.tol = ext * 9.094947017729282e-13;
     q.n_cells = q.g.gw * q.g.gh;
     return q;
+}
+
+// bounding box of the generator table (point-set mode only; once per tess_set_generators)
+static int generator_bbox(tess_ctx* c, cudaStream_t s) {
+    if (c->gb_valid) return TESS_OK;
+    TRY(points_bbox(c, c->k, c->node, c->gb, s, false));
+    c->gb_valid = 1;
+    return TESS_OK;
 }
 
 static int ensure_cells(tess_ctx* c, int n_cells) {
@@ -719,7 +747,8 @@ extern "C" int tess_lloyd_accumulate(tess_ctx* c, void* stream) {
         timing_mark(c, s, 1);
         n = c->H * c->W;
     } else {
-        Geometry q = box_geometry(c->pb, c->k);
+        TRY(generator_bbox(c, s));
+        Geometry q = box_geometry(c, c->pb);
         TRY(build_index(c, q, 1, c->mom, n_mom, s));
         timing_mark(c, s, 0);
         TRY(run_points(c, q, 1, 1, c->n_pts, c->pts_xy, c->pts_w, nullptr, s));
@@ -954,7 +983,8 @@ extern "C" int tess_assign_points(tess_ctx* c, long m, const double* xy, int32_t
     cudaStream_t s = S(stream);
     double box[4];
     TRY(points_bbox(c, m, xy, box, s));
-    Geometry q = box_geometry(box, c->k);
+    TRY(generator_bbox(c, s));
+    Geometry q = box_geometry(c, box);
     TRY(build_index(c, q, 0, nullptr, 0, s));
     TRY(run_points(c, q, 0, 0, m, xy, nullptr, out, s));
     return TESS_OK;

@@ -251,3 +251,42 @@ def test_lloyd_edge_cases_follow_the_reference(eng):
     vt = VoronoiTessellation(g, engine=eng)
     with pytest.raises(ValueError):                      # scipy's KDTree.query: 'x' must be finite
         vt.partition_points(np.array([[0.5, np.inf]]))
+
+
+def test_degenerate_point_sets(eng):
+    """Point-query grids for degenerate geometry: points on a line, a single point, generators far
+    from the points (disjoint bounding boxes), one far outlier generator.  The grid covers the overlap
+    of the two bounding boxes and everything else is clamped into border cells (exact)."""
+    from tess_b200.lloyd import lloyd
+    from tess_b200.voronoi import VoronoiTessellation
+    rng = np.random.default_rng(9)
+
+    def brute(pts, g):
+        d = (pts[:, None, 0] - g[None, :, 0]) ** 2 + (pts[:, None, 1] - g[None, :, 1]) ** 2
+        return d.argmin(axis=1)
+
+    g = rng.uniform(0, 100, (200, 2))
+    cases = {
+        "vertical line": np.column_stack((np.full(300, 37.25), rng.uniform(-20, 120, 300))),
+        "horizontal line": np.column_stack((rng.uniform(0, 100, 300), np.full(300, 1e-3))),
+        "single point": np.array([[50.5, 49.5]]),
+        "identical points": np.tile([[10.0, 90.0]], (50, 1)),
+        "disjoint boxes": rng.uniform(1000, 1100, (300, 2)),
+        "points around": rng.uniform(-500, 600, (300, 2)),
+    }
+    vt = VoronoiTessellation(g, engine=eng)
+    for name, pts in cases.items():
+        assert np.array_equal(vt.partition_points(pts), brute(pts, g)), name
+    g2 = g.copy()
+    g2[0] = [1e7, -3e6]                                   # one far outlier generator
+    vt2 = VoronoiTessellation(g2, engine=eng)
+    pts = rng.uniform(0, 100, (400, 2))
+    assert np.array_equal(vt2.partition_points(pts), brute(pts, g2))
+    # and a Lloyd run on a line of points (the reference's kd-tree has no trouble with it)
+    pts = cases["vertical line"]
+    w = rng.uniform(0.5, 1.0, 300)
+    seeds = pts[rng.choice(300, 12, replace=False)] + rng.uniform(-0.1, 0.1, (12, 2))
+    n, i, c = lloyd(pts, w, seeds, 20, engine=eng)
+    rn, ri, rc = O.c_lloyd(pts, w, seeds, 20)[:3]
+    assert np.array_equal(i, ri) and c == rc
+    np.testing.assert_allclose(n, rn, rtol=0, atol=1e-9)
