@@ -601,6 +601,7 @@ TESS_DEVFN void tess_quadrant_body(const TessImgArgs& a, TessWarpSmem<MODE, HAS_
                 for (int c = 0; c < 2; ++c) { bd[r][c] = INFINITY; bs[r][c] = 0; }
             const int n_ev = use_leaf ? len : p_len;
             bool tied = false;
+#pragma unroll 1     // the compiler's own 2x unrolling costs 1.3 % (instruction cache)
             for (int j = 0; j < n_ev; ++j) {
                 double2 g;
                 int e;
@@ -635,6 +636,7 @@ TESS_DEVFN void tess_quadrant_body(const TessImgArgs& a, TessWarpSmem<MODE, HAS_
                 for (int r = 0; r < 4; ++r)
 #pragma unroll
                     for (int c = 0; c < 2; ++c) { bd[r][c] = INFINITY; bs[r][c] = 0; bg[r][c] = 0x7fffffff; }
+#pragma unroll 1
                 for (int j = 0; j < n_ev; ++j) {
                     int e;
                     if (use_leaf) e = ls[j];
