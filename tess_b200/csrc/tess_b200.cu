@@ -589,7 +589,8 @@ static void launch_image(tess_ctx* c, const TessImgArgs& a, bool vec, long want,
 #define TESS_GO(KERN)                                                   \
     do {                                                                \
         long g_ = resident_ctas(c, KERN);                               \
-        if (g_ > want) g_ = want;                                       \
+        /* one warp per quadrant, but the tail phase has 32 / TESS_RING_ROWS strips per queued quadrant */ \
+        if (g_ > want * (32 / TESS_RING_ROWS)) g_ = want * (32 / TESS_RING_ROWS); \
         if (g_ < 1) g_ = 1;                                             \
         TESS_LAUNCH((KERN), (int)g_, TESS_MAIN_THREADS, s, a, vec ? 1 : 0); \
     } while (0)
