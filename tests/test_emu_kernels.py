@@ -290,3 +290,36 @@ def test_degenerate_point_sets(eng):
     rn, ri, rc = O.c_lloyd(pts, w, seeds, 20)[:3]
     assert np.array_equal(i, ri) and c == rc
     np.testing.assert_allclose(n, rn, rtol=0, atol=1e-9)
+
+
+def test_randomised_small_maps_against_the_oracle(eng):
+    """The CPU twin of tools/fuzz_parity.py at emulator sizes: random shapes, window origins, bin sizes
+    from thousands of pixels down to one, ties, duplicates, scales, all kernel modes -- labels
+    bit-exact and moments to 1e-12 against the oracle."""
+    rng = np.random.default_rng(17)
+    for case in range(14):
+        H, W = int(rng.integers(1, 90)), int(rng.integers(1, 90))
+        x0, y0 = (float(rng.uniform(-20, 20)), float(rng.uniform(-20, 20))) if case % 2 else (0.0, 0.0)
+        area = float(np.exp(rng.uniform(np.log(0.8), np.log(3000.0))))
+        k = int(min(max(1, H * W / area), 4000))
+        g = np.column_stack((rng.uniform(x0 - 5, x0 + W + 5, k), rng.uniform(y0 - 5, y0 + H + 5, k)))
+        if case % 3 == 0:
+            m = max(1, k // 8)
+            g[:m] = np.round(g[:m] - [x0, y0]) + [x0, y0]      # on pixel centres: exact ties
+        if k > 3:
+            g[k // 2] = g[1]
+        scale = rng.uniform(0.6, 1.7, k) if case % 4 == 1 else None
+        w = rng.uniform(0.5, 1.5, (H, W))
+        if case % 5 == 2:
+            w[rng.integers(0, H), rng.integers(0, W)] = np.nan
+        x, y = np.meshgrid(x0 + np.arange(W, dtype=float), y0 + np.arange(H, dtype=float))
+        pts = np.column_stack((x.ravel(), y.ravel()))
+        ref = O.c_assign_points(pts, g, scale=scale).reshape(H, W)
+        eng.set_image(density=w, x0=x0, y0=y0)
+        eng.set_generators(g, scale=scale)
+        assert np.array_equal(eng.assign_grid(x0, y0, H, W), ref), (case, H, W, k)
+        eng.accumulate()
+        assert np.array_equal(eng.labels(), ref), (case, H, W, k)
+        good = np.isfinite(w).ravel()
+        rm = O.np_moments(pts[good], w.ravel()[good], ref.ravel()[good], k)
+        np.testing.assert_allclose(eng.moments()[:, :4], rm[:, :4], rtol=1e-12, atol=1e-12, err_msg=str((case, H, W, k)))
