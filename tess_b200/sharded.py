@@ -75,7 +75,7 @@ class ShardedLloyd(object):
         self._view = None
         self._want = os.environ.get("TESS_EXCHANGE", exchange)
         self._peer = None
-        self.exchange = "nccl all_reduce" if self._want == "nccl" else "undecided"
+        self.exchange = "backend all_reduce (NCCL on GPUs)" if self._want == "nccl" else "undecided"
 
     # ------------------------------------------------------------------ inputs
     def set_image_rows(self, density=None, signal=None, noise=None, row0=0, x0=0.0, y0=0.0, total_rows=None):
@@ -138,7 +138,7 @@ class ShardedLloyd(object):
                 self._view = None
             if self._want == "peer":
                 raise
-            self.exchange = "nccl all_reduce (symmetric memory unavailable: %s)" % (str(e).splitlines()[0][:120] if str(e) else type(e).__name__)
+            self.exchange = "backend all_reduce (symmetric memory unavailable: %s)" % (str(e).splitlines()[0][:120] if str(e) else type(e).__name__)
 
     # ------------------------------------------------------------------ iteration
     def _moments(self):
