@@ -100,16 +100,23 @@ class ShardedLloyd(object):
         need = 6 * self.eng.k + 2
         if self._peer is not None and self._peer["n"] >= need:
             return
-        self._peer = None
+        if self._peer is not None:          # outgrown: back to a library-owned vector until replaced
+            self.eng.set_moment_buffer(None, 0)
+            self._peer = None
+            self._view = None
+        import ctypes
+        import os
+        gen = self.eng.generators()
+        if self.world < 2 or self.world > 16 or not isinstance(gen, self.torch.Tensor):
+            # the same on every rank (CPU tests with NumPy memory, a lone rank): no agreement needed
+            why = "engine memory is not CUDA" if self.world >= 2 else "world size %d" % self.world
+            if self._want == "peer":
+                raise RuntimeError("peer exchange unavailable: " + why)
+            self.exchange = "backend all_reduce (symmetric memory unavailable: %s)" % why
+            return
+        dev, err, peer = gen.device, None, None
         try:
-            import ctypes
-            import os
-            if self.world < 2 or self.world > 16:
-                raise RuntimeError("world size %d" % self.world)
-            if not isinstance(self.eng.generators(), self.torch.Tensor):
-                raise RuntimeError("engine memory is not CUDA")
             import torch.distributed._symmetric_memory as symm
-            dev = self.eng.generators().device
             buf = symm.empty(need, dtype=self.torch.float64, device=dev)
             buf.zero_()
             grp = self.group if self.group is not None else self.dist.group.WORLD
@@ -122,23 +129,24 @@ class ShardedLloyd(object):
             force = os.environ.get("TESS_PEER_NO_MC", "")
             if force == "1" or (force != "0" and self.world < 8):
                 mc = 0
-            self.eng.set_moment_buffer(buf, need)
-            self._peer = dict(buf=buf, hdl=hdl, ptrs=ptrs, mc=mc, n=need)
-            # all ranks or none: the exchange is collective
-            ok = self.torch.ones(1, dtype=self.torch.int32, device=dev)
-            self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN, group=self.group)
-            if int(ok.item()) != 1:
-                raise RuntimeError("a peer rank could not set up symmetric memory")
-            self.exchange = ("own kernel, NVLS multicast reduction (multimem.ld_reduce/st)" if mc
+            peer = dict(buf=buf, hdl=hdl, ptrs=ptrs, mc=mc, n=need)
+        except Exception as e:      # no symmetric memory on this rank (driver / fabric support missing)
+            err = str(e).splitlines()[0][:120] if str(e) else type(e).__name__
+        # all ranks or none -- the exchange is collective, so every rank takes part in this vote
+        # whatever happened above
+        ok = self.torch.tensor([1 if peer is not None else 0], dtype=self.torch.int32, device=dev)
+        self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 1:
+            self.eng.set_moment_buffer(peer["buf"], need)
+            self._peer = peer
+            self._view = None
+            self.exchange = ("own kernel, NVLS multicast reduction (multimem.ld_reduce/st)" if peer["mc"]
                              else "own kernel, two-shot over NVLink peer memory")
-        except Exception as e:      # no symmetric memory here (CPU tests, single GPU, missing driver support)
-            if self._peer is not None:
-                self.eng.set_moment_buffer(None, 0)
-                self._peer = None
-                self._view = None
-            if self._want == "peer":
-                raise
-            self.exchange = "backend all_reduce (symmetric memory unavailable: %s)" % (str(e).splitlines()[0][:120] if str(e) else type(e).__name__)
+            return
+        err = err or "a peer rank could not set up symmetric memory"
+        if self._want == "peer":
+            raise RuntimeError("peer exchange unavailable: " + err)
+        self.exchange = "backend all_reduce (symmetric memory unavailable: %s)" % err
 
     # ------------------------------------------------------------------ iteration
     def _moments(self):
