@@ -1,4 +1,4 @@
-"""examples/demo_iso_sn_voronoi.py -- the reference's scripts/demo_iso_sn_voronoi.py (config C1) with
+"""examples/c1_equal_sn_cvt.py -- what the reference's scripts/demo_iso_sn_voronoi.py does (config C1), with
 `tess` replaced by `tess_b200`: the 256^2 Gaussian image with constant noise (:20-26), generators
 from the equal-S/N accretor, `CVTessellation.from_image(pix_sn ** 2, generators)` (:38) -- the same
 call, now on the GPU -- and the two segmentation maps written as FITS instead of matplotlib figures
@@ -8,7 +8,7 @@ The accretor (`EqualSNAccretor(img, noise, 50., start=(0, 0))`, :29-31) is a seq
 generator and out of scope; its 271 centroids for exactly these inputs are in
 tests/golden/lloyd_demo256.npz, made by running the reference itself (tests/golden/make_golden.py).
 
-    python examples/demo_iso_sn_voronoi.py [outdir]
+    python examples/c1_equal_sn_cvt.py [outdir]
 """
 import os
 import sys
@@ -23,12 +23,14 @@ from tess_b200.voronoi import CVTessellation       # noqa: E402
 
 
 def main(out="."):
-    shape = (256, 256)
-    pix_x, pix_y = np.meshgrid(np.arange(shape[1], dtype=float), np.arange(shape[0], dtype=float))
-    img = 10. * np.exp(-((pix_x - 128.) ** 2. / (2. * 50. ** 2.) + (pix_y - 128.) ** 2. / (2. * 50. ** 2.)))
-    noise = np.ones(shape, dtype=float)
+    n, sigma, amplitude = 256, 50.0, 10.0
+    col, row = np.meshgrid(np.arange(n, dtype=np.float64), np.arange(n, dtype=np.float64))
+    r2 = (col - n / 2) ** 2 + (row - n / 2) ** 2
+    img = amplitude * np.exp(-r2 / (2.0 * sigma ** 2))          # the script's 2-D Gaussian, :24-25
+    noise = np.ones_like(img)                                   # constant noise, :26
     pix_sn = img / noise
-    generator_centroids = np.load(os.path.join(ROOT, "tests", "golden", "lloyd_demo256.npz"))["seeds"]
+    fixture = np.load(os.path.join(ROOT, "tests", "golden", "lloyd_demo256.npz"))
+    generator_centroids = fixture["seeds"]                      # EqualSNAccretor(img, noise, 50.) centroids
 
     cvt = CVTessellation.from_image(pix_sn ** 2., generator_centroids)
     cvt_xy = cvt.nodes
