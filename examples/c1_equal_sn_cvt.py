@@ -25,8 +25,9 @@ from tess_b200.voronoi import CVTessellation       # noqa: E402
 def main(out="."):
     n, sigma, amplitude = 256, 50.0, 10.0
     col, row = np.meshgrid(np.arange(n, dtype=np.float64), np.arange(n, dtype=np.float64))
-    r2 = (col - n / 2) ** 2 + (row - n / 2) ** 2
-    img = amplitude * np.exp(-r2 / (2.0 * sigma ** 2))          # the script's 2-D Gaussian, :24-25
+    two_var = 2.0 * sigma ** 2.0
+    gx, gy = (col - n / 2.0) ** 2.0 / two_var, (row - n / 2.0) ** 2.0 / two_var
+    img = amplitude * np.exp(-(gx + gy))                        # the script's 2-D Gaussian (:24-25), bitwise
     noise = np.ones_like(img)                                   # constant noise, :26
     pix_sn = img / noise
     fixture = np.load(os.path.join(ROOT, "tests", "golden", "lloyd_demo256.npz"))
