@@ -28,12 +28,12 @@ def _np(a):
 
 
 class VoronoiTessellation(object):
-    """A Voronoi Tessellation, defined by a set of nodes on a 2D plane.
+    """Voronoi tessellation of the plane given by its nodes (generators); GPU-backed.
 
     Parameters
     ----------
-    xy : ndarray, (n_nodes, 2)
-        Array of node ``(x,y)`` coordinates.
+    xy : (n_nodes, 2) float64 array, NumPy or torch CUDA
+        ``(x, y)`` of every node.
     """
     def __init__(self, xy, device=None, engine=None):
         super(VoronoiTessellation, self).__init__()
@@ -69,7 +69,7 @@ class VoronoiTessellation(object):
     # -- reference surface -----------------------------------------------------------------
     @property
     def nodes(self):
-        """Voronoi tessellation nodes, a ``(n_points, 2)`` array."""
+        """The ``(n_nodes, 2)`` node coordinates."""
         return self._xy
 
     def set_pixel_grid(self, xlim, ylim):
@@ -78,7 +78,7 @@ class VoronoiTessellation(object):
         assert len(ylim) == 2, "ylim must be (min, max) sequence"
         self.xlim = xlim
         self.ylim = ylim
-        # Reset dependencies
+        # cached products depend on the grid
         self._segmap = None
         self._cell_areas = None
 
@@ -165,7 +165,7 @@ class CVTessellation(VoronoiTessellation):
     node_xy : ndarray ``(n_nodes, 2)``
         Pre-computed generators; ``None`` makes every point its own generator (voronoi.py:298-299).
     max_iters : int
-        Maximum number of iterations of Lloyd's algorithm.
+        Iteration budget of the Lloyd loop (the reference runs at most max_iters + 2 bodies).
     """
     def __init__(self, xy_points, dens_points, node_xy=None, max_iters=300, device=None, engine=None):
         self._device = device
@@ -228,7 +228,7 @@ class CVTessellation(VoronoiTessellation):
             xy, densPoints = np.asarray(xy), np.asarray(densPoints)
         _check_f64("xy", xy, 2)
         _check_f64("dens_points", densPoints, 1)
-        # Obtain pre-generator node coordinates
+        # default generators: every point its own node (reference voronoi.py:298-299)
         if node_xy is None:
             node_xy = xy.clone() if self._torch_out else xy.copy()
         eng = self._new_engine(xy)
@@ -238,7 +238,7 @@ class CVTessellation(VoronoiTessellation):
 
     @property
     def membership(self):
-        """Array of indices into Voronoi bins for each point."""
+        """Bin index of every (finite-density) point, int64."""
         return self._vbin_num
 
     @property
