@@ -112,8 +112,9 @@ int tess_set_domain(tess_ctx* ctx, double x0, double y0, double x1, double y1);
 
 /*
  * Point mode -- the `xy`, `w` arguments of lloyd() (reference tess/lloyd.pyx:10-11):
- * xy is AoS [n][2], w is [n].  Points are binned once into spatial tiles (a sorted copy is
- * kept in the context's workspace); labels are returned in the caller's point order.
+ * xy is AoS [n][2], w is [n], both BORROWED for as long as they are set (no copy is made); the
+ * call computes their bounding box (one pass, one host synchronisation).  Labels are returned in
+ * the caller's point order.
  */
 int tess_set_points(tess_ctx* ctx, long n, const double* xy, const double* w, void* stream);
 

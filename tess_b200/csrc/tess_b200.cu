@@ -3,7 +3,7 @@
 //
 // One Lloyd iteration (reference tess/lloyd.pyx:47-90) is the launch sequence
 //   k_cell_count -> k_cell_blocksum -> k_cell_scan -> k_cell_scatter   generator grid (replaces cKDTree build, :54)
-//   k_build_qlists                                       per-quadrant candidate lists (sorted, in an arena)
+//   k_build_qlists                                       per-quadrant candidate lists (arena records, any order)
 //   k_image_main | k_points_main                         assignment (:55) fused with the sums (:58-65)
 //   k_count_prefilter -> k_compare_labels                "did any label change" (convergence, :85)
 //   [multi-GPU: the host all-reduces the moment vector here]

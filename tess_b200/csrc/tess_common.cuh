@@ -74,7 +74,7 @@ struct TessState {
     unsigned spare_;                 // quadrant queue of k_image_main (edge instantiation)
     unsigned update_ran;             // k_update_nodes did work this iteration (read by k_update_finish)
     int last_parity;                 // label buffer (0/1) written by the most recent accumulate
-    int pad_;
+    int flags_next;                  // flags raised by k_update_nodes; k_update_finish folds them into `flags`
 };
 #define TESS_FLAG_NONFINITE 1
 // iteration kernels are no-ops once the latch closed or an error flag is up (unless forced)

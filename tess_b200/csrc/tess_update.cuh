@@ -115,7 +115,9 @@ k_update_nodes(TessState* st, int honor, const double* mom, const double* mom_ta
                 nx = __ddiv_rn(m23.x, m01.y);
                 ny = __ddiv_rn(m23.y, m01.y);
             }
-            if (!(isfinite(nx) && isfinite(ny))) atomicOr(&st->flags, TESS_FLAG_NONFINITE);
+            // raised into flags_next, not flags: CTAs that start later still test the entry condition
+            // against the flags of the previous kernel, so every node is rewritten (lloyd.pyx:66-74)
+            if (!(isfinite(nx) && isfinite(ny))) atomicOr(&st->flags_next, TESS_FLAG_NONFINITE);
             const double dx = __dsub_rn(old.x, nx), dy = __dsub_rn(old.y, ny);
             d = __dadd_rn(d, __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
             *np = make_double2(nx, ny);
@@ -177,6 +179,8 @@ k_update_finish(TessState* st, const double* mom_tail, const double* delta_part,
         st->iters_done += 1;
         st->have_prev = 1;
         st->update_ran = 0u;
+        st->flags |= st->flags_next;
+        st->flags_next = 0;
     }
 }
 

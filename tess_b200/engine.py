@@ -39,7 +39,11 @@ class Engine(object):
         self.api = get_api()
         if device is None:
             device = torch.cuda.current_device()
-        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        if not isinstance(device, int):
+            device = torch.device(device).index          # 'cuda' / index-less: the current device, not GPU 0
+            if device is None:
+                device = torch.cuda.current_device()
+        self.device = torch.device("cuda", device)
         torch.cuda.init()
         with torch.cuda.device(self.device):
             torch.empty(1, device=self.device)          # make sure the primary context exists
@@ -48,6 +52,9 @@ class Engine(object):
 
     def _init_common(self):
         self._keep = {}
+        # whose generator table the context holds (several tessellation objects may share one Engine):
+        # reset by every call that rewrites the table, claimed by the object that uploaded it
+        self.gen_owner = None
         self.shape = None
         self.n = 0
         self.k = 0
@@ -150,6 +157,7 @@ class Engine(object):
         if sc is not None and (sc.ndim != 1 or sc.shape[0] != node.shape[0]):
             raise ValueError("set_generators: scale must be (k,)")
         self.k = int(node.shape[0])
+        self.gen_owner = None
         self.api.call("tess_set_generators", self.ctx, self.k, self._ptr(node), self._ptr(sc), self._stream())
 
     # ------------------------------------------------------------------ iteration
@@ -157,13 +165,16 @@ class Engine(object):
         self.api.call("tess_lloyd_accumulate", self.ctx, self._stream())
 
     def update(self):
+        self.gen_owner = None
         self.api.call("tess_lloyd_update", self.ctx, self._stream())
 
     def step(self, n=1):
+        self.gen_owner = None
         self.api.call("tess_lloyd_step", self.ctx, int(n), self._stream())
 
     def run(self, max_iters):
         """Reference loop and stop rule (tess/lloyd.pyx:47-90).  Returns (converged, n_iters)."""
+        self.gen_owner = None
         return self.api.lloyd_run(self.ctx, int(max_iters), self._stream())
 
     def set_moment_buffer(self, t, n_doubles):

@@ -41,7 +41,9 @@ def _check_f64(name, a, ndim):
 def shared_engine(device=None):
     """One cached Engine per device: repeated lloyd() calls reuse its workspace."""
     import torch
-    idx = torch.cuda.current_device() if device is None else torch.device(device).index or 0
+    idx = None if device is None else torch.device(device).index
+    if idx is None:                      # 'cuda' / an index-less tensor device: the current device, not GPU 0
+        idx = torch.cuda.current_device()
     eng = _ENGINES.get(idx)
     if eng is None or eng.ctx is None:
         eng = _ENGINES[idx] = Engine(idx)

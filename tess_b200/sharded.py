@@ -115,24 +115,36 @@ class ShardedLloyd(object):
             self.exchange = "backend all_reduce (symmetric memory unavailable: %s)" % why
             return
         dev, err, peer = gen.device, None, None
+        symm = buf = None
         try:
             import torch.distributed._symmetric_memory as symm
             buf = symm.empty(need, dtype=self.torch.float64, device=dev)
             buf.zero_()
-            grp = self.group if self.group is not None else self.dist.group.WORLD
-            hdl = symm.rendezvous(buf, grp)
-            ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs])
-            mc = int(hdl.multicast_ptr) if getattr(hdl, "has_multicast_support", False) and hdl.multicast_ptr else 0
-            # fp64 multimem operations are 8 bytes each (no vector form): measured 126 us per 32 MB
-            # exchange at 8 GPUs against 141 us for the two-shot kernel and 147 us for NCCL, but
-            # 128 us against 83 / 80 us at 2 GPUs -- the switch reduction pays from 8 ranks on
-            force = os.environ.get("TESS_PEER_NO_MC", "")
-            if force == "1" or (force != "0" and self.world < 8):
-                mc = 0
-            peer = dict(buf=buf, hdl=hdl, ptrs=ptrs, mc=mc, n=need)
         except Exception as e:      # no symmetric memory on this rank (driver / fabric support missing)
             err = str(e).splitlines()[0][:120] if str(e) else type(e).__name__
-        # all ranks or none -- the exchange is collective, so every rank takes part in this vote
+            buf = None
+        # first vote: the rendezvous below is itself collective, so it is entered only when every
+        # rank got its allocation (a rank that failed above would otherwise leave its peers waiting)
+        ok = self.torch.tensor([1 if buf is not None else 0], dtype=self.torch.int32, device=dev)
+        self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 1:
+            try:
+                grp = self.group if self.group is not None else self.dist.group.WORLD
+                hdl = symm.rendezvous(buf, grp)
+                ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs])
+                mc = int(hdl.multicast_ptr) if getattr(hdl, "has_multicast_support", False) and hdl.multicast_ptr else 0
+                # fp64 multimem operations are 8 bytes each (no vector form): measured 126 us per 32 MB
+                # exchange at 8 GPUs against 141 us for the two-shot kernel and 147 us for NCCL, but
+                # 128 us against 83 / 80 us at 2 GPUs -- the switch reduction pays from 8 ranks on
+                force = os.environ.get("TESS_PEER_NO_MC", "")
+                if force == "1" or (force != "0" and self.world < 8):
+                    mc = 0
+                peer = dict(buf=buf, hdl=hdl, ptrs=ptrs, mc=mc, n=need)
+            except Exception as e:
+                err = str(e).splitlines()[0][:120] if str(e) else type(e).__name__
+        else:
+            err = err or "a peer rank could not allocate symmetric memory"
+        # second vote, all ranks or none: the exchange is collective, so every rank takes part in it
         # whatever happened above
         ok = self.torch.tensor([1 if peer is not None else 0], dtype=self.torch.int32, device=dev)
         self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN, group=self.group)

@@ -44,7 +44,6 @@ class VoronoiTessellation(object):
         self.ylim = None         #: ``(min, max)`` coords of y pixel grid
         self._device = device
         self._engine = engine
-        self._engine_has_nodes = False
         self._torch_out = _is_torch(xy)
 
     # -- engine plumbing -------------------------------------------------------------------
@@ -54,9 +53,11 @@ class VoronoiTessellation(object):
             if dev is None and _is_torch(self._xy) and self._xy.is_cuda:
                 dev = self._xy.device
             self._engine = Engine(dev)
-        if not self._engine_has_nodes:
+        # several objects may share one Engine (the public `engine=` argument): upload this
+        # object's table unless it is the one the context holds
+        if self._engine.gen_owner is not self:
             self._engine.set_generators(self._xy)
-            self._engine_has_nodes = True
+            self._engine.gen_owner = self
         return self._engine
 
     def _out(self, t, dtype=None):
@@ -170,11 +171,10 @@ class CVTessellation(VoronoiTessellation):
     def __init__(self, xy_points, dens_points, node_xy=None, max_iters=300, device=None, engine=None):
         self._device = device
         self._engine = engine
-        self._engine_has_nodes = True       # generators are set by _run below
         self._torch_out = _is_torch(xy_points)
         xy, vbin_num = self._tessellate(xy_points, dens_points, node_xy=node_xy, max_iters=max_iters)
         super(CVTessellation, self).__init__(xy, device=device, engine=self._engine)
-        self._engine_has_nodes = True       # the context already holds the converged generators
+        self._engine.gen_owner = self       # the context already holds the converged generators
         self._vbin_num = vbin_num
 
     def _new_engine(self, like):
@@ -193,7 +193,6 @@ class CVTessellation(VoronoiTessellation):
         self = cls.__new__(cls)
         self._device = device
         self._engine = engine
-        self._engine_has_nodes = True       # generators are set by _run below
         self._torch_out = _is_torch(density)
         if not self._torch_out:
             density = np.asarray(density)
@@ -204,7 +203,7 @@ class CVTessellation(VoronoiTessellation):
         good = eng._finite_mask(dens_dev)           # voronoi.py:285
         nodes, labels = self._run(eng, generators, max_iters)
         VoronoiTessellation.__init__(self, nodes, device=device, engine=eng)
-        self._engine_has_nodes = True
+        eng.gen_owner = self                # the context already holds the converged generators
         self._vbin_num = self._out(labels.reshape(-1)[good], "int64")
         self.densPoints = self._out(dens_dev[good])
         self.set_pixel_grid((0, density.shape[1]), (0, density.shape[0]))

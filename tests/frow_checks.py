@@ -109,3 +109,23 @@ def check_wvt_binning(make_engine, N=72, k=14):
     assert np.all(np.isfinite(wvt["scales"])) and np.all(wvt["scales"] > 0)
     assert wvt["history"][0][0] == 4 and wvt["n_iters"] <= 32
     return wvt
+
+
+def check_flagmap(vt, g):
+    """compute_cell_areas(flagmap) / cell_point_density(flagmap): pixels with flagmap > 0 are not
+    counted (docstring of tess/voronoi.py:116-152; the reference's own branch cannot run)."""
+    seg = g["segmap"]
+    rng = np.random.default_rng(31)
+    flag = (rng.uniform(size=seg.shape) < 0.3).astype(np.int64) * rng.integers(1, 4, seg.shape)
+    flag[:3] = -1                                            # negative and zero flags keep the pixel
+    keep = ~(flag > 0)
+    want = np.bincount(seg[keep].ravel())
+    got = vt.compute_cell_areas(flagmap=flag)
+    assert np.array_equal(_host(got), want)
+    vt._cell_areas = None
+    dens = vt.cell_point_density(g["points"], mass=g["mass"], flagmap=flag.astype(np.float64))
+    n = min(len(want), len(g["cell_mass"]))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        np.testing.assert_allclose(_host(dens)[:n], g["cell_mass"][:n] / want[:n], rtol=1e-13)
+    vt._cell_areas = None
+    assert np.array_equal(_host(vt.compute_cell_areas()), np.bincount(seg.ravel()))

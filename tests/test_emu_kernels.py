@@ -123,6 +123,13 @@ def test_voronoi_api_matches_reference_fixture():
     assert np.array_equal(vt.compute_cell_areas(), np.bincount(g["segmap"].ravel()))
     flag = np.zeros(g["segmap"].shape); flag[:10] = 1
     assert np.array_equal(vt.compute_cell_areas(flag)[:5], np.bincount(g["segmap"][10:].ravel(), minlength=40)[:5])
+    import frow_checks
+    frow_checks.check_flagmap(vt, g)
+    # a second object on the same Engine replaces the context's generators: the first one notices
+    vt2 = VoronoiTessellation(g["gens"][:7] + 0.25, engine=vt._engine)
+    vt2.set_pixel_grid((0, 20), (0, 20))
+    assert np.array_equal(vt2.segmap, O.c_assign_grid(20, 20, g["gens"][:7] + 0.25))
+    assert np.array_equal(vt.partition_points(g["points"]), g["partition"])
 
 
 def test_from_image_with_nan_matches_reference_fixture():
@@ -323,3 +330,29 @@ def test_randomised_small_maps_against_the_oracle(eng):
         good = np.isfinite(w).ravel()
         rm = O.np_moments(pts[good], w.ravel()[good], ref.ravel()[good], k)
         np.testing.assert_allclose(eng.moments()[:, :4], rm[:, :4], rtol=1e-12, atol=1e-12, err_msg=str((case, H, W, k)))
+
+
+def test_zero_weight_bin_updates_every_other_node(eng):
+    """A bin with pixels but zero total weight (lloyd.pyx:66-74 gives NaN for it): every OTHER node
+    must still be rewritten by that iteration, also when the table spans several CTAs of
+    k_update_nodes (k > 256), and the error is reported once the iteration is complete."""
+    N, k = 128, 700
+    rng = np.random.default_rng(12)
+    w = rng.uniform(0.5, 1.5, (N, N))
+    w[:24, :24] = 0.0                                   # zero-density corner
+    seeds = np.column_stack((rng.uniform(0, N - 1, k), rng.uniform(0, N - 1, k)))
+    eng.set_image(density=w)
+    eng.set_generators(seeds)
+    eng.step(1)
+    lab = O.c_assign_grid(N, N, seeds)
+    x, y = np.meshgrid(np.arange(N, dtype=float), np.arange(N, dtype=float))
+    rm = O.np_moments(np.column_stack((x.ravel(), y.ravel())), w.ravel(), lab.ravel(), k)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        want, _ = O.np_update_nodes(rm, seeds)
+    got = eng.generators()
+    bad = ~np.isfinite(want).all(axis=1)
+    assert bad.sum() > 0 and np.array_equal(~np.isfinite(got).all(axis=1), bad)
+    np.testing.assert_allclose(got[~bad], want[~bad], rtol=0, atol=1e-9)
+    assert eng.status() == (False, True) and eng.stats()[2] == 1
+    eng.step(1)                                         # error flag up: further steps are no-ops
+    assert eng.stats()[2] == 1

@@ -85,6 +85,9 @@ def test_voronoi_api_fixture():
     assert np.array_equal(vt.compute_cell_areas(), np.bincount(g["segmap"].ravel()))
     dens = vt.cell_point_density(g["points"], mass=g["mass"])
     np.testing.assert_allclose(dens, g["cell_mass"] / np.bincount(g["segmap"].ravel()), rtol=1e-13)
+    # flagmap > 0 pixels are left out of the areas (docstring semantics of tess/voronoi.py:116-152)
+    import frow_checks
+    frow_checks.check_flagmap(vt, g)
 
 
 def test_from_image_nan_fixture():
@@ -325,6 +328,105 @@ def test_config_c5_segmap_large(eng):
         assert torch.equal(ex, seg[y0:y0 + H, x0:x0 + W])
     # idempotence: the same call returns the same map
     assert torch.equal(eng.assign_grid(0.0, 0.0, N, N), seg)
+
+
+def _bincount_moments(torch, lab, w, N, y0=0):
+    """Independent device-side per-bin sums (torch.bincount) of count, w, w x, w y for a [H, N] map."""
+    l = lab.reshape(-1).long()
+    ax = torch.arange(N, dtype=torch.float64, device=lab.device)
+    ay = torch.arange(y0, y0 + lab.shape[0], dtype=torch.float64, device=lab.device)
+    out = [torch.bincount(l), torch.bincount(l, weights=w.reshape(-1)),
+           torch.bincount(l, weights=(w * ax[None, :]).reshape(-1)),
+           torch.bincount(l, weights=(w * ay[:, None]).reshape(-1))]
+    return out
+
+
+def test_config_c3_sn_mode_full_size(eng):
+    """C3 in signal + noise mode (6 moments, 20 B/px) at full size: labels equal the CVT-mode labels,
+    all six moments against torch.bincount over the whole map, per-bin S/N, NaN/Inf mask."""
+    import torch
+    N, k = 8192, 100000
+    sig = torch.sqrt(_device_gaussian(N, torch)) + 1.0
+    noise = torch.sqrt(sig + 1.0)
+    bad = torch.from_numpy(np.random.default_rng(2).choice(N * N, N * N // 1000, replace=False)).cuda()
+    sig.view(-1)[bad[::2]] = float("nan")
+    noise.view(-1)[bad[1::2]] = float("inf")
+    seeds = _gauss_seeds(N, k, 0)
+    eng.set_image(signal=sig, noise=noise)
+    eng.set_generators(seeds)
+    eng.accumulate()
+    lab, mom = eng.labels(), eng.moments()
+    assert torch.equal(lab, eng.assign_grid(0.0, 0.0, N, N))
+    w = (sig / noise) ** 2
+    good = torch.isfinite(w) & torch.isfinite(sig) & torch.isfinite(noise)
+    assert float(mom[:, 0].sum().item()) == float(good.sum().item())
+    zero = torch.zeros((), dtype=torch.float64, device="cuda")
+    wz, sz, nz = torch.where(good, w, zero), torch.where(good, sig, zero), torch.where(good, noise, zero)
+    ref = _bincount_moments(torch, lab, wz, N)
+    ref[0] = torch.bincount(lab.reshape(-1).long(), weights=good.reshape(-1).double())
+    ref += [torch.bincount(lab.reshape(-1).long(), weights=sz.reshape(-1)),
+            torch.bincount(lab.reshape(-1).long(), weights=(nz * nz).reshape(-1))]
+    for c, r in enumerate(ref):
+        r = torch.nn.functional.pad(r.double(), (0, k - r.numel()))
+        assert torch.allclose(mom[:, c], r, rtol=1e-11, atol=0), c
+    x0, y0, H, W = 3900, 4000, 96, 128
+    sub = O.c_assign_grid(H, W, seeds, x0=float(x0), y0=float(y0))
+    assert np.array_equal(h(lab[y0:y0 + H, x0:x0 + W]), sub)
+
+
+def _full_size_checks(torch, eng, N, k, lab, mom, dens, seeds, windows, strips):
+    assert int(lab.min().item()) >= 0 and int(lab.max().item()) < k
+    if mom is not None:
+        assert float(mom[:, 0].sum().item()) == float(N) * N
+        ref = _bincount_moments(torch, lab, dens, N)
+        assert torch.equal(torch.nn.functional.pad(ref[0], (0, k - ref[0].numel())).double(), mom[:, 0])
+        for c in (1, 2, 3):
+            r = torch.nn.functional.pad(ref[c], (0, k - ref[c].numel()))
+            assert torch.allclose(mom[:, c], r, rtol=1e-11, atol=0), c
+        del ref
+    for (x0, y0, H, W) in windows:
+        ex = eng.assign_grid(float(x0), float(y0), H, W, exhaustive=True)
+        assert torch.equal(ex, lab[y0:y0 + H, x0:x0 + W]), (x0, y0)
+    for (x0, y0, H, W) in strips:
+        assert np.array_equal(h(lab[y0:y0 + H, x0:x0 + W]), O.c_assign_grid(H, W, seeds, x0=float(x0), y0=float(y0)))
+
+
+def test_config_c4_full_size_one_gpu(eng):
+    """C4 (32768^2 px x 1e6 generators, CVT mode) on ONE GPU: conservation, per-bin sums against
+    torch.bincount over the whole map, Lloyd path == segmap path, tiled == exhaustive on windows
+    through the dense centre and a far corner, oracle strips."""
+    import torch
+    N, k = 32768, 1000000
+    dens = _device_gaussian(N, torch)
+    seeds = _gauss_seeds(N, k, 0)
+    eng.set_image(density=dens)
+    eng.set_generators(seeds)
+    eng.accumulate()
+    lab, mom = eng.labels(), eng.moments()
+    _full_size_checks(torch, eng, N, k, lab, mom, dens, seeds,
+                      windows=((16300, 16350, 160, 256), (0, 0, 128, 256), (32512, 20000, 128, 256)),
+                      strips=((16000, 16384, 4, 256), (30000, 3000, 4, 256)))
+    seg = eng.assign_grid(0.0, 0.0, N, N)
+    assert torch.equal(seg, lab)
+    del seg
+    eng.step(2)
+    d, _, it = eng.stats()
+    assert it == 2 and np.isfinite(d) and d > 0
+
+
+def test_config_c5_full_size(eng):
+    """C5 at BASELINE's size: segmentation map of 32768^2 px x 1e6 generators."""
+    import torch
+    N, k = 32768, 1000000
+    seeds = _gauss_seeds(N, k, 5)
+    eng.set_generators(seeds)
+    seg = eng.assign_grid(0.0, 0.0, N, N)
+    _full_size_checks(torch, eng, N, k, seg, None, None, seeds,
+                      windows=((16384, 16300, 160, 256), (32000, 200, 128, 256)),
+                      strips=((16100, 16500, 4, 256), (100, 32700, 4, 256)))
+    cnt = torch.bincount(seg.reshape(-1).long(), minlength=k)
+    assert int(cnt.sum().item()) == N * N
+    assert torch.equal(eng.assign_grid(0.0, 0.0, N, N), seg)             # idempotence
 
 
 # ---------------------------------------------------------------- WVT extension, options, diagnostics
