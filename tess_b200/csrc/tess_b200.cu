@@ -20,6 +20,7 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #define TESS_VERSION_NUM 100
@@ -94,6 +95,10 @@ struct tess_ctx {
     double* delta_part; // per-CTA partial deltas of k_update_nodes
     int cell_shift;     // image grids: cell = 64 px >> cell_shift; -1 = not decided for geo_key yet
     double geo_key[4];  // window (x0, y0, H, W) the shift was decided for
+    TessTileMap tmap[2];   // TMA descriptors of the pixel map(s) (32x32-px box), see make_tile_map
+    int tmap_ok;
+    const double* tmap_src[2];
+    long tmap_hw[2];
     int timing;        // TESS_OPT_KERNEL_TIMING
 #ifndef TESS_EMU
     cudaEvent_t ev[2 * 512];
@@ -584,6 +589,53 @@ static int resident_ctas(tess_ctx* c, K kern) {
 #endif
 }
 
+// ---- TMA descriptor of an [H][W] fp64 map with a 32x32-px box (the quadrant tile).  The encoder is a
+// driver entry point, fetched through the runtime so that the library does not link libcuda.
+#ifndef TESS_EMU
+#include <cuda.h>
+#include <cudaTypedefs.h>
+static bool make_tile_map(const double* base, long H, long W, TessTileMap* out) {
+    static PFN_cuTensorMapEncodeTiled_v12000 enc = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess)
+            enc = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+        cudaGetLastError();
+    }
+    if (!enc || !base || ((uintptr_t)base & 15u) || (W & 1) || W < 32 || H < 32 || W > (1L << 31) || H > (1L << 31)) return false;
+    static_assert(sizeof(CUtensorMap) == sizeof(TessTileMap), "tensor map size");
+    CUtensorMap m;
+    const cuuint64_t dims[2] = {(cuuint64_t)W, (cuuint64_t)H};
+    const cuuint64_t strides[1] = {(cuuint64_t)W * 8u};
+    const cuuint32_t box[2] = {32u, 32u};
+    const cuuint32_t estr[2] = {1u, 1u};
+    const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    memcpy(out, &m, sizeof(m));
+    return true;
+}
+#else
+static bool make_tile_map(const double*, long, long, TessTileMap*) { return false; }
+#endif
+
+// descriptors of the current pixel maps (re-encoded only when a pointer or the shape changed)
+static void ensure_tile_maps(tess_ctx* c, int mode, long H, long W) {
+    const double* src[2] = {mode == 2 ? c->sig : c->dens, mode == 2 ? c->noise : nullptr};
+    if (c->tmap_ok && c->tmap_src[0] == src[0] && c->tmap_src[1] == src[1] && c->tmap_hw[0] == H && c->tmap_hw[1] == W) return;
+    c->tmap_ok = 0;
+    c->tmap_src[0] = src[0]; c->tmap_src[1] = src[1]; c->tmap_hw[0] = H; c->tmap_hw[1] = W;
+    if (mode == 0 || !make_tile_map(src[0], H, W, &c->tmap[0])) return;
+    if (mode == 2 && !make_tile_map(src[1], H, W, &c->tmap[1])) return;
+    if (mode != 2) c->tmap[1] = c->tmap[0];
+    c->tmap_ok = 1;
+}
+
 template <int MODE>
 static void launch_image(tess_ctx* c, const TessImgArgs& a, bool vec, long want, cudaStream_t s) {
 #define TESS_GO(KERN)                                                   \
@@ -592,10 +644,16 @@ static void launch_image(tess_ctx* c, const TessImgArgs& a, bool vec, long want,
         /* one warp per quadrant, but the tail phase has 32 / TESS_RING_ROWS strips per queued quadrant */ \
         if (g_ > want * (32 / TESS_RING_ROWS)) g_ = want * (32 / TESS_RING_ROWS); \
         if (g_ < 1) g_ = 1;                                             \
-        TESS_LAUNCH((KERN), (int)g_, TESS_MAIN_THREADS, s, a, vec ? 1 : 0); \
+        TESS_LAUNCH((KERN), (int)g_, TESS_MAIN_THREADS, s, a, vec ? 1 : 0, use_tma, c->tmap[0], c->tmap[1]); \
     } while (0)
     // interior quadrants (aligned 128-bit accesses), then the ragged edge / unaligned remainder
     const bool has_edge = !vec || (a.W % 32 != 0) || (a.H % 32 != 0);
+    int use_tma = 0;
+    static const bool no_tma = getenv("TESS_NO_TMA") != nullptr;     // measurement aid: A/B the prefetch
+    if (vec && MODE != 0 && !no_tma) {
+        ensure_tile_maps(c, MODE, a.H, a.W);
+        use_tma = c->tmap_ok;
+    }
     if (c->has_scale) {
         if (vec) TESS_GO((k_image_main<MODE, true, false>));
         if (has_edge) TESS_GO((k_image_main<MODE, true, true>));

@@ -39,6 +39,18 @@ static long g_tess_launches = 0;   // kernels launched by the library (host-side
 #define TESS_MAIN_MINBLOCKS_SN 6 // same for the signal/noise mode (two maps in flight: <= 168 registers)
 #endif
 #define TESS_FULL 0xffffffffu
+
+// A TMA tensor map (CUtensorMap: 128 opaque bytes, 64-byte aligned) of a pixel map [H][W] fp64 with a
+// 32x32-px box -- the quadrant tile.  Encoded on the host (tess_b200.cu::make_tile_map), passed to the
+// image kernel as a __grid_constant__ parameter.
+struct alignas(64) TessTileMap {
+    unsigned long long opaque[16];
+};
+#ifdef TESS_EMU
+#define TESS_GRID_CONSTANT
+#else
+#define TESS_GRID_CONSTANT __grid_constant__
+#endif
 #define TESS_NAN (__longlong_as_double(0x7ff8000000000000LL))
 
 // relative slack on bound comparisons, 1 + 2^-39

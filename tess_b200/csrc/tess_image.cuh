@@ -48,13 +48,22 @@
 #ifndef TESS_LEAF_MIN
 #define TESS_LEAF_MIN 3     // parent lists up to this length are evaluated without a leaf filter
 #endif
-// quadrant list capacity of the fast path = entries of a warp's accumulator table
-#define TESS_QCAP(MODE) ((MODE) == 2 ? 96 : 128)
+// quadrant list capacity of the fast path (records staged in the warp's shared memory)
+#define TESS_QCAP(MODE) 128
 #ifndef TESS_DYNAMIC
 #define TESS_DYNAMIC 1
 #endif
 #ifndef TESS_RING_ROWS
 #define TESS_RING_ROWS 2
+#endif
+#ifndef TESS_MERGE_ENTER
+#define TESS_MERGE_ENTER 16 // retiring lanes from which the same-bin groups are merged with shuffles first
+#endif
+#ifndef TESS_MERGE_MIN
+#define TESS_MERGE_MIN 12   // smallest group worth a shuffle tree
+#endif
+#ifndef TESS_PREFETCH
+#define TESS_PREFETCH 1     // the next quadrant's pixel tile is prefetched into L2 by the TMA unit
 #endif
 
 struct TessImgArgs {
@@ -82,7 +91,7 @@ struct TessImgArgs {
 // v = sum w, sum w*x, sum w*y [, sum S, sum N^2]
 template <int NV>
 struct TessRun {
-    int key;    // position in the quadrant's candidate list; -1 = none yet
+    int key;    // generator id of the bin being summed; -1 = none yet
     int n;      // pixel count
     double v[NV];
 };
@@ -117,69 +126,79 @@ TESS_DEVFN void tess_cp_async4(void* dst, const void* src) {
     memcpy(dst, src, 4);
 #endif
 }
+// TMA prefetch of the 32x32-px tile whose first pixel is (col, row) into L2: ONE instruction for the
+// whole 8 KB tile (cp.async.bulk.prefetch.tensor -> UTMAPF), no register or shared-memory destination,
+// no per-row address arithmetic.  Issued by one lane.
+TESS_DEVFN void tess_prefetch_tile(const TessTileMap* tm, int col, int row) {
+#ifndef TESS_EMU
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tm), "r"(col), "r"(row) : "memory");
+#else
+    (void)tm; (void)col; (void)row;
+#endif
+}
 TESS_DEVFN void tess_cp_async_wait() {
 #ifndef TESS_EMU
     asm volatile("cp.async.wait_all;" ::: "memory");
 #endif
 }
 
-// Lanes with `flush` set add their run (key, n, v) to the warp's table.  Lanes holding the same key
-// take turns: every pending lane writes its id to claim[key], the one whose id survives does a plain
-// read-modify-write, the others try again (warp-level aggregation without atomics: the table is
-// private to the warp).  All 32 lanes must call; no divergence.
+// Lanes with `flush` set retire their run: its pixel count and sums go straight to the bin's row of
+// the global moment vector as fire-and-forget fp64 reductions (red.global.add.f64; the moment table
+// is a few MB and lives in L2).  Runs are keyed by GENERATOR id, so a run outlives the quadrant it
+// started in: a lane inside a large bin keeps adding to its registers quadrant after quadrant and
+// issues no reduction at all until its bin changes or the kernel ends.  No shared-memory table, no
+// election between lanes, no divergence beyond the predicate.
 template <int NV>
-TESS_DEVFN void tess_table_flush(bool flush, int key, int n, const double (&v)[NV], double* tab,
-                                 unsigned short* claim, int lane) {
-    bool pending = flush;
-    while (__any_sync(TESS_FULL, pending)) {
-        if (pending) claim[key] = (unsigned short)lane;
-        __syncwarp();     // orders the previous turn's table writes before this turn's, publishes the claims
-        if (pending && claim[key] == (unsigned short)lane) {
-            double* t = tab + key * (NV + 1);
-            t[0] += (double)n;
+TESS_DEVFN void tess_run_flush(bool flush, const TessRun<NV>& cur, double* mom, int lane) {
+    // Many lanes retiring at once usually retire the SAME bin (a warp that leaves a large bin): their
+    // sums are merged with shuffles first and one lane issues the reductions -- same-address fp64
+    // reductions serialise in L2, 32 lanes x thousands of warps on a handful of rows is a hot spot.
+    // A handful of retiring lanes (a bin boundary inside the warp tile) go straight to L2.
+    unsigned todo = __ballot_sync(TESS_FULL, flush);
+    if (__popc(todo) >= TESS_MERGE_ENTER) {
+#pragma unroll 1
+        for (int turn = 0; turn < 2; ++turn) {
+            const int leader = __ffs((int)todo) - 1;
+            const int key = __shfl_sync(TESS_FULL, cur.key, leader);
+            const bool mine = flush && (cur.key == key);
+            const unsigned grp = __ballot_sync(TESS_FULL, mine);
+            if (__popc(grp) < TESS_MERGE_MIN) break;             // small groups: every lane goes direct below
+            int n = mine ? cur.n : 0;
+            double v[NV];
 #pragma unroll
-            for (int i = 0; i < NV; ++i) t[1 + i] = __dadd_rn(t[1 + i], v[i]);
-            pending = false;
-        }
-    }
-    __syncwarp();
-}
-
-// End of a quadrant: every lane retires its live run.  Lanes that hold the same bin are merged with
-// shuffles first, so the table receives one add per bin.
-template <int NV>
-TESS_DEVFN void tess_warp_retire(TessRun<NV>& cur, double* tab, int lane) {
-    unsigned todo = __ballot_sync(TESS_FULL, cur.n > 0);
-    while (todo) {
-        const int leader = __ffs((int)todo) - 1;
-        const int key = __shfl_sync(TESS_FULL, cur.key, leader);
-        const bool mine = (cur.n > 0) && (cur.key == key);
-        const unsigned grp = __ballot_sync(TESS_FULL, mine);
-        int n = mine ? cur.n : 0;
-        double s[NV];
-#pragma unroll
-        for (int i = 0; i < NV; ++i) s[i] = mine ? cur.v[i] : 0.0;
-        if (grp != (1u << leader)) {
+            for (int i = 0; i < NV; ++i) v[i] = mine ? cur.v[i] : 0.0;
 #pragma unroll
             for (int m = 16; m >= 1; m >>= 1) {
                 n += __shfl_xor_sync(TESS_FULL, n, m);
 #pragma unroll
-                for (int i = 0; i < NV; ++i) s[i] = __dadd_rn(s[i], __shfl_xor_sync(TESS_FULL, s[i], m));
+                for (int i = 0; i < NV; ++i) v[i] = __dadd_rn(v[i], __shfl_xor_sync(TESS_FULL, v[i], m));
             }
-        }
-        if (lane == leader) {
-            double* t = tab + key * (NV + 1);
-            t[0] += (double)n;
+            if (lane == leader) {
+                double* m = mom + (long)key * (NV + 1);
+                tess_gmem_add(m, (double)n);
 #pragma unroll
-            for (int i = 0; i < NV; ++i) t[1 + i] = __dadd_rn(t[1 + i], s[i]);
+                for (int i = 0; i < NV; ++i) tess_gmem_add(m + 1 + i, v[i]);
+            }
+            flush = flush && !mine;
+            todo &= ~grp;
+            if (__popc(todo) < TESS_MERGE_MIN) break;
         }
-        todo &= ~grp;
     }
-    __syncwarp();
-    cur.key = -1;
-    cur.n = 0;
+    if (flush) {
+        double* m = mom + (long)cur.key * (NV + 1);
+        tess_gmem_add(m, (double)cur.n);
 #pragma unroll
-    for (int i = 0; i < NV; ++i) cur.v[i] = 0.0;
+        for (int i = 0; i < NV; ++i) tess_gmem_add(m + 1 + i, cur.v[i]);
+    }
+}
+
+// The lane's run moves to bin `key` where `sw` is set (after its old contents were flushed).
+template <int NV>
+TESS_DEVFN void tess_run_switch(bool sw, int key, TessRun<NV>& cur) {
+    cur.key = sw ? key : cur.key;
+    cur.n = sw ? 0 : cur.n;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) cur.v[i] = sw ? 0.0 : cur.v[i];
 }
 
 // upper bound of sqrt(x) for x >= 0 from the fp32 unit (exact value is not needed, only >=)
@@ -351,6 +370,53 @@ TESS_DEVFN int tess_filter(const double2* qxy, const double* qinv, const unsigne
                            double2* lg, double* li, int cap) {
     const int rank = tess_group_rank<GROUP>(lane);
     double umin = INFINITY, imax = 1.0;
+    int n = 0;
+    if (plen_max <= 3 * GROUP) {
+        // ---- short parent list (the common case): every lane holds its (at most three) centre
+        //      distances in registers, so the list is read and measured once
+        double dd[3];
+        int ee[3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const int i = rank + GROUP * t;
+            dd[t] = INFINITY;
+            ee[t] = 0;
+            if (i < plen) {
+                const int e = pident ? i : (int)pl[i];
+                const double2 g = qxy[e];
+                const double dx = ccx - g.x, dy = ccy - g.y;
+                double d = dx * dx + dy * dy;
+                if (HAS_SCALE) { const double iv = qinv[e]; d *= iv; imax = fmax(imax, iv); }
+                dd[t] = d;
+                ee[t] = e;
+            }
+        }
+        umin = tess_group_min<GROUP>(fmin(fmin(dd[0], dd[1]), dd[2]));
+        double c = 2.0 * rho;
+        if (HAS_SCALE) {
+            imax = -tess_group_min<GROUP>(-imax);
+            c *= tess_sqrt_up(imax);
+        }
+        const double thr = tess_center_thr(umin, c);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            if (GROUP * t < plen_max) {                          // warp-uniform (ballots inside)
+                const bool keep = active && (dd[t] <= thr);      // dd = inf beyond the list
+                const unsigned gb = tess_group_bits<GROUP>(__ballot_sync(TESS_FULL, keep), lane);
+                const int pos = n + __popc(gb & ((1u << rank) - 1u));
+                if (keep && pos < cap) {
+                    out[pos] = (unsigned short)ee[t];
+                    if (LEAF) {
+                        lg[pos] = qxy[ee[t]];
+                        if (HAS_SCALE) li[pos] = qinv[ee[t]];
+                    }
+                }
+                n += __popc(gb);
+            }
+        }
+        __syncwarp();
+        return n;
+    }
     for (int i = rank; i < plen; i += GROUP) {
         const int e = pident ? i : (int)pl[i];
         const double2 g = qxy[e];
@@ -366,7 +432,6 @@ TESS_DEVFN int tess_filter(const double2* qxy, const double* qinv, const unsigne
         c *= tess_sqrt_up(imax);
     }
     const double thr = tess_center_thr(umin, c);
-    int n = 0;
     for (int b0 = 0; b0 < plen_max; b0 += GROUP) {     // plen_max: warp-uniform bound (ballots inside)
         const int i = b0 + rank;
         bool keep = false;
@@ -432,12 +497,10 @@ struct TessWarpSmem {
     double2 qxy[2][QC];                                      // quadrant list (double buffered): coordinates,
     double qinv[HAS_SCALE ? 2 : 1][HAS_SCALE ? QC : 1];     //   1/scale^2,
     int qgid[2][QC];                                         //   generator index
-    double tab[(MODE != 0) ? QC * (NV + 1) : 1];             // accumulators per list position
     double2 lg[4][TESS_LEAF_CAP];                            // leaf lists: coordinates,
     double li[HAS_SCALE ? 4 : 1][HAS_SCALE ? TESS_LEAF_CAP : 1];   //   1/scale^2,
     unsigned short ls[4][TESS_LEAF_CAP];                     //   quadrant-list position
     unsigned short bl[2][TESS_BCAP];                         // 16x16 block lists (positions)
-    unsigned short claim[(MODE != 0) ? QC : 1];              // election of the lane that adds to a table entry
 };
 
 // One quadrant on the fast path (list of at most QCAP candidates staged in sm.q*[buf]).  INTERIOR:
@@ -445,18 +508,13 @@ struct TessWarpSmem {
 // rectangle radii); the general variant guards every access and is kept out of line.
 template <int MODE, bool HAS_SCALE, bool INTERIOR>
 TESS_DEVFN void tess_quadrant_body(const TessImgArgs& a, TessWarpSmem<MODE, HAS_SCALE>& sm, int buf, int32_t* labels,
-                                   const double* src, int c_q, int qx0, int qy0, int lane) {
+                                   const double* src, int c_q, int qx0, int qy0, int lane,
+                                   TessRun<(MODE == 2) ? 5 : 3>& cur) {
     constexpr int NV = (MODE == 2) ? 5 : 3;
     const int cx = lane & 15, ry = lane >> 4;          // patch: cols 2cx,2cx+1; rows 4ry..4ry+3
     const int leaf = cx >> 2;                          // 8-px-wide leaf of the warp tile
     const int blk = cx >> 3;                           // 16-px-wide block
-    double* const tab = sm.tab;
     const int Wi = (int)a.W, Hi = (int)a.H;
-    TessRun<NV> cur;                 // the lane's running same-bin sum (registers)
-    cur.key = -1;
-    cur.n = 0;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) cur.v[i] = 0.0;
     const double2* const qxy = sm.qxy[buf];
     const double* const qinv = HAS_SCALE ? sm.qinv[buf] : nullptr;
     const int* const gidv = sm.qgid[buf];
@@ -465,7 +523,7 @@ TESS_DEVFN void tess_quadrant_body(const TessImgArgs& a, TessWarpSmem<MODE, HAS_
     const double X0 = a.x0 + (double)px, X1 = a.x0 + (double)(px + 1);
 
     // ---- one-bin quadrant (a single candidate, interior, MODE 1): constant labels, closed-form
-    //      patch sums, one shuffle reduction and four global reductions for the whole quadrant
+    //      patch sums that simply extend the lane's run
     if (MODE == 1 && c_q == 1 && interior) {
         const int gid = gidv[0];
         double s0 = 0.0, s1 = 0.0, s2 = 0.0;
@@ -492,23 +550,18 @@ TESS_DEVFN void tess_quadrant_body(const TessImgArgs& a, TessWarpSmem<MODE, HAS_
             s2 = __dadd_rn(s2, sy);
         }
         if (__all_sync(TESS_FULL, clean)) {
-#pragma unroll
-            for (int m = 16; m >= 1; m >>= 1) {
-                s0 = __dadd_rn(s0, __shfl_xor_sync(TESS_FULL, s0, m));
-                s1 = __dadd_rn(s1, __shfl_xor_sync(TESS_FULL, s1, m));
-                s2 = __dadd_rn(s2, __shfl_xor_sync(TESS_FULL, s2, m));
-            }
-            if (lane < 4) {
-                double* m = a.mom + (long)gid * (NV + 1);
-                tess_gmem_add(m + lane, lane == 0 ? 1024.0 : (lane == 1 ? s0 : (lane == 2 ? s1 : s2)));
-            }
+            // the whole quadrant joins the lane's run (no shuffles, no reductions while the bin lasts)
+            const bool sw = (cur.key != gid);
+            tess_run_flush<NV>(sw && cur.n > 0, cur, a.mom, lane);
+            tess_run_switch<NV>(sw, gid, cur);
+            cur.n += 32;
+            cur.v[0] = __dadd_rn(cur.v[0], s0);
+            cur.v[1] = __dadd_rn(cur.v[1], s1);
+            cur.v[2] = __dadd_rn(cur.v[2], s2);
             return;
         }
         // a masked pixel somewhere: fall through to the general path (labels are rewritten there)
     }
-
-    // (the accumulator table is all zero here: it is cleared once at kernel start and every entry is
-    //  zeroed again when it is flushed)
 
     const unsigned short* pl = nullptr;   // parent list of the leaf filter (quadrant-list positions)
     bool p_ident = true;
@@ -550,8 +603,8 @@ TESS_DEVFN void tess_quadrant_body(const TessImgArgs& a, TessWarpSmem<MODE, HAS_
         double2* const lg = sm.lg[leaf];
         unsigned short* const ls = sm.ls[leaf];
         double* const li = HAS_SCALE ? sm.li[leaf] : nullptr;
-        int len = 0;
-        bool use_leaf = false;
+        int len = 0;                                   // entries of this lane's leaf list (lg / ls / li)
+        bool slow = false;                             // leaf list overflowed: evaluate the parent list instead
         bool uniform = (c_q == 1);                     // the whole warp tile belongs to one bin
         int ukey = 0;
         if (!uniform) {
@@ -565,16 +618,28 @@ TESS_DEVFN void tess_quadrant_body(const TessImgArgs& a, TessWarpSmem<MODE, HAS_
                                                       a.x0 + 0.5 * (double)(lx0 + lx1),
                                                       a.y0 + 0.5 * (double)(wy0 + ly1), rho, interior || lx0 < a.W, lane, ls, lg, li,
                                                       TESS_LEAF_CAP);
-                use_leaf = (len <= TESS_LEAF_CAP);
+                slow = (len > TESS_LEAF_CAP);
                 // all (in-image) leaves ended with the same single candidate?
                 const int one = (len == 1) ? (int)ls[0] : ((interior || lx0 < a.W) ? -1 : -3);
                 const int ref = __reduce_max_sync(TESS_FULL, one);
                 uniform = (ref >= 0) && __all_sync(TESS_FULL, one == ref || one == -3);
                 ukey = ref;
+            } else {
+                // a handful of candidates: they all go to the leaf arrays unfiltered, so that the
+                // evaluation loop below has a single, branch-free way of reading its list
+                const int rk = tess_group_rank<8>(lane);
+                if (rk < p_len) {
+                    const int e = p_ident ? rk : (int)pl[rk];
+                    ls[rk] = (unsigned short)e;
+                    lg[rk] = qxy[e];
+                    if (HAS_SCALE) li[rk] = qinv[e];
+                }
+                len = p_len;
+                __syncwarp();
             }
         }
 
-        int bs[4][2];                                  // winning quadrant-list position per pixel
+        int bs[4][2];                                  // winner per pixel: quadrant-list position, then generator id
         if (uniform) {
             // ---- one bin for all 256 pixels: constant labels
             const int gid = gidv[ukey];
@@ -589,7 +654,8 @@ TESS_DEVFN void tess_quadrant_body(const TessImgArgs& a, TessWarpSmem<MODE, HAS_
                         if ((py + r < a.H) && (px + c < a.W)) labels[base0 + r * a.W + c] = gid;
             }
 #pragma unroll
-            for (int r = 0; r < 4; ++r) { bs[r][0] = ukey; bs[r][1] = ukey; }
+            for (int r = 0; r < 4; ++r) { bs[r][0] = gid; bs[r][1] = gid; }
+            ukey = gid;                                // from here on keys are generator ids
         } else {
             // ---- evaluate the surviving candidates with the pinned formula.  Lists are in no
             //      particular order, so an exact tie (d == best so far) is only RECORDED here; the
@@ -599,22 +665,13 @@ TESS_DEVFN void tess_quadrant_body(const TessImgArgs& a, TessWarpSmem<MODE, HAS_
             for (int r = 0; r < 4; ++r)
 #pragma unroll
                 for (int c = 0; c < 2; ++c) { bd[r][c] = INFINITY; bs[r][c] = 0; }
-            const int n_ev = use_leaf ? len : p_len;
-            bool tied = false;
+            const int n_ev = slow ? 0 : len;
+            bool tied = slow;          // an overflowed leaf list is evaluated by the exact loop below
 #pragma unroll 1     // the compiler's own 2x unrolling costs 1.3 % (instruction cache)
             for (int j = 0; j < n_ev; ++j) {
-                double2 g;
-                int e;
-                double inv = 1.0;
-                if (use_leaf) {
-                    g = lg[j];
-                    e = ls[j];
-                    if (HAS_SCALE) inv = li[j];
-                } else {
-                    e = p_ident ? j : (int)pl[j];
-                    g = qxy[e];
-                    if (HAS_SCALE) inv = qinv[e];
-                }
+                const double2 g = lg[j];
+                const int e = ls[j];
+                const double inv = HAS_SCALE ? li[j] : 1.0;
                 const double dx0 = __dsub_rn(X0, g.x), dx1 = __dsub_rn(X1, g.x);
                 const double dxx0 = __dmul_rn(dx0, dx0), dxx1 = __dmul_rn(dx1, dx1);
 #pragma unroll
@@ -636,10 +693,11 @@ TESS_DEVFN void tess_quadrant_body(const TessImgArgs& a, TessWarpSmem<MODE, HAS_
                 for (int r = 0; r < 4; ++r)
 #pragma unroll
                     for (int c = 0; c < 2; ++c) { bd[r][c] = INFINITY; bs[r][c] = 0; bg[r][c] = 0x7fffffff; }
+                const int n_ex = slow ? p_len : len;
 #pragma unroll 1
-                for (int j = 0; j < n_ev; ++j) {
+                for (int j = 0; j < n_ex; ++j) {
                     int e;
-                    if (use_leaf) e = ls[j];
+                    if (!slow) e = ls[j];
                     else e = p_ident ? j : (int)pl[j];
                     const double2 g = qxy[e];
                     const double inv = HAS_SCALE ? qinv[e] : 1.0;
@@ -657,17 +715,20 @@ TESS_DEVFN void tess_quadrant_body(const TessImgArgs& a, TessWarpSmem<MODE, HAS_
                 }
             }
             __syncwarp();                              // the leaves' lists differ in length
+            // ---- winners as generator ids (they key the runs and are the labels)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { bs[r][0] = gidv[bs[r][0]]; bs[r][1] = gidv[bs[r][1]]; }
             // ---- labels out: 16 lanes x 8 B = one 128-byte line per row
             if (interior) {
 #pragma unroll
                 for (int r = 0; r < 4; ++r)
-                    *reinterpret_cast<int2*>(labels + base0 + r * a.W) = make_int2(gidv[bs[r][0]], gidv[bs[r][1]]);
+                    *reinterpret_cast<int2*>(labels + base0 + r * a.W) = make_int2(bs[r][0], bs[r][1]);
             } else {
 #pragma unroll
                 for (int r = 0; r < 4; ++r)
 #pragma unroll
                     for (int c = 0; c < 2; ++c)
-                        if ((py + r < a.H) && (px + c < a.W)) labels[base0 + r * a.W + c] = gidv[bs[r][c]];
+                        if ((py + r < a.H) && (px + c < a.W)) labels[base0 + r * a.W + c] = bs[r][c];
             }
         }
         if (MODE == 0) continue;
@@ -705,13 +766,8 @@ TESS_DEVFN void tess_quadrant_body(const TessImgArgs& a, TessWarpSmem<MODE, HAS_
         if (uniform && all_clean) {
             // closed form for a one-bin patch: sum w x = X0 col0 + X1 col1, sum w y = sum_r Y_r row_r
             const bool sw = (cur.key != ukey);
-            if (__any_sync(TESS_FULL, sw)) {
-                tess_table_flush<NV>(sw && cur.n > 0, cur.key, cur.n, cur.v, tab, sm.claim, lane);
-                cur.key = ukey;
-                cur.n = sw ? 0 : cur.n;
-#pragma unroll
-                for (int i = 0; i < NV; ++i) cur.v[i] = sw ? 0.0 : cur.v[i];
-            }
+            tess_run_flush<NV>(sw && cur.n > 0, cur, a.mom, lane);
+            tess_run_switch<NV>(sw, ukey, cur);
             double sy = 0.0;
 #pragma unroll
             for (int r = 0; r < 4; ++r) sy = __dadd_rn(sy, __dmul_rn(__dadd_rn(wv[r][0], wv[r][1]), Y[r]));
@@ -743,56 +799,49 @@ TESS_DEVFN void tess_quadrant_body(const TessImgArgs& a, TessWarpSmem<MODE, HAS_
 #pragma unroll
                 for (int r = 0; r < 4; ++r) present = present || (bs[r][0] == cur.key) || (bs[r][1] == cur.key);
                 const bool sw = (rest >= 0) && !present;
-                if (__any_sync(TESS_FULL, sw)) {
-                    tess_table_flush<NV>(sw && cur.n > 0, cur.key, cur.n, cur.v, tab, sm.claim, lane);
-                    cur.key = sw ? rest : cur.key;
-                    cur.n = sw ? 0 : cur.n;
-#pragma unroll
-                    for (int i = 0; i < NV; ++i) cur.v[i] = sw ? 0.0 : cur.v[i];
-                }
+                tess_run_flush<NV>(sw && cur.n > 0, cur, a.mom, lane);
+                tess_run_switch<NV>(sw, rest, cur);
                 // the lane's pixels of this bin, summed in patch-local coordinates (column offset
                 // 0/1, row offset 0..3) and shifted once: sum w x = X0 sum w + sum_{col 1} w,
-                // sum w y = Y0 sum w + sum_r r (w_r0 + w_r1)
-                double t[4], c1 = 0.0;
+                // sum w y = Y0 sum w + sum_r r (w_r0 + w_r1).  Predicated adds: a pixel of another
+                // bin costs its compare only.
+                const int key = cur.key;
+                double sA = 0.0, sB = 0.0, c1 = 0.0, sy = 0.0, ss = 0.0, nn = 0.0;
                 int nh = 0;
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
-                    const bool h0 = (bs[r][0] == cur.key), h1 = (bs[r][1] == cur.key);
-                    const double w0 = h0 ? wv[r][0] : 0.0, w1 = h1 ? wv[r][1] : 0.0;
-                    nh += (h0 ? 1 : 0) + (h1 ? 1 : 0);
-                    t[r] = __dadd_rn(w0, w1);
-                    c1 = __dadd_rn(c1, w1);
-                    if (MODE == 2) {
-                        cur.v[NV - 2] = __dadd_rn(cur.v[NV - 2], __dadd_rn(h0 ? w_[r][0] : 0.0, h1 ? w_[r][1] : 0.0));
-                        const double z0 = h0 ? n_[r][0] : 0.0, z1 = h1 ? n_[r][1] : 0.0;
-                        cur.v[NV - 1] = __dadd_rn(cur.v[NV - 1], __dadd_rn(__dmul_rn(z0, z0), __dmul_rn(z1, z1)));
+                    if (bs[r][0] == key) {
+                        sA = __dadd_rn(sA, wv[r][0]);
+                        if (r == 1) sy = __dadd_rn(sy, wv[r][0]);
+                        if (r > 1) sy = __fma_rn((double)r, wv[r][0], sy);
+                        if (MODE == 2) { ss = __dadd_rn(ss, w_[r][0]); nn = __fma_rn(n_[r][0], n_[r][0], nn); }
+                        ++nh;
+                        bs[r][0] = -2;
                     }
-                    bs[r][0] = h0 ? -2 : bs[r][0];
-                    bs[r][1] = h1 ? -2 : bs[r][1];
+                    if (bs[r][1] == key) {
+                        sB = __dadd_rn(sB, wv[r][1]);
+                        if (r == 1) sy = __dadd_rn(sy, wv[r][1]);
+                        if (r > 1) sy = __fma_rn((double)r, wv[r][1], sy);
+                        if (MODE == 2) { ss = __dadd_rn(ss, w_[r][1]); nn = __fma_rn(n_[r][1], n_[r][1], nn); }
+                        ++nh;
+                        bs[r][1] = -2;
+                    }
                 }
-                const double wsum = __dadd_rn(__dadd_rn(t[0], t[1]), __dadd_rn(t[2], t[3]));
-                const double sy = __fma_rn(3.0, t[3], __fma_rn(2.0, t[2], t[1]));
+                c1 = sB;
+                const double wsum = __dadd_rn(sA, sB);
                 cur.n += nh;
                 cur.v[0] = __dadd_rn(cur.v[0], wsum);
                 cur.v[1] = __dadd_rn(cur.v[1], __fma_rn(X0, wsum, c1));
                 cur.v[2] = __dadd_rn(cur.v[2], __fma_rn(Y[0], wsum, sy));
+                if (MODE == 2) {
+                    cur.v[NV - 2] = __dadd_rn(cur.v[NV - 2], ss);
+                    cur.v[NV - 1] = __dadd_rn(cur.v[NV - 1], nn);
+                }
             }
         }
     }   // steps
 
-    // ---- end of the quadrant: retire the live runs (merged across the warp), table -> global
-    if (MODE != 0) {
-        tess_warp_retire<NV>(cur, tab, lane);
-        for (int e = lane; e < c_q; e += 32) {
-            const double* t = tab + e * (NV + 1);
-            if (t[0] != 0.0) {
-                double* m = a.mom + (long)gidv[e] * (NV + 1);
-#pragma unroll
-                for (int i = 0; i <= NV; ++i) { tess_gmem_add(m + i, t[i]); tab[e * (NV + 1) + i] = 0.0; }
-            }
-        }
-        __syncwarp();
-    }
+    // (the lanes' runs stay live: the next quadrant may continue them)
 }
 
 // MODE 0: labels only; 1: density map (4 moments); 2: signal + noise maps (6 moments).
@@ -800,7 +849,8 @@ TESS_DEVFN void tess_quadrant_body(const TessImgArgs& a, TessWarpSmem<MODE, HAS_
 // EDGE = true: the remaining ones (image edges; all of them when vec == 0), with guarded accesses.
 template <int MODE, bool HAS_SCALE, bool EDGE>
 __global__ void __launch_bounds__(TESS_MAIN_THREADS, (MODE == 2) ? TESS_MAIN_MINBLOCKS_SN : TESS_MAIN_MINBLOCKS)
-k_image_main(TessImgArgs a, int vec) {
+k_image_main(const TESS_GRID_CONSTANT TessImgArgs a, int vec, int use_tma, const TESS_GRID_CONSTANT TessTileMap tm0,
+             const TESS_GRID_CONSTANT TessTileMap tm1) {
     constexpr int NV = (MODE == 2) ? 5 : 3;
     constexpr int NW = TESS_MAIN_THREADS / 32;
     constexpr int QC = TESS_QCAP(MODE);
@@ -810,15 +860,15 @@ k_image_main(TessImgArgs a, int vec) {
     __shared__ __align__(16) TessWarpSmem<MODE, HAS_SCALE> s_w[NW];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     TessWarpSmem<MODE, HAS_SCALE>& sm = s_w[wib];
-    double* const tab = sm.tab;
     const double* const src = (MODE == 2) ? a.sig : a.dens;   // MODE 1: weight map; MODE 2: signal map
     const int n_q = a.L.nqx * a.L.nqy;               // < 2^31 (checked by the host)
     const int stride = (int)gridDim.x * NW;
 
-    if (MODE != 0) {
-        for (int i = lane; i < QC * (NV + 1); i += 32) tab[i] = 0.0;
-        __syncwarp();
-    }
+    TessRun<NV> cur;                 // the lane's running same-bin sum (registers), alive across quadrants
+    cur.key = -1;
+    cur.n = 0;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) cur.v[i] = 0.0;
     // ---- software pipeline over this warp's quadrants q, q + stride, ...: the list of quadrant i+1 is
     //      copied to shared memory (cp.async) while quadrant i is processed; (offset, count) of
     //      quadrant i+2 are loaded at the same time.
@@ -863,16 +913,25 @@ k_image_main(TessImgArgs a, int vec) {
         const int qy = q / a.L.nqx, qx = q - qy * a.L.nqx;
         const int qx0 = 32 * qx, qy0 = 32 * qy;            // pixel coordinates fit 32 bits (host-checked)
         const bool interior = vec && (qx0 + 32 <= a.W) && (qy0 + 32 <= a.H);
+#if TESS_PREFETCH
+        // the NEXT quadrant's pixels start their trip from DRAM now: one 256-byte row per lane
+        if (MODE != 0 && !EDGE && use_tma && q1 < n_q && cnt1 > 0 && lane == 0) {
+            const int qy1 = q1 / a.L.nqx, qx1 = q1 - qy1 * a.L.nqx;
+            tess_prefetch_tile(&tm0, 32 * qx1, 32 * qy1);          // (clipped at the image edge by the unit)
+            if (MODE == 2) tess_prefetch_tile(&tm1, 32 * qx1, 32 * qy1);
+        }
+#endif
         const int cnt_cur = (interior != EDGE) ? cnt : 0, off_cur = off;   // the other kernel's quadrants are skipped
         // cnt < 0 (builder overflow) and cnt > QC (list too long for the fast path) are done in the
         // tail below, spread over all warps
         if (cnt_cur > 0 && cnt_cur <= QC)
-            tess_quadrant_body<MODE, HAS_SCALE, !EDGE>(a, sm, buf, labels, src, cnt_cur, qx0, qy0, lane);
+            tess_quadrant_body<MODE, HAS_SCALE, !EDGE>(a, sm, buf, labels, src, cnt_cur, qx0, qy0, lane, cur);
         // ---- rotate the pipeline
         q = q1; cnt = cnt1; off = off1;
         q1 = q2; cnt1 = cnt2; off1 = off2;
         buf ^= 1;
     }
+    if (MODE != 0) tess_run_flush<NV>(cur.n > 0, cur, a.mom, lane);      // the runs still live
     // ---- tail: rows of the overflowed quadrants, spread over all warps of the grid (only in the
     //      instantiation that is always launched: the interior one for vector-friendly images)
     if (EDGE != (vec != 0)) {

@@ -47,12 +47,17 @@ class VoronoiTessellation(object):
         self._torch_out = _is_torch(xy)
 
     # -- engine plumbing -------------------------------------------------------------------
-    def _eng(self):
+    def _eng_raw(self):
+        """The engine, without making sure that it holds this object's generators."""
         if self._engine is None:
             dev = self._device
             if dev is None and _is_torch(self._xy) and self._xy.is_cuda:
                 dev = self._xy.device
             self._engine = Engine(dev)
+        return self._engine
+
+    def _eng(self):
+        self._eng_raw()
         # several objects may share one Engine (the public `engine=` argument): upload this
         # object's table unless it is the one the context holds
         if self._engine.gen_owner is not self:
@@ -63,8 +68,8 @@ class VoronoiTessellation(object):
     def _out(self, t, dtype=None):
         """Device tensor -> the caller's array family."""
         if self._torch_out:
-            return t if dtype is None else t.to(dtype=getattr(self._eng()._torch, dtype))
-        a = self._eng()._to_host(t)
+            return t if dtype is None else t.to(dtype=getattr(self._eng_raw()._torch, dtype))
+        a = self._eng_raw()._to_host(t)
         return a if dtype is None else a.astype(dtype)
 
     # -- reference surface -----------------------------------------------------------------
