@@ -50,8 +50,8 @@
 #endif
 // quadrant list capacity of the fast path (records staged in the warp's shared memory)
 #define TESS_QCAP(MODE) 128
-#ifndef TESS_DYNAMIC
-#define TESS_DYNAMIC 1
+#ifndef TESS_CHUNK
+#define TESS_CHUNK 2        // consecutive quadrants per draw from the device queue (4: -5 %, 8: -17 %: wider chunks spread the streams)
 #endif
 #ifndef TESS_RING_ROWS
 #define TESS_RING_ROWS 2
@@ -497,9 +497,9 @@ struct TessWarpSmem {
     double2 qxy[2][QC];                                      // quadrant list (double buffered): coordinates,
     double qinv[HAS_SCALE ? 2 : 1][HAS_SCALE ? QC : 1];     //   1/scale^2,
     int qgid[2][QC];                                         //   generator index
-    double2 lg[4][TESS_LEAF_CAP];                            // leaf lists: coordinates,
-    double li[HAS_SCALE ? 4 : 1][HAS_SCALE ? TESS_LEAF_CAP : 1];   //   1/scale^2,
-    unsigned short ls[4][TESS_LEAF_CAP];                     //   quadrant-list position
+    double2 lg[4][TESS_LEAF_CAP + 1];                        // leaf lists (+1: read-ahead pad): coordinates,
+    double li[HAS_SCALE ? 4 : 1][HAS_SCALE ? TESS_LEAF_CAP + 1 : 1];   //   1/scale^2,
+    unsigned short ls[4][TESS_LEAF_CAP + 2];                 //   quadrant-list position
     unsigned short bl[2][TESS_BCAP];                         // 16x16 block lists (positions)
 };
 
@@ -668,10 +668,18 @@ TESS_DEVFN void tess_quadrant_body(const TessImgArgs& a, TessWarpSmem<MODE, HAS_
             const int n_ev = slow ? 0 : len;
             bool tied = slow;          // an overflowed leaf list is evaluated by the exact loop below
 #pragma unroll 1     // the compiler's own 2x unrolling costs 1.3 % (instruction cache)
+            // (the record of the NEXT candidate is read while this one is evaluated: the arrays are
+            //  padded by one entry, so the read past the list is harmless)
+            double2 gn = lg[0];
+            int en = ls[0];
+            double invn = HAS_SCALE ? li[0] : 1.0;
             for (int j = 0; j < n_ev; ++j) {
-                const double2 g = lg[j];
-                const int e = ls[j];
-                const double inv = HAS_SCALE ? li[j] : 1.0;
+                const double2 g = gn;
+                const int e = en;
+                const double inv = invn;
+                gn = lg[j + 1];
+                en = ls[j + 1];
+                if (HAS_SCALE) invn = li[j + 1];
                 const double dx0 = __dsub_rn(X0, g.x), dx1 = __dsub_rn(X1, g.x);
                 const double dxx0 = __dmul_rn(dx0, dx0), dxx1 = __dmul_rn(dx1, dx1);
 #pragma unroll
@@ -869,23 +877,36 @@ k_image_main(const TESS_GRID_CONSTANT TessImgArgs a, int vec, int use_tma, const
     cur.n = 0;
 #pragma unroll
     for (int i = 0; i < NV; ++i) cur.v[i] = 0.0;
-    // ---- software pipeline over this warp's quadrants q, q + stride, ...: the list of quadrant i+1 is
-    //      copied to shared memory (cp.async) while quadrant i is processed; (offset, count) of
-    //      quadrant i+2 are loaded at the same time.
-    //      The first two quadrants of a warp are fixed (q, q + stride); the following ones are drawn
-    //      from a device counter (one atomic per quadrant by lane 0, requested a whole quadrant
-    //      before its value is needed), so that no warp idles while others still have a queue:
-    //      with fixed strides the per-warp sums of 28 quadrant costs differed by ~9 %.
-    int q = (int)blockIdx.x * NW + wib;
+    // ---- software pipeline over this warp's quadrants: the list of quadrant i+1 is copied to shared
+    //      memory (cp.async) while quadrant i is processed; (offset, count) of quadrant i+2 are loaded
+    //      at the same time.  Quadrants are handed out in CHUNKS of TESS_CHUNK consecutive ones: the
+    //      first chunk of a warp is fixed (its global warp index), the following ones are drawn from a
+    //      device counter, so that no warp idles while others still have a queue (with fixed strides
+    //      the per-warp sums of quadrant costs differed by ~9 %).  One atomic per chunk, requested a
+    //      whole chunk before its value is needed: a counter asked once per quadrant by 2 400 warps
+    //      was itself a hot spot (5 % of all warp stalls waited for its answer), and neighbouring
+    //      quadrants let a lane's run live on.
+    constexpr int G = TESS_CHUNK;
+    int* const counter = EDGE ? reinterpret_cast<int*>(&a.st->spare_) : &a.st->tile_counter;
+    int tok = 0;                                   // lane 0: the chunk after the current one
+    if (lane == 0) tok = stride + atomicAdd(counter, 1);
+    auto next_q = [&](int qq) {
+        if (qq >= n_q) return n_q;
+        int nq = qq + 1;
+        if ((nq % G) == 0) {                       // chunk exhausted
+            const int t = __shfl_sync(TESS_FULL, tok, 0);
+            const bool more = t < (n_q + G - 1) / G;
+            if (lane == 0 && more) tok = stride + atomicAdd(counter, 1);
+            nq = more ? t * G : n_q;
+        }
+        return min(nq, n_q);
+    };
+    int q = min(((int)blockIdx.x * NW + wib) * G, n_q);
+    if ((long)((int)blockIdx.x * NW + wib) * G >= n_q) q = n_q;
     int cnt = (q < n_q) ? a.L.q_cnt[q] : 0, off = (q < n_q) ? a.L.q_off[q] : 0;
-    int q1 = q + stride;
+    int q1 = next_q(q);
     int cnt1 = (q1 < n_q) ? a.L.q_cnt[q1] : 0, off1 = (q1 < n_q) ? a.L.q_off[q1] : 0;
     int buf = 0;
-#if TESS_DYNAMIC
-    int* const counter = EDGE ? reinterpret_cast<int*>(&a.st->spare_) : &a.st->tile_counter;
-    int tok = 0;
-    if (lane == 0) tok = 2 * stride + atomicAdd(counter, 1);
-#endif
     auto stage = [&](int b, int o, int n) {
         if (n > 0 && n <= QC) {
             for (int i = lane; i < n; i += 32) {
@@ -899,12 +920,7 @@ k_image_main(const TESS_GRID_CONSTANT TessImgArgs a, int vec, int use_tma, const
 
     while (q < n_q) {
         // (offset, count) of the quadrant after the next: in flight during this quadrant
-#if TESS_DYNAMIC
-        const int q2 = __shfl_sync(TESS_FULL, tok, 0);
-        if (lane == 0 && q2 < n_q) tok = 2 * stride + atomicAdd(counter, 1);
-#else
-        const int q2 = q1 + stride;
-#endif
+        const int q2 = next_q(q1);
         int cnt2 = 0, off2 = 0;
         if (q2 < n_q) { cnt2 = a.L.q_cnt[q2]; off2 = a.L.q_off[q2]; }
         tess_cp_async_wait();          // this quadrant's list has landed
