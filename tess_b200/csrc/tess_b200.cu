@@ -16,6 +16,7 @@
 #include "tess_image.cuh"
 #include "tess_points.cuh"
 #include "tess_update.cuh"
+#include "tess_phases.cuh"
 #include "tess_peer.cuh"
 
 #include <stdarg.h>
@@ -94,11 +95,16 @@ struct tess_ctx {
     double* scratch;   // 8 doubles (bounding-box reduction)
     double* delta_part; // per-CTA partial deltas of k_update_nodes
     int cell_shift;     // image grids: cell = 64 px >> cell_shift; -1 = not decided for geo_key yet
+    int regrid_tried;   // the grid was re-decided after an overflow since the last tess_set_generators
     double geo_key[4];  // window (x0, y0, H, W) the shift was decided for
     TessTileMap tmap[2];   // TMA descriptors of the pixel map(s) (32x32-px box), see make_tile_map
     int tmap_ok;
     const double* tmap_src[2];
     long tmap_hw[2];
+    int index_valid;   // the generator grid in the workspace is that of the CURRENT nodes for index_geo
+    TessGrid index_geo;
+    int phase_grid;    // CTAs of k_iteration_phases (all resident: cooperative launch); 0 = not decided
+    int coop_ok;
     int timing;        // TESS_OPT_KERNEL_TIMING
 #ifndef TESS_EMU
     cudaEvent_t ev[2 * 512];
@@ -235,6 +241,7 @@ extern "C" int tess_set_image(tess_ctx* c, long H, long W, double x0, double y0,
     const bool cvt = density && !signal && !noise, sn = !density && signal && noise;
     if (!cvt && !sn) return tess_fail(TESS_ERR_ARG, "tess_set_image: give either density or signal+noise");
     c->source = SRC_IMAGE;
+    c->index_valid = 0;
     c->img_mode = cvt ? 1 : 2;
     c->H = H; c->W = W; c->x0 = x0; c->y0 = y0;
     c->dens = density; c->sig = signal; c->noise = noise;
@@ -246,6 +253,7 @@ extern "C" int tess_set_image(tess_ctx* c, long H, long W, double x0, double y0,
 
 extern "C" int tess_set_domain(tess_ctx* c, double x0, double y0, double x1, double y1) {
     TRY(bind(c));
+    c->index_valid = 0;
     if (!(x1 >= x0) || !(y1 >= y0)) { c->has_domain = 0; c->cell_shift = -1; return TESS_OK; }
     if (!isfinite(x0) || !isfinite(y0) || !isfinite(x1) || !isfinite(y1))
         return tess_fail(TESS_ERR_ARG, "tess_set_domain: non-finite rectangle");
@@ -307,6 +315,7 @@ extern "C" int tess_set_points(tess_ctx* c, long n, const double* xy, const doub
     if (n <= 0 || !xy || !w) return tess_fail(TESS_ERR_ARG, "tess_set_points: need n > 0, xy and w");
     if (n > 2000000000L) return tess_fail(TESS_ERR_ARG, "tess_set_points: n too large");
     c->source = SRC_POINTS;
+    c->index_valid = 0;
     c->img_mode = 0;
     c->n_pts = n; c->pts_xy = xy; c->pts_w = w;
     c->dens = c->sig = c->noise = nullptr;
@@ -321,6 +330,7 @@ extern "C" int tess_set_generators(tess_ctx* c, long k, const double* node_xy, c
     if (k <= 0 || !node_xy) return tess_fail(TESS_ERR_ARG, "tess_set_generators: need k > 0 and node_xy");
     if (k > 1000000000L) return tess_fail(TESS_ERR_ARG, "tess_set_generators: k too large");
     cudaStream_t s = S(stream);
+    cudaStream_t s_early = s;
     if (k > c->k_cap) {
         void** ps[] = {(void**)&c->node, (void**)&c->scale, (void**)&c->inv_s2, (void**)&c->cell_of,
                        (void**)&c->cell_items, (void**)&c->cell_xy, (void**)&c->cell_inv, (void**)&c->prev_count};
@@ -337,7 +347,11 @@ extern "C" int tess_set_generators(tess_ctx* c, long k, const double* node_xy, c
         c->k_cap = (int)k;
     }
     c->k = (int)k;
+    if (c->cell_cnt && c->cells_cap > 0)   // (an update that raised NONFINITE leaves a partial histogram behind)
+        CU_TRY(cudaMemsetAsync(c->cell_cnt, 0, sizeof(int) * (size_t)c->cells_cap, s_early));
+    c->index_valid = 0;
     c->cell_shift = -1;
+    c->regrid_tried = 0;
     c->gb_valid = 0;
     // WVT scale updates need a scale table: start from unit scales when none is given
     c->has_scale = (scale || c->wvt_update) ? 1 : 0;
@@ -545,6 +559,7 @@ static int ensure_moments(tess_ctx* c) {
 // counting sort of the generators into q.g; `mom`/n_mom: moment vector to clear (or null/0)
 static int build_index(tess_ctx* c, const Geometry& q, int honor, double* mom, long n_mom, cudaStream_t s) {
     TRY(ensure_cells(c, q.n_cells));
+    c->index_valid = 0;      // whatever grid the iteration had built is overwritten
     const int k = c->k;
     int nb = (int)(((long)k + 255) / 256);
     int nbz = (int)((n_mom + 255) / 256);
@@ -560,17 +575,18 @@ static int build_index(tess_ctx* c, const Geometry& q, int honor, double* mom, l
     return TESS_OK;
 }
 
-static int build_lists(tess_ctx* c, const Geometry& q, int honor, int mode, cudaStream_t s) {
+static int build_lists(tess_ctx* c, const Geometry& q, int honor, int mode, cudaStream_t s, double* mom_clear = nullptr,
+                       long n_clear = 0) {
     TRY(ensure_lists(c, q.T));
     const int qcap = TESS_QCAP(mode);          // longest list the image kernel of this mode stages
     int grid = (q.T.n_tiles + TESS_LIST_WARPS - 1) / TESS_LIST_WARPS;
     if (grid > c->sm_count * 32) grid = c->sm_count * 32;
     if (c->has_scale)
         TESS_LAUNCH((k_build_qlists<true>), grid, TESS_LIST_WARPS * 32, s, c->st, honor, q.T, q.g, c->cell_start,
-                    c->cell_items, c->cell_xy, c->cell_inv, c->ql, c->tile_ring, c->cell_shift > 0 ? 1 : 0, qcap);
+                    c->cell_items, c->cell_xy, c->cell_inv, c->ql, c->tile_ring, c->cell_shift > 0 ? 1 : 0, qcap, mom_clear, n_clear);
     else
         TESS_LAUNCH((k_build_qlists<false>), grid, TESS_LIST_WARPS * 32, s, c->st, honor, q.T, q.g, c->cell_start,
-                    c->cell_items, c->cell_xy, c->cell_inv, c->ql, c->tile_ring, c->cell_shift > 0 ? 1 : 0, qcap);
+                    c->cell_items, c->cell_xy, c->cell_inv, c->ql, c->tile_ring, c->cell_shift > 0 ? 1 : 0, qcap, mom_clear, n_clear);
     CU_TRY(cudaGetLastError());
     return TESS_OK;
 }
@@ -587,6 +603,69 @@ static int resident_ctas(tess_ctx* c, K kern) {
     (void)kern;
     return c->sm_count * 2;
 #endif
+}
+
+// ------------------------------------------------------------------------------------ phased O(k) steps
+static bool same_grid(const TessGrid& a, const TessGrid& b) {
+    return a.ox == b.ox && a.oy == b.oy && a.cs == b.cs && a.gw == b.gw && a.gh == b.gh;
+}
+
+static int n_moments(const tess_ctx* c);
+
+static void phase_args(tess_ctx* c, const Geometry& q, TessPhaseArgs* a) {
+    memset(a, 0, sizeof(*a));
+    a->st = c->st;
+    a->mom = c->mom; a->M = n_moments(c); a->k = c->k;
+    a->prev_count = c->prev_count; a->node = c->node;
+    a->scale = c->has_scale ? c->scale : nullptr;
+    a->inv_s2 = c->inv_s2;
+    a->inv_in = c->has_scale ? c->inv_s2 : nullptr;
+    a->wvt_update = c->wvt_update;
+    a->delta_part = c->delta_part;
+    a->mask_mode = (c->source == SRC_IMAGE) ? c->img_mode : 0;
+    a->lab0 = c->lab[0]; a->lab1 = c->lab[1];
+    a->n = (c->source == SRC_IMAGE) ? c->H * c->W : c->n_pts;
+    a->dens = c->dens; a->sig = c->sig; a->noise = c->noise;
+    a->uniform_weight = c->uniform_weight;
+    a->g = q.g; a->n_cells = q.n_cells;
+    a->cell_cnt = c->cell_cnt; a->cell_of = c->cell_of; a->cell_start = c->cell_start; a->block_sum = c->block_sum;
+    a->cell_items = c->cell_items; a->cell_xy = c->cell_xy; a->cell_inv = c->cell_inv;
+}
+
+// phases lo..hi of k_iteration_phases (tess_phases.cuh): one cooperative launch, or one launch per
+// phase where grid barriers do not exist (the SIMT emulator; a device without cooperative launch)
+static int run_phases(tess_ctx* c, const Geometry& q, int lo, int hi, int with_update, cudaStream_t s) {
+    TRY(ensure_cells(c, q.n_cells));
+    TessPhaseArgs a;
+    phase_args(c, q, &a);
+#ifndef TESS_EMU
+    if (c->phase_grid == 0) {
+        int per_sm = 0, coop = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_iteration_phases, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+        int cap = 4;
+        if (const char* e = getenv("TESS_PHASE_CTAS")) cap = atoi(e) > 0 ? atoi(e) : cap;      // tuning aid
+        if (per_sm > cap) per_sm = cap;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
+        cudaGetLastError();
+        c->phase_grid = c->sm_count * per_sm;
+        c->coop_ok = coop;
+    }
+    if (c->coop_ok && hi > lo) {
+        void* args[] = {(void*)&a, (void*)&lo, (void*)&hi, (void*)&with_update};
+        ++g_tess_launches;
+        CU_TRY(cudaLaunchCooperativeKernel((const void*)k_iteration_phases, dim3(c->phase_grid), dim3(256), args, 0, s));
+        return TESS_OK;
+    }
+    const int grid = c->phase_grid;
+#else
+    const int grid = 2;          // (every emulated thread is an OS thread: keep the grid small)
+#endif
+    for (int ph = lo; ph <= hi; ++ph) {
+        if (ph == TESS_PH_SCAN && q.n_cells <= TESS_SINGLE_SCAN_MAX) continue;
+        TESS_LAUNCH((k_iteration_phases), grid, 256, s, a, ph, ph, with_update);
+    }
+    CU_TRY(cudaGetLastError());
+    return TESS_OK;
 }
 
 // ---- TMA descriptor of an [H][W] fp64 map with a 32x32-px box (the quadrant tile).  The encoder is a
@@ -754,30 +833,17 @@ extern "C" int tess_get_kernel_timing(tess_ctx* c, double* ms_total, long* launc
 
 extern "C" long tess_launch_count(void) { return g_tess_launches; }
 
-__global__ void k_count_long_lists(const int* q_cnt, long nq, int cap, unsigned long long* out) {
-    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nq && q_cnt[i] > cap) atomicAdd(out, 1ull);
-}
-
+// list diagnostics of the most recent list build, all from one snapshot of the state block:
+// [0] quadrants of tiles that overflowed the builder (per-pixel ring search), [1] arena records used,
+// [2] arena capacity, [3] quadrants whose list is longer than the fast path stages (scanned from L2)
 extern "C" int tess_get_list_stats(tess_ctx* c, long* out4) {
     TRY(bind(c));
     if (!out4) return tess_fail(TESS_ERR_ARG, "tess_get_list_stats: out is null");
     TRY(fetch_state(c, nullptr));
-    out4[0] = c->h_st->n_brute;      // ring-search quadrants + long lists; the latter are subtracted below
+    out4[0] = c->h_st->n_overflow;
     out4[1] = c->h_st->list_cursor;
     out4[2] = c->ql.capacity;
-    out4[3] = 0;
-    const long nq = (long)c->ql.nqx * c->ql.nqy;
-    if (nq > 0 && c->ql.q_cnt) {
-        unsigned long long* d = (unsigned long long*)c->scratch;
-        CU_TRY(cudaMemset(d, 0, 8));
-        const int cap = (c->source == SRC_IMAGE && c->img_mode == 2) ? TESS_QCAP(2) : TESS_QCAP(1);
-        TESS_LAUNCH((k_count_long_lists), (int)((nq + 255) / 256), 256, nullptr, c->ql.q_cnt, nq, cap, d);
-        unsigned long long h = 0;
-        CU_TRY(cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost));
-        out4[3] = (long)h;
-        out4[0] -= (long)h;
-    }
+    out4[3] = c->h_st->n_brute - c->h_st->n_overflow;
     return TESS_OK;
 }
 
@@ -789,44 +855,45 @@ static int check_ready(tess_ctx* c, const char* who) {
 }
 
 // ------------------------------------------------------------------------------------ iteration
+// geometry of the generator grid for the current source (image window or point set)
+static int source_geometry(tess_ctx* c, cudaStream_t s, Geometry* q) {
+    if (c->source == SRC_IMAGE) return image_geometry(c, c->x0, c->y0, c->H, c->W, s, q);
+    TRY(generator_bbox(c, s));
+    *q = box_geometry(c, c->pb);
+    return TESS_OK;
+}
+
+// accumulate without its closing "did anything change" phases (the caller appends them)
+static int accumulate_core(tess_ctx* c, const Geometry& q, cudaStream_t s) {
+    const long n_rows = (long)c->k * n_moments(c);
+    // the generator grid: left behind by the previous update (phases 3-6 of its launch), else built now
+    if (!(c->index_valid && same_grid(q.g, c->index_geo))) TRY(run_phases(c, q, TESS_PH_UPDATE, TESS_PH_SCATTER, 0, s));
+    c->index_valid = 0;
+    if (c->source == SRC_IMAGE) {
+        TRY(build_lists(c, q, 1, c->img_mode, s, c->mom, n_rows));
+        timing_mark(c, s, 0);
+        TRY(run_image(c, q, c->img_mode, 1, nullptr, s));
+        timing_mark(c, s, 1);
+    } else {
+        int grid = (int)((n_rows + 255) / 256);
+        if (grid > c->sm_count * 8) grid = c->sm_count * 8;
+        TESS_LAUNCH((k_clear_moments), grid, 256, s, c->st, 1, c->mom, n_rows);
+        timing_mark(c, s, 0);
+        TRY(run_points(c, q, 1, 1, c->n_pts, c->pts_xy, c->pts_w, nullptr, s));
+        timing_mark(c, s, 1);
+    }
+    CU_TRY(cudaGetLastError());
+    return TESS_OK;
+}
+
 extern "C" int tess_lloyd_accumulate(tess_ctx* c, void* stream) {
     TRY(check_ready(c, "tess_lloyd_accumulate"));
     cudaStream_t s = S(stream);
     TRY(ensure_moments(c));
-    const int M = n_moments(c);
-    const long n_mom = (long)c->k * M + TESS_TAIL;
-    long n;
-    if (c->source == SRC_IMAGE) {
-        Geometry q;
-        TRY(image_geometry(c, c->x0, c->y0, c->H, c->W, s, &q));
-        TRY(build_index(c, q, 1, c->mom, n_mom, s));
-        TRY(build_lists(c, q, 1, c->img_mode, s));
-        timing_mark(c, s, 0);
-        TRY(run_image(c, q, c->img_mode, 1, nullptr, s));
-        timing_mark(c, s, 1);
-        n = c->H * c->W;
-    } else {
-        TRY(generator_bbox(c, s));
-        Geometry q = box_geometry(c, c->pb);
-        TRY(build_index(c, q, 1, c->mom, n_mom, s));
-        timing_mark(c, s, 0);
-        TRY(run_points(c, q, 1, 1, c->n_pts, c->pts_xy, c->pts_w, nullptr, s));
-        timing_mark(c, s, 1);
-        n = c->n_pts;
-    }
-    const int nb = (c->k + 255) / 256;
-    double* tail = c->mom + (long)c->k * M;
-    TESS_LAUNCH((k_count_prefilter), nb, 256, s, c->st, 1, c->mom, M, c->k, c->prev_count, tail);
-    long want = (n + 256L * 8 - 1) / (256L * 8);
-    int grid = (int)(want < 1 ? 1 : (want > c->sm_count * 8 ? c->sm_count * 8 : want));
-    if (c->source == SRC_IMAGE && c->img_mode == 1)
-        TESS_LAUNCH((k_compare_labels<1>), grid, 256, s, c->st, 1, c->lab[0], c->lab[1], n, c->dens, nullptr, nullptr, 0, tail);
-    else if (c->source == SRC_IMAGE)
-        TESS_LAUNCH((k_compare_labels<2>), grid, 256, s, c->st, 1, c->lab[0], c->lab[1], n, nullptr, c->sig, c->noise,
-                                                c->uniform_weight, tail);
-    else
-        TESS_LAUNCH((k_compare_labels<0>), grid, 256, s, c->st, 1, c->lab[0], c->lab[1], n, nullptr, nullptr, nullptr, 0, tail);
-    CU_TRY(cudaGetLastError());
+    Geometry q;
+    TRY(source_geometry(c, s, &q));
+    TRY(accumulate_core(c, q, s));
+    TRY(run_phases(c, q, TESS_PH_PREFILTER, TESS_PH_COMPARE, 1, s));
     return TESS_OK;
 }
 
@@ -893,29 +960,33 @@ extern "C" int tess_peer_allreduce(tess_ctx* c, int world, int rank, double* con
 #endif
 }
 
+// Node update, delta and latch, and -- in the same launch -- the generator grid of the new nodes for the
+// next accumulate (wasted only after the very last iteration: ~10 us).
 extern "C" int tess_lloyd_update(tess_ctx* c, void* stream) {
     TRY(check_ready(c, "tess_lloyd_update"));
     if (!c->mom) return tess_fail(TESS_ERR_STATE, "tess_lloyd_update: no accumulate has run");
     cudaStream_t s = S(stream);
-    const int M = n_moments(c);
-    int nb = (c->k + 255) / 256;
-    if (nb > c->sm_count * 8) nb = c->sm_count * 8;
-    double* tail = c->mom + (long)c->k * M;
-    if (M == 6)
-        TESS_LAUNCH((k_update_nodes<6>), nb, 256, s, c->st, 1, c->mom, tail, c->k, c->node, c->has_scale ? c->scale : nullptr,
-                                            c->inv_s2, c->wvt_update, c->delta_part);
-    else
-        TESS_LAUNCH((k_update_nodes<4>), nb, 256, s, c->st, 1, c->mom, tail, c->k, c->node, nullptr, c->inv_s2, 0,
-                    c->delta_part);
-    TESS_LAUNCH((k_update_finish), 1, 256, s, c->st, tail, c->delta_part, nb, (M == 6 && c->wvt_update && c->has_scale) ? 1 : 0);
-    CU_TRY(cudaGetLastError());
+    Geometry q;
+    TRY(source_geometry(c, s, &q));
+    TRY(run_phases(c, q, TESS_PH_UPDATE, TESS_PH_SCATTER, 1, s));
+    c->index_valid = 1;
+    c->index_geo = q.g;
     return TESS_OK;
 }
 
+// One iteration = list builder + image (or point) kernel + ONE phased launch (change tests, update,
+// latch, next grid).
 extern "C" int tess_lloyd_step(tess_ctx* c, long n_steps, void* stream) {
+    TRY(check_ready(c, "tess_lloyd_step"));
+    cudaStream_t s = S(stream);
     for (long i = 0; i < n_steps; ++i) {
-        TRY(tess_lloyd_accumulate(c, stream));
-        TRY(tess_lloyd_update(c, stream));
+        TRY(ensure_moments(c));
+        Geometry q;
+        TRY(source_geometry(c, s, &q));
+        TRY(accumulate_core(c, q, s));
+        TRY(run_phases(c, q, TESS_PH_PREFILTER, TESS_PH_SCATTER, 1, s));
+        c->index_valid = 1;
+        c->index_geo = q.g;
     }
     return TESS_OK;
 }
@@ -925,7 +996,11 @@ static int fetch_state(tess_ctx* c, cudaStream_t s) {
     CU_TRY(cudaStreamSynchronize(s));
     // generators that drift into a dense clump overflow tiles the coarse grid was not refined for:
     // the host is synchronised here anyway, so let the next accumulate decide the cell size again
-    if (c->source == SRC_IMAGE && c->cell_shift == 0 && c->h_st->n_brute > 0) c->cell_shift = -1;
+    // (true overflows only -- a merely long list does not want a finer grid -- and once per table)
+    if (c->source == SRC_IMAGE && c->cell_shift == 0 && c->h_st->n_overflow > 0 && !c->regrid_tried) {
+        c->cell_shift = -1;
+        c->regrid_tried = 1;
+    }
     return TESS_OK;
 }
 

@@ -81,7 +81,8 @@ struct TessState {
     int flags;                       // TESS_FLAG_*; non-zero also stops the iteration kernels
     int tile_counter;                // quadrant queue of k_image_main (interior); also the scratch of k_cell_occupancy_max
     int have_prev;                   // previous-iteration labels exist
-    int n_brute;                     // quadrants handed to the per-pixel ring search (entries of ring_q)
+    int n_brute;                     // quadrants off the fast path of the image kernel (entries of ring_q)
+    int n_overflow;                  // of those: tiles that overflowed the list builder (per-pixel ring search)
     unsigned list_cursor;            // bump allocator of the candidate-list arena
     unsigned spare_;                 // quadrant queue of k_image_main (edge instantiation)
     unsigned update_ran;             // k_update_nodes did work this iteration (read by k_update_finish)

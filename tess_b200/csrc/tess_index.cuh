@@ -12,12 +12,13 @@
 #include "tess_common.cuh"
 
 // Generator cell + histogram.  Also clears the moment vector of this iteration (grid-stride),
-// because it is the first kernel of an iteration that honours the convergence latch.
-// cell_cnt is all-zero on entry: k_cell_scatter drains it back to zero.
-__global__ void __launch_bounds__(256)
-k_cell_count(const TessState* st, int honor, TessGrid g, const double* node, int k, int* cell_cnt, int* cell_of,
-             double* mom, long n_mom) {
-    if (TESS_STOPPED(st, honor)) return;
+// because it is the first phase of an iteration that honours the convergence latch.
+// cell_cnt is all-zero on entry: the scatter drains it back to zero.
+// (Every O(k) step of the iteration is written as a grid-stride device function `tess_p_*` that works
+//  for any grid of 256-thread CTAs: the stand-alone kernels below wrap them one to one, and
+//  k_iteration_phases (tess_phases.cuh) runs several of them in ONE cooperative launch with grid-wide
+//  barriers in between.)
+TESS_DEVFN void tess_p_cell_count(TessGrid g, const double* node, int k, int* cell_cnt, int* cell_of, double* mom, long n_mom) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long stride = (long)gridDim.x * blockDim.x;
     for (long j = i; j < n_mom; j += stride) mom[j] = 0.0;
@@ -28,6 +29,12 @@ k_cell_count(const TessState* st, int honor, TessGrid g, const double* node, int
         cell_of[j] = c;
         atomicAdd(&cell_cnt[c], 1);
     }
+}
+__global__ void __launch_bounds__(256)
+k_cell_count(const TessState* st, int honor, TessGrid g, const double* node, int k, int* cell_cnt, int* cell_of,
+             double* mom, long n_mom) {
+    if (TESS_STOPPED(st, honor)) return;
+    tess_p_cell_count(g, node, k, cell_cnt, cell_of, mom, n_mom);
 }
 
 // Largest number of generators in one cell of grid g (set-up only: decides how far the grid is
@@ -52,98 +59,133 @@ k_cell_occupancy_max(TessState* st, TessGrid g, const double* node, int k, int* 
 #define TESS_SCAN_THREADS 256
 #define TESS_SCAN_BLOCK (TESS_SCAN_ITEMS * TESS_SCAN_THREADS)
 
+TESS_DEVFN void tess_p_cell_blocksum(const int* cell_cnt, int n_cells, int* block_sum) {
+    __shared__ int s_w[TESS_SCAN_THREADS / 32];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int nsb = (n_cells + TESS_SCAN_BLOCK - 1) / TESS_SCAN_BLOCK;
+    for (int b = blockIdx.x; b < nsb; b += gridDim.x) {
+        const int base = b * TESS_SCAN_BLOCK;
+        int tot = 0;
+#pragma unroll
+        for (int j = 0; j < TESS_SCAN_ITEMS; ++j) {
+            const int i = base + j * TESS_SCAN_THREADS + t;      // coalesced
+            tot += (i < n_cells) ? cell_cnt[i] : 0;
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) tot += __shfl_xor_sync(TESS_FULL, tot, m);
+        __syncthreads();                 // s_w of the previous trip has been read
+        if (lane == 0) s_w[w] = tot;
+        __syncthreads();
+        if (t == 0) {
+            int s = 0;
+            for (int i = 0; i < TESS_SCAN_THREADS / 32; ++i) s += s_w[i];
+            block_sum[b] = s;
+        }
+    }
+}
 __global__ void __launch_bounds__(TESS_SCAN_THREADS)
 k_cell_blocksum(const TessState* st, int honor, const int* cell_cnt, int n_cells, int* block_sum) {
     if (TESS_STOPPED(st, honor)) return;
-    __shared__ int s_w[TESS_SCAN_THREADS / 32];
-    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-    const int base = blockIdx.x * TESS_SCAN_BLOCK;
-    int tot = 0;
-#pragma unroll
-    for (int j = 0; j < TESS_SCAN_ITEMS; ++j) {
-        const int i = base + j * TESS_SCAN_THREADS + t;      // coalesced
-        tot += (i < n_cells) ? cell_cnt[i] : 0;
-    }
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) tot += __shfl_xor_sync(TESS_FULL, tot, m);
-    if (lane == 0) s_w[w] = tot;
-    __syncthreads();
-    if (t == 0) {
-        int s = 0;
-        for (int i = 0; i < TESS_SCAN_THREADS / 32; ++i) s += s_w[i];
-        block_sum[blockIdx.x] = s;
-    }
+    tess_p_cell_blocksum(cell_cnt, n_cells, block_sum);
 }
 
-__global__ void __launch_bounds__(TESS_SCAN_THREADS)
-k_cell_scan(TessState* st, int honor, const int* cell_cnt, int* cell_start, int n_cells, const int* block_sum) {
-    if (TESS_STOPPED(st, honor)) return;
+// Scalars of the state block that belong to one list build (done by one thread while the cells are
+// scanned).  (flags_next is never cleared here: once raised the iteration is over until
+// tess_set_generators resets the whole block, and other CTAs of a phased launch may be reading it.)
+TESS_DEVFN void tess_reset_iteration_scalars(TessState* st, int honor) {
+    (void)honor;
+    st->list_cursor = 0u;
+    st->tile_counter = 0;      // quadrant queues of the interior / edge image kernels
+    st->spare_ = 0u;
+    st->n_brute = 0;
+    st->n_overflow = 0;
+}
+// Scalars that one accumulate + update pair produces (done by one thread of the first kernel of the
+// accumulate): they stay readable -- tess_get_iter_stats -- until the next accumulate starts.
+TESS_DEVFN void tess_reset_accumulate_scalars(TessState* st) {
+    st->n_changed = 0ull;
+    st->count_changed = 0;
+    st->counted = 0;
+    st->min_inv_next = 0x7ff0000000000000ull;   // +inf
+}
+
+TESS_DEVFN void tess_p_cell_scan(TessState* st, int honor, const int* cell_cnt, int* cell_start, int n_cells, const int* block_sum) {
     __shared__ int s_w[TESS_SCAN_THREADS / 32];
     __shared__ int s_base;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-    // totals of the preceding blocks (a few hundred at most)
-    int pre = 0;
-    for (int i = t; i < (int)blockIdx.x; i += TESS_SCAN_THREADS) pre += block_sum[i];
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) pre += __shfl_xor_sync(TESS_FULL, pre, m);
-    if (lane == 0) s_w[w] = pre;
-    __syncthreads();
-    if (t == 0) {
-        int s = 0;
-        for (int i = 0; i < TESS_SCAN_THREADS / 32; ++i) s += s_w[i];
-        s_base = s;
-    }
-    __syncthreads();
-    const int carry = s_base;
-    __syncthreads();
-    const int i0 = blockIdx.x * TESS_SCAN_BLOCK + t * TESS_SCAN_ITEMS;
-    int v[TESS_SCAN_ITEMS];
-#pragma unroll
-    for (int j = 0; j < TESS_SCAN_ITEMS; ++j) v[j] = (i0 + j < n_cells) ? cell_cnt[i0 + j] : 0;
-    int tot = 0;
-#pragma unroll
-    for (int j = 0; j < TESS_SCAN_ITEMS; ++j) { const int x = v[j]; v[j] = tot; tot += x; }   // local exclusive
-    int inc = tot;                                                                           // warp inclusive
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int y = __shfl_up_sync(TESS_FULL, inc, d);
-        if (lane >= d) inc += y;
-    }
-    if (lane == 31) s_w[w] = inc;
-    __syncthreads();
-    int woff = 0;
-    for (int i = 0; i < w; ++i) woff += s_w[i];
-    const int off = carry + woff + (inc - tot);
-#pragma unroll
-    for (int j = 0; j < TESS_SCAN_ITEMS; ++j)
-        if (i0 + j < n_cells) cell_start[i0 + j] = off + v[j];
-    if (i0 <= n_cells - 1 && n_cells - 1 < i0 + TESS_SCAN_ITEMS) cell_start[n_cells] = off + tot;   // owner of the last cell
-    if (blockIdx.x == 0 && t == 0) {
-        if (honor) {   // part of a Lloyd iteration (not a stand-alone assignment query)
-            st->delta = 0.0;
-            st->n_changed = 0ull;
-            st->count_changed = 0;
-            st->counted = 0;
-            st->min_inv_next = 0x7ff0000000000000ull;   // +inf
+    const int nsb = (n_cells + TESS_SCAN_BLOCK - 1) / TESS_SCAN_BLOCK;
+    for (int b = blockIdx.x; b < nsb; b += gridDim.x) {
+        // totals of the preceding blocks (a few hundred at most), or -- no block sums -- of the preceding cells
+        int pre = 0;
+        if (block_sum) {
+            for (int i = t; i < b; i += TESS_SCAN_THREADS) pre += block_sum[i];
+        } else {
+            for (int i = t; i < b * TESS_SCAN_BLOCK; i += TESS_SCAN_THREADS) pre += cell_cnt[i];
         }
-        st->list_cursor = 0u;
-        st->tile_counter = 0;      // quadrant queues of the interior / edge image kernels
-        st->spare_ = 0u;
-        st->n_brute = 0;
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) pre += __shfl_xor_sync(TESS_FULL, pre, m);
+        __syncthreads();
+        if (lane == 0) s_w[w] = pre;
+        __syncthreads();
+        if (t == 0) {
+            int s = 0;
+            for (int i = 0; i < TESS_SCAN_THREADS / 32; ++i) s += s_w[i];
+            s_base = s;
+        }
+        __syncthreads();
+        const int carry = s_base;
+        __syncthreads();
+        const int i0 = b * TESS_SCAN_BLOCK + t * TESS_SCAN_ITEMS;
+        int v[TESS_SCAN_ITEMS];
+#pragma unroll
+        for (int j = 0; j < TESS_SCAN_ITEMS; ++j) v[j] = (i0 + j < n_cells) ? cell_cnt[i0 + j] : 0;
+        int tot = 0;
+#pragma unroll
+        for (int j = 0; j < TESS_SCAN_ITEMS; ++j) { const int x = v[j]; v[j] = tot; tot += x; }   // local exclusive
+        int inc = tot;                                                                           // warp inclusive
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(TESS_FULL, inc, d);
+            if (lane >= d) inc += y;
+        }
+        if (lane == 31) s_w[w] = inc;
+        __syncthreads();
+        int woff = 0;
+        for (int i = 0; i < w; ++i) woff += s_w[i];
+        const int off = carry + woff + (inc - tot);
+#pragma unroll
+        for (int j = 0; j < TESS_SCAN_ITEMS; ++j)
+            if (i0 + j < n_cells) cell_start[i0 + j] = off + v[j];
+        if (i0 <= n_cells - 1 && n_cells - 1 < i0 + TESS_SCAN_ITEMS) cell_start[n_cells] = off + tot;   // owner of the last cell
     }
+    if (blockIdx.x == 0 && t == 0) tess_reset_iteration_scalars(st, honor);
+}
+__global__ void __launch_bounds__(TESS_SCAN_THREADS)
+k_cell_scan(TessState* st, int honor, const int* cell_cnt, int* cell_start, int n_cells, const int* block_sum) {
+    if (TESS_STOPPED(st, honor)) return;
+    tess_p_cell_scan(st, honor, cell_cnt, cell_start, n_cells, block_sum);
 }
 
+// Grids of up to TESS_SINGLE_SCAN_MAX cells are scanned WITHOUT the block-sum phase (and its grid
+// barrier): tess_p_cell_scan with block_sum == nullptr lets every scan block add up the cells that
+// precede it by itself (coalesced; at most 16 blocks of 4096 cells, i.e. 256 KB of reads per CTA).
+#define TESS_SINGLE_SCAN_MAX 65536
+
+TESS_DEVFN void tess_p_cell_scatter(const int* cell_of, int k, const int* cell_start, int* cell_cnt, const double* node,
+                                    const double* inv_s2, int* cell_items, double2* cell_xy, double* cell_inv) {
+    for (long j = (long)blockIdx.x * blockDim.x + threadIdx.x; j < k; j += (long)gridDim.x * blockDim.x) {
+        const int c = cell_of[j];
+        const int pos = cell_start[c] + atomicSub(&cell_cnt[c], 1) - 1;
+        cell_items[pos] = (int)j;
+        cell_xy[pos] = make_double2(node[2 * j], node[2 * j + 1]);
+        if (inv_s2) cell_inv[pos] = inv_s2[j];
+    }
+}
 __global__ void __launch_bounds__(256)
 k_cell_scatter(const TessState* st, int honor, const int* cell_of, int k, const int* cell_start, int* cell_cnt,
                const double* node, const double* inv_s2, int* cell_items, double2* cell_xy, double* cell_inv) {
     if (TESS_STOPPED(st, honor)) return;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= k) return;
-    const int c = cell_of[j];
-    const int pos = cell_start[c] + atomicSub(&cell_cnt[c], 1) - 1;
-    cell_items[pos] = j;
-    cell_xy[pos] = make_double2(node[2 * (long)j], node[2 * (long)j + 1]);
-    if (inv_s2) cell_inv[pos] = inv_s2[j];
+    tess_p_cell_scatter(cell_of, k, cell_start, cell_cnt, node, inv_s2, cell_items, cell_xy, cell_inv);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -198,8 +240,13 @@ struct TessQLists {
 template <bool HAS_SCALE>
 __global__ void __launch_bounds__(TESS_LIST_WARPS * 32)
 k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cell_start, const int* cell_items,
-               const double2* cell_xy, const double* cell_inv, TessQLists L, int* tile_ring, int dense, int qcap) {
+               const double2* cell_xy, const double* cell_inv, TessQLists L, int* tile_ring, int dense, int qcap,
+               double* mom_clear, long n_clear) {
     if (TESS_STOPPED(st, honor)) return;
+    // first kernel of an accumulate in image mode: the moment rows of the previous iteration go
+    // (their tail slots were cleared with the scan of the generator grid)
+    for (long j = (long)blockIdx.x * blockDim.x + threadIdx.x; j < n_clear; j += (long)gridDim.x * blockDim.x) mom_clear[j] = 0.0;
+    if (honor && blockIdx.x == 0 && threadIdx.x == 0) tess_reset_accumulate_scalars(st);
     __shared__ __align__(16) double2 s_xy[TESS_LIST_WARPS][TESS_CAP];
     __shared__ double s_iv[HAS_SCALE ? TESS_LIST_WARPS : 1][HAS_SCALE ? TESS_CAP : 1];
     __shared__ unsigned s_key[TESS_LIST_WARPS][TESS_CAP];
@@ -238,7 +285,7 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
                     const long qid = (long)(2 * ty + (q >> 1)) * L.nqx + (2 * tx + (q & 1));
                     L.q_off[qid] = 0;
                     L.q_cnt[qid] = in ? -1 : 0;
-                    if (in) L.ring_q[atomicAdd(&st->n_brute, 1)] = (int)qid;
+                    if (in) { L.ring_q[atomicAdd(&st->n_brute, 1)] = (int)qid; atomicAdd(&st->n_overflow, 1); }
                 }
                 continue;
             }
@@ -464,7 +511,10 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
                 L.q_cnt[qid] = !qin[q] ? 0 : (ok ? nq_[q] : -1);
                 // off the fast path of the image kernel (overflow, or a list longer than it stages):
                 // queued for its tail phase
-                if (qin[q] && (!ok || nq_[q] > qcap)) L.ring_q[atomicAdd(&st->n_brute, 1)] = (int)qid;
+                if (qin[q] && (!ok || nq_[q] > qcap)) {
+                    L.ring_q[atomicAdd(&st->n_brute, 1)] = (int)qid;
+                    if (!ok) atomicAdd(&st->n_overflow, 1);     // a true overflow (not merely a long list)
+                }
             }
             if (ok && qin[q]) {
                 int wpos = 0;

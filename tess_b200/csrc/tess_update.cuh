@@ -16,44 +16,48 @@
 // reported as 0), which reproduces the reference's bitwise node_{t+1} == node_t.
 #pragma once
 #include "tess_common.cuh"
+#include "tess_index.cuh"
 
 // moment-vector tail layout (after k*M doubles)
 #define TESS_TAIL 2
 #define TESS_TAIL_CHANGED 0   // sum over ranks of (labels changed ? 1 : 0)
 #define TESS_TAIL_SPARE 1
 
-__global__ void __launch_bounds__(256)
-k_count_prefilter(TessState* st, int honor, const double* mom, int M, int k, double* prev_count, double* mom_tail) {
-    if (TESS_STOPPED(st, honor)) return;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    bool diff = false;
-    if (j < k) {
-        const double c = mom[(long)j * M];
-        diff = (c != prev_count[j]);
-        prev_count[j] = c;
+TESS_DEVFN void tess_p_count_prefilter(TessState* st, const double* mom, int M, int k, double* prev_count, double* mom_tail) {
+    // whole warps walk the table together (the vote below), one store per warp at most (every writer
+    // stores the same value; a store per thread would serialise in L2).  The tail slot was zeroed
+    // together with the moments.
+    for (long base = (long)blockIdx.x * blockDim.x; base < k; base += (long)gridDim.x * blockDim.x) {
+        const long j = base + threadIdx.x;
+        bool diff = false;
+        if (j < k) {
+            const double c = mom[j * M];
+            diff = (c != prev_count[j]);
+            prev_count[j] = c;
+        }
+        if (__any_sync(TESS_FULL, diff) && (threadIdx.x & 31) == 0) {
+            st->count_changed = 1;
+            mom_tail[TESS_TAIL_CHANGED] = 1.0;
+        }
     }
-    // one store per warp at most (every writer stores the same value; a store per thread would
-    // serialise in L2).  The tail slot was zeroed together with the moments.
-    if (__any_sync(TESS_FULL, diff) && (threadIdx.x & 31) == 0) {
-        st->count_changed = 1;
-        mom_tail[TESS_TAIL_CHANGED] = 1.0;
-    }
-    if (j == 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
         st->last_parity = (int)(st->iters_done & 1);
         if (!st->have_prev) mom_tail[TESS_TAIL_CHANGED] = 1.0;   // nothing to compare with yet
     }
+}
+__global__ void __launch_bounds__(256)
+k_count_prefilter(TessState* st, int honor, const double* mom, int M, int k, double* prev_count, double* mom_tail) {
+    if (TESS_STOPPED(st, honor)) return;
+    tess_p_count_prefilter(st, mom, M, k, prev_count, mom_tail);
 }
 
 // Compares the two label buffers on the pixels/points that take part in the sums.
 // MASK_MODE 0: all; 1: finite density; 2: finite signal, noise and weight
 // No fences, no "last block" tail: the flag is an idempotent store, ordering comes from the
-// kernel boundaries (a device-wide fence in a streaming kernel drains the SM's memory pipeline
-// and costs far more than an extra launch).
-template <int MASK_MODE>
-__global__ void __launch_bounds__(256)
-k_compare_labels(TessState* st, int honor, int32_t* lab0, int32_t* lab1, long n, const double* dens,
-                 const double* sig, const double* noise, int uniform_weight, double* mom_tail) {
-    if (TESS_STOPPED(st, honor)) return;
+// kernel boundaries / grid barriers (a device-wide fence in a streaming kernel drains the SM's
+// memory pipeline and costs far more than an extra launch).
+TESS_DEVFN void tess_p_compare_labels(TessState* st, int mask_mode, int32_t* lab0, int32_t* lab1, long n, const double* dens,
+                                      const double* sig, const double* noise, int uniform_weight, double* mom_tail) {
     const bool need = (!st->count_changed) && st->have_prev;
     if (blockIdx.x == 0 && threadIdx.x == 0) st->counted = need ? 1 : 0;
     if (!need) return;
@@ -64,8 +68,8 @@ k_compare_labels(TessState* st, int honor, int32_t* lab0, int32_t* lab1, long n,
     unsigned long long diff = 0;
     for (; i < n; i += stride) {
         bool ok = true;
-        if (MASK_MODE == 1) ok = isfinite(dens[i]);
-        if (MASK_MODE == 2) {
+        if (mask_mode == 1) ok = isfinite(dens[i]);
+        if (mask_mode == 2) {
             const double S = sig[i], N = noise[i];
             double wv = 1.0;
             if (!uniform_weight) { const double q = __ddiv_rn(S, N); wv = __dmul_rn(q, q); }
@@ -79,6 +83,13 @@ k_compare_labels(TessState* st, int honor, int32_t* lab0, int32_t* lab1, long n,
         mom_tail[TESS_TAIL_CHANGED] = 1.0;
     }
 }
+template <int MASK_MODE>
+__global__ void __launch_bounds__(256)
+k_compare_labels(TessState* st, int honor, int32_t* lab0, int32_t* lab1, long n, const double* dens,
+                 const double* sig, const double* noise, int uniform_weight, double* mom_tail) {
+    if (TESS_STOPPED(st, honor)) return;
+    tess_p_compare_labels(st, MASK_MODE, lab0, lab1, n, dens, sig, noise, uniform_weight, mom_tail);
+}
 
 // 128-bit global load the compiler may not split or sink below a dependent branch
 TESS_DEVFN double2 tess_ld2(const double* p) {
@@ -91,25 +102,26 @@ TESS_DEVFN double2 tess_ld2(const double* p) {
 #endif
 }
 
-// One thread per generator.  `mom` holds the (globally reduced) moments, `mom_tail` the summed
-// "changed" flags.  Nodes are rewritten in place unless the latch closes.
+// One thread per generator (grid-stride).  `mom` holds the (globally reduced) moments, `mom_tail` the
+// summed "changed" flags.  Nodes are rewritten in place unless the latch closes.
+// With `cell_cnt` the thread also drops its NEW node into the histogram of the generator grid `g` (the
+// first step of the next iteration's counting sort: it needs nothing but the node just computed).
 template <int M>
-__global__ void __launch_bounds__(256)
-k_update_nodes(TessState* st, int honor, const double* mom, const double* mom_tail, int k, double* node,
-               double* scale, double* inv_s2, int wvt_update, double* delta_part) {
-    if (TESS_STOPPED(st, honor)) return;
+TESS_DEVFN void tess_p_update_nodes(TessState* st, const double* mom, const double* mom_tail, int k, double* node,
+                                    double* scale, double* inv_s2, int wvt_update, double* delta_part,
+                                    const TessGrid* g = nullptr, int* cell_cnt = nullptr, int* cell_of = nullptr) {
     __shared__ double s_red[8];
     const bool changed = mom_tail[TESS_TAIL_CHANGED] != 0.0;
     if (changed) {
         double d = 0.0;
-        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < k; j += gridDim.x * blockDim.x) {
-            const double* m = mom + (long)j * M;
+        for (long j = (long)blockIdx.x * blockDim.x + threadIdx.x; j < k; j += (long)gridDim.x * blockDim.x) {
+            const double* m = mom + j * M;
             // the moment row as 128-bit loads (rows are 32 or 48 bytes, 16-byte aligned)
             const double2 m01 = tess_ld2(m), m23 = tess_ld2(m + 2);
             // the old node is loaded together with the moments: issued after the divide (one more
             // dependent DRAM round trip, interleaved with the node stores) the kernel measured 5x slower
             double2* np = reinterpret_cast<double2*>(node) + j;
-            const double2 old = tess_ld2(node + 2 * (long)j);
+            const double2 old = tess_ld2(node + 2 * j);
             double nx = 0.0, ny = 0.0;
             if (m01.x > 0.0) {   // population test, not weight (lloyd.pyx:68)
                 nx = __ddiv_rn(m23.x, m01.y);
@@ -121,6 +133,11 @@ k_update_nodes(TessState* st, int honor, const double* mom, const double* mom_ta
             const double dx = __dsub_rn(old.x, nx), dy = __dsub_rn(old.y, ny);
             d = __dadd_rn(d, __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
             *np = make_double2(nx, ny);
+            if (cell_cnt) {
+                const int c = tess_cell_coord(ny, g->oy, g->inv_cs, g->gh) * g->gw + tess_cell_coord(nx, g->ox, g->inv_cs, g->gw);
+                cell_of[j] = c;
+                atomicAdd(&cell_cnt[c], 1);
+            }
             if (M == 6 && wvt_update && scale) {
                 // WVT scale length (Diehl & Statler 2006 eq. 4, as in vorbin): sqrt(area / (S/N));
                 // bins with no pixels or no signal keep their scale.
@@ -140,22 +157,27 @@ k_update_nodes(TessState* st, int honor, const double* mom, const double* mom_ta
         if (threadIdx.x < 32) {
             double v = (threadIdx.x < (blockDim.x >> 5)) ? s_red[threadIdx.x] : 0.0;
             v = tess_warp_sum(v);
-            // one partial per CTA, summed by k_update_finish
+            // one partial per CTA, summed by the finish step
             if (threadIdx.x == 0) delta_part[blockIdx.x] = v;
         }
     }
-    // "this update ran" marker for k_update_finish (a flag raised in the loop above must not make
-    // the finish kernel skip the bookkeeping of this iteration)
+    // "this update ran" marker for the finish step (a flag raised in the loop above must not make
+    // it skip the bookkeeping of this iteration)
     if (blockIdx.x == 0 && threadIdx.x == 0) st->update_ran = 1u;
 }
-
-// Single CTA, launched right after k_update_nodes: sums the per-CTA deltas and advances the
-// iteration state (latch lloyd.pyx:85-86).  A separate launch instead of a "last block done"
-// tail: the device-wide fences that pattern needs cost ~90 us per update at k = 1e6 on cold
-// lines, an extra launch costs ~2 us.
+template <int M>
 __global__ void __launch_bounds__(256)
-k_update_finish(TessState* st, const double* mom_tail, const double* delta_part, int n_part, int wvt_scales) {
-    if (st->update_ran != 1u) return;   // k_update_nodes was a no-op (latch closed or error flag up)
+k_update_nodes(TessState* st, int honor, const double* mom, const double* mom_tail, int k, double* node,
+               double* scale, double* inv_s2, int wvt_update, double* delta_part) {
+    if (TESS_STOPPED(st, honor)) return;
+    tess_p_update_nodes<M>(st, mom, mom_tail, k, node, scale, inv_s2, wvt_update, delta_part);
+}
+
+// One CTA, right after the node update: sums the per-CTA deltas and advances the iteration state
+// (latch lloyd.pyx:85-86).  A separate step instead of a "last block done" tail: the device-wide
+// fences that pattern needs cost ~90 us per update at k = 1e6 on cold lines.
+TESS_DEVFN void tess_p_update_finish(TessState* st, const double* mom_tail, const double* delta_part, int n_part, int wvt_scales) {
+    if (st->update_ran != 1u) return;   // the node update was a no-op (latch closed or error flag up)
     __shared__ double s_red[8];
     const bool changed = mom_tail[TESS_TAIL_CHANGED] != 0.0;
     double tot = 0.0;
@@ -179,9 +201,21 @@ k_update_finish(TessState* st, const double* mom_tail, const double* delta_part,
         st->iters_done += 1;
         st->have_prev = 1;
         st->update_ran = 0u;
-        st->flags |= st->flags_next;
-        st->flags_next = 0;
+        st->flags |= st->flags_next;      // (flags_next itself is cleared with the per-iteration scalars: other
+                                          //  CTAs of a phased launch may still be reading it)
     }
+}
+__global__ void __launch_bounds__(256)
+k_update_finish(TessState* st, const double* mom_tail, const double* delta_part, int n_part, int wvt_scales) {
+    tess_p_update_finish(st, mom_tail, delta_part, n_part, wvt_scales);
+}
+
+// moment rows of the previous iteration -> 0 (point mode; image mode clears them in the list builder)
+__global__ void __launch_bounds__(256)
+k_clear_moments(TessState* st, int honor, double* mom, long n) {
+    if (TESS_STOPPED(st, honor)) return;
+    for (long j = (long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long)gridDim.x * blockDim.x) mom[j] = 0.0;
+    if (honor && blockIdx.x == 0 && threadIdx.x == 0) tess_reset_accumulate_scalars(st);
 }
 
 // finiteness of the generator table / scales, inv_s2 (run at set_generators)
