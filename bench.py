@@ -273,7 +273,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample clocks during the timed region")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-single", action="store_true", help="N>1: skip rank 0's one-GPU run of the same map")
+    ap.add_argument("--no-single", action="store_true", help="N>1: skip rank 0's one-GPU run of the same map (and the parity check against it)")
+    ap.add_argument("--no-extras", action="store_true", help="N=1: skip the other-mode and the sustained measurements")
+    ap.add_argument("--sustain-s", type=float, default=2.0, help="N=1: length of the sustained run in seconds")
     ap.add_argument("--no-balance", dest="balance", action="store_false",
                     help="N>1: equal-height row shards instead of cost-balanced ones")
     ap.add_argument("--trace-steps", action="store_true",
@@ -410,11 +412,28 @@ def main():
     if k_n > 0:
         k_ms_avg = k_ms / k_n
         alg_bytes = BYTES_PER_PX[mode] * float(r1 - r0) * N          # per launch (this rank's rows)
+        per_rank = None
+        if world > 1:
+            # every rank's kernel time and bytes: the line reports the SLOWEST rank (the one the step
+            # waits for) and the aggregate over the machine, not rank 0's shard
+            t = torch.tensor([k_ms_avg, alg_bytes], dtype=torch.float64, device=device)
+            allk = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allk, t)
+            per_rank = [(float(x[0].item()), float(x[1].item())) for x in allk]
+            slow = max(range(world), key=lambda i: per_rank[i][0])
+            k_ms_avg, alg_bytes = per_rank[slow]
         ach = alg_bytes / (k_ms_avg * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                 "kernel": "k_image_main", "kernel_ms": k_ms_avg, "kernel_share_of_step": k_ms_avg / ms_step,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "step_frac_of_roofline": (BYTES_PER_PX[mode] * float(N) * N / world / (ms_step * 1e-3) / 1e9) / peak}
+        if per_rank is not None:
+            tot_b = sum(b for _, b in per_rank)
+            t_max = max(ms for ms, _ in per_rank)
+            roof["rank"] = "slowest of %d (rank %d)" % (world, slow)
+            roof["aggregate_frac"] = (tot_b / world / (t_max * 1e-3) / 1e9) / peak
+            roof["per_rank_kernel_ms"] = [round(ms, 4) for ms, _ in per_rank]
+            roof["per_rank_frac"] = [round(b / (ms * 1e-3) / 1e9 / peak, 4) for ms, b in per_rank]
         tf = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes per launch from the ncu --set full capture
         if os.path.exists(tf):
             try:
@@ -518,13 +537,41 @@ def main():
         e2.close()
         del host_in, lab_pin
 
-    # ---- N > 1: the same map on ONE GPU (rank 0), so the speed-up is apples to apples
+    # ---- N > 1: the same map on ONE GPU (rank 0), so the speed-up is apples to apples -- and an untimed
+    #      parity check of the sharded path against it: after T identical iterations from the same
+    #      seeds the generator tables agree to 1e-9 px, rank 0's whole shard and every rank's first
+    #      and last row carry the same labels, and all ranks hold bit-identical tables
     single = None
+    parity = None
     if world > 1 and not args.no_single:
+        T_CHECK = 3
         barrier()
+        drv.set_generators(seeds)
+        drv.step(T_CHECK)
+        g_sh = drv.generators()
+        lab_sh = drv.local_labels()
+        edge = torch.stack((lab_sh[0], lab_sh[-1])).contiguous()               # this rank's boundary rows
+        edges = [torch.empty_like(edge) for _ in range(world)] if rank == 0 else None
+        dist.gather(edge, edges, dst=0)
+        h = (g_sh.view(torch.int64) * torch.arange(1, g_sh.numel() + 1, device=device).view_as(g_sh)).sum().view(1)
+        hs = [torch.zeros_like(h) for _ in range(world)]
+        dist.all_gather(hs, h)
+        identical = all(int(x.item()) == int(hs[0].item()) for x in hs)
         if rank == 0:
             e1 = Engine(local)
             setup(e1, 0, N)
+            e1.step(T_CHECK)
+            g1 = e1.generators()
+            lab1 = e1.labels()
+            dg = float((g1 - g_sh).abs().max().item())
+            shard_equal = bool(torch.equal(lab1[r0:r1], lab_sh))
+            edges_equal = all(bool(torch.equal(edges[i][0], lab1[shards[i][0]])) and
+                              bool(torch.equal(edges[i][1], lab1[shards[i][1] - 1])) for i in range(world))
+            parity = {"ok": bool(dg <= 1e-9 and shard_equal and edges_equal and identical), "iterations": T_CHECK,
+                      "max_abs_generator_diff_px": dg, "rank0_shard_labels_equal": shard_equal,
+                      "boundary_rows_labels_equal": edges_equal, "tables_bit_identical_on_all_ranks": identical}
+            del lab1, g1
+            e1.set_generators(seeds)
             e1.step(args.warmup)
             torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -533,7 +580,62 @@ def main():
             single = {"ms_per_step": ms1, "value": (float(N) * N) / (ms1 * 1e-3) / 1e9, "unit": UNIT,
                       "speedup": ms1 / ms_step}
             e1.close()
+        del lab_sh, g_sh
         barrier()
+
+    # ---- N = 1: the other mode of the same workload and a seconds-long run
+    modes = None
+    sustained = None
+    if world == 1 and fake is None and not args.no_extras:
+        other = "sn" if mode == "cvt" else "cvt"
+        eo = Engine(local)
+        sig = device_signal_rows(N, 0, N, torch, device)
+        if other == "sn":
+            noise_o = torch.ones_like(sig)
+            eo.set_image(signal=sig, noise=noise_o)
+        else:
+            dens_o = sig ** 2
+            eo.set_image(density=dens_o)
+        eo.set_generators(seeds)
+        eo.step(args.warmup)
+        eo.set_option(_capi.OPT_KERNEL_TIMING, 1)
+        eo.kernel_timing()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); eo.step(args.steps); b.record(); torch.cuda.synchronize()
+        ko_ms, ko_n = eo.kernel_timing()
+        eo.set_option(_capi.OPT_KERNEL_TIMING, 0)
+        mso = a.elapsed_time(b) / args.steps
+        bo = BYTES_PER_PX[other] * float(N) * N
+        modes = {other: {"ms_per_step": mso, "value": float(N) * N / (mso * 1e-3) / 1e9, "unit": UNIT,
+                         "bytes_per_px": BYTES_PER_PX[other], "kernel_ms": ko_ms / max(ko_n, 1),
+                         "kernel_frac": bo / (ko_ms / max(ko_n, 1) * 1e-3) / 1e9 / peak,
+                         "step_frac_of_roofline": bo / (mso * 1e-3) / 1e9 / peak}}
+        eo.close()
+        del eo, sig
+        # sustained: >= 2 s of back-to-back iterations (chunks of 500, restarted from the seeds so that
+        # the run never reaches the convergence latch), clocks sampled throughout
+        samp2 = ClockSampler(local)
+        if not args.no_clocks:
+            samp2.start()
+        eng.set_generators(seeds)
+        eng.step(args.warmup)
+        torch.cuda.synchronize()
+        samp2.active = True
+        tot_ms, tot_it = 0.0, 0
+        while tot_ms < args.sustain_s * 1e3 and tot_it < 200000:
+            eng.set_generators(seeds)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); eng.step(500); b.record(); torch.cuda.synchronize()
+            if eng.status()[0]:
+                break
+            tot_ms += a.elapsed_time(b); tot_it += 500
+        ck = samp2.stop() if not args.no_clocks else None
+        if tot_it:
+            sustained = {"seconds": tot_ms * 1e-3, "iterations": tot_it, "ms_per_step": tot_ms / tot_it,
+                         "value": float(N) * N / (tot_ms / tot_it * 1e-3) / 1e9, "unit": UNIT,
+                         "step_frac_of_roofline": BYTES_PER_PX[mode] * float(N) * N / (tot_ms / tot_it * 1e-3) / 1e9 / peak,
+                         "clocks": ck}
 
     # ---- CPU baseline: the compiled reference on a bounded slab (rank 0, N = 1 only)
     cpu = None
@@ -560,6 +662,12 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roof, "cpu_baseline": cpu}
         if single is not None:
             line["single_gpu_same_workload"] = single
+        if parity is not None:
+            line["parity_check"] = parity
+        if modes is not None:
+            line["modes"] = modes
+        if sustained is not None:
+            line["sustained"] = sustained
         if breakdown is not None:
             line["per_rank_breakdown"] = breakdown
         sys.stdout.flush()

@@ -160,6 +160,19 @@ int tess_set_moment_buffer(tess_ctx* ctx, double* buf, long n_doubles);
 int tess_peer_allreduce(tess_ctx* ctx, int world, int rank, double* const* peer_ptrs, double* multicast_ptr,
                         long n_doubles, void* stream);
 
+/*
+ * Sparse form of the same exchange, for generator tables numbered in spatial order (rows of a rank's
+ * pixel shard then touch one short range of bins).  tess_peer_publish_range (after
+ * tess_lloyd_accumulate, before the first barrier) writes the first and last bin with a non-zero
+ * local count into the LAST TWO doubles of the caller's buffer (which must therefore hold
+ * >= k*M + 2 + 2 doubles; its size must be the same on every rank); tess_peer_allreduce_sparse
+ * then reads a row only from the peers whose published range holds it and broadcasts the totals
+ * to all -- bit-identical to the dense sum, since the skipped rows are exact zeros.  The range
+ * is reset by tess_lloyd_update.  `n_doubles` is the summed length (tess_moments_ptr).
+ */
+int tess_peer_publish_range(tess_ctx* ctx, void* stream);
+int tess_peer_allreduce_sparse(tess_ctx* ctx, int world, int rank, double* const* peer_ptrs, long n_doubles, void* stream);
+
 /* n_steps iterations back to back, no host synchronisation (benchmarks, fixed-step use). */
 int tess_lloyd_step(tess_ctx* ctx, long n_steps, void* stream);
 

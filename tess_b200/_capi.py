@@ -41,6 +41,8 @@ SIGNATURES = {
     "tess_moments_ptr": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_l), ctypes.POINTER(_i)]),
     "tess_set_moment_buffer": (_i, [_vp, _vp, _l]),
     "tess_peer_allreduce": (_i, [_vp, _i, _i, ctypes.POINTER(_vp), _vp, _l, _vp]),
+    "tess_peer_publish_range": (_i, [_vp, _vp]),
+    "tess_peer_allreduce_sparse": (_i, [_vp, _i, _i, ctypes.POINTER(_vp), _l, _vp]),
     "tess_lloyd_update": (_i, [_vp, _vp]),
     "tess_lloyd_step": (_i, [_vp, _l, _vp]),
     "tess_lloyd_run": (_i, [_vp, _l, ctypes.POINTER(_i), ctypes.POINTER(_l), _vp]),

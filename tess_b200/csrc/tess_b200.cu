@@ -919,14 +919,51 @@ extern "C" int tess_set_moment_buffer(tess_ctx* c, double* buf, long n_doubles) 
     c->mom = buf;
     c->mom_cap = n_doubles;
     c->mom_external = 1;
+    // the two slots behind the vector that tess_peer_publish_range fills (sparse exchange): empty range
+    TESS_LAUNCH((k_reset_range), 1, 1, nullptr, reinterpret_cast<unsigned long long*>(buf + n_doubles - TESS_RANGE_SLOTS));
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(nullptr));
     return TESS_OK;
 }
 
+// slots of the published row range, or null when the caller's buffer has no room for them
+static unsigned long long* range_slots(tess_ctx* c) {
+    if (!c->mom_external || !c->mom) return nullptr;
+    const long used = (long)c->k * n_moments(c) + TESS_TAIL;
+    if (c->mom_cap < used + TESS_RANGE_SLOTS || ((c->mom_cap - TESS_RANGE_SLOTS) & 1)) return nullptr;
+    return reinterpret_cast<unsigned long long*>(c->mom + c->mom_cap - TESS_RANGE_SLOTS);
+}
+
+extern "C" int tess_peer_publish_range(tess_ctx* c, void* stream) {
+    TRY(check_ready(c, "tess_peer_publish_range"));
+    unsigned long long* r = range_slots(c);
+    if (!r) return tess_fail(TESS_ERR_STATE, "tess_peer_publish_range: needs a moment buffer from tess_set_moment_buffer with "
+                                             "%d spare doubles behind the vector", TESS_RANGE_SLOTS);
+    int nb = (c->k + 255) / 256;
+    if (nb > c->sm_count * 8) nb = c->sm_count * 8;
+    TESS_LAUNCH((k_touched_range), nb, 256, S(stream), c->st, c->mom, n_moments(c), c->k, r);
+    CU_TRY(cudaGetLastError());
+    return TESS_OK;
+}
+
+static int peer_allreduce(tess_ctx* c, int world, int rank, double* const* peer_ptrs, double* multicast_ptr,
+                          long n_doubles, int sparse, void* stream);
+
 extern "C" int tess_peer_allreduce(tess_ctx* c, int world, int rank, double* const* peer_ptrs, double* multicast_ptr,
                                    long n_doubles, void* stream) {
+    return peer_allreduce(c, world, rank, peer_ptrs, multicast_ptr, n_doubles, 0, stream);
+}
+
+extern "C" int tess_peer_allreduce_sparse(tess_ctx* c, int world, int rank, double* const* peer_ptrs, long n_doubles,
+                                          void* stream) {
+    return peer_allreduce(c, world, rank, peer_ptrs, nullptr, n_doubles, 1, stream);
+}
+
+static int peer_allreduce(tess_ctx* c, int world, int rank, double* const* peer_ptrs, double* multicast_ptr,
+                          long n_doubles, int sparse, void* stream) {
     TRY(bind(c));
 #ifdef TESS_EMU
-    (void)world; (void)rank; (void)peer_ptrs; (void)multicast_ptr; (void)n_doubles; (void)stream;
+    (void)world; (void)rank; (void)peer_ptrs; (void)multicast_ptr; (void)n_doubles; (void)stream; (void)sparse;
     return tess_fail(TESS_ERR_STATE, "tess_peer_allreduce: no peer memory in the emulator build");
 #else
     if (world < 1 || world > TESS_PEER_MAX || rank < 0 || rank >= world || n_doubles <= 0 || (!peer_ptrs && !multicast_ptr))
@@ -953,7 +990,15 @@ extern "C" int tess_peer_allreduce(tess_ctx* c, int world, int rank, double* con
         }
         nb = ((hi - lo) / 2 + 255) / 256;
         if (nb > c->sm_count * 8) nb = c->sm_count * 8;
-        TESS_LAUNCH((k_peer_sum_p2p), (int)nb, 256, S(stream), P, lo, hi);
+        if (sparse) {
+            unsigned long long* rs = range_slots(c);
+            if (!rs) return tess_fail(TESS_ERR_STATE, "tess_peer_allreduce_sparse: no published range (tess_peer_publish_range)");
+            const int M = n_moments(c);
+            TESS_LAUNCH((k_peer_sum_p2p_sparse), (int)nb, 256, S(stream), P, lo, hi, M, (long)c->k * M,
+                        (long)(reinterpret_cast<double*>(rs) - c->mom));
+        } else {
+            TESS_LAUNCH((k_peer_sum_p2p), (int)nb, 256, S(stream), P, lo, hi);
+        }
     }
     CU_TRY(cudaGetLastError());
     return TESS_OK;
@@ -971,6 +1016,10 @@ extern "C" int tess_lloyd_update(tess_ctx* c, void* stream) {
     TRY(run_phases(c, q, TESS_PH_UPDATE, TESS_PH_SCATTER, 1, s));
     c->index_valid = 1;
     c->index_geo = q.g;
+    if (unsigned long long* rs = range_slots(c)) {       // the published row range of this iteration is spent
+        TESS_LAUNCH((k_reset_range), 1, 1, s, rs);
+        CU_TRY(cudaGetLastError());
+    }
     return TESS_OK;
 }
 

@@ -319,6 +319,7 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
                     key[pos] = (unsigned)cell_items[i];      // generator index (independent, coalesced load)
                 }
             };
+#pragma unroll 1
             for (int j0 = xj0; j0 <= xj1; j0 += 32) {
                 const int j = j0 + lane;
                 int s = 0, e = 0;
@@ -329,11 +330,14 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
                 const int rows = min(32, xj1 - j0 + 1);
                 const int tot = __reduce_add_sync(TESS_FULL, e - s);
                 if (tot <= 6 * rows) {
+#pragma unroll 1
                     for (int i = s; i < e; ++i) look(i);
                     __syncwarp();
                 } else {
+#pragma unroll 1
                     for (int src = 0; src < rows; ++src) {
                         const int ss = __shfl_sync(TESS_FULL, s, src), ee = __shfl_sync(TESS_FULL, e, src);
+#pragma unroll 1
                         for (int i = ss + lane; i < ee; i += 32) look(i);
                     }
                     __syncwarp();
@@ -357,6 +361,7 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
         if (n_box <= TESS_CAP) {
             // in shared memory: order-free compaction in place (write position <= read position)
             cnt = 0;
+#pragma unroll 1
             for (int b0 = 0; b0 < n_box; b0 += 32) {
                 const int i = b0 + lane;
                 double2 p = make_double2(0.0, 0.0);
@@ -385,6 +390,7 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
             // the box does not fit: second pass over the grid cells
             if (lane == 0) s_cnt[wib] = 0;
             __syncwarp();
+#pragma unroll 1
             for (int j0 = xj0; j0 <= xj1; j0 += 32) {
                 const int j = j0 + lane;
                 int s = 0, e = 0;
@@ -409,11 +415,14 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
                     }
                 };
                 if (tot <= 6 * rows) {
+#pragma unroll 1
                     for (int i = s; i < e; ++i) take(i);
                     __syncwarp();
                 } else {
+#pragma unroll 1
                     for (int src = 0; src < rows; ++src) {
                         const int ss = __shfl_sync(TESS_FULL, s, src), ee = __shfl_sync(TESS_FULL, e, src);
+#pragma unroll 1
                         for (int i = ss + lane; i < ee; i += 32) take(i);
                     }
                     __syncwarp();
@@ -445,6 +454,7 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
         if (!overflow && cnt > TESS_LEAF_MIN_BUILD) {
             double umin[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
             double imax = 1.0;
+#pragma unroll 1
             for (int i = lane; i < cnt; i += 32) {
                 const double2 p = xy[i];
                 double v = 1.0;
@@ -471,6 +481,7 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
                 const double su = (double)sqrtf((float)um) * 1.000001 + 1e-18;      // >= sqrt(umin)
                 qthr[q] = (um + 2.0 * c * su + c * c) * TESS_SLACK;
             }
+#pragma unroll 1
             for (int b = 0; 32 * b < cnt; ++b) {
                 const int i = 32 * b + lane;
                 double2 p = make_double2(0.0, 0.0);
@@ -518,6 +529,7 @@ k_build_qlists(TessState* st, int honor, TessTiles T, TessGrid g, const int* cel
             }
             if (ok && qin[q]) {
                 int wpos = 0;
+#pragma unroll 1
                 for (int b = 0; 32 * b < cnt; ++b) {
                     const bool keep = (bits[q] >> b) & 1u;
                     const unsigned bb = __ballot_sync(TESS_FULL, keep);

@@ -189,6 +189,16 @@ class Engine(object):
         self.api.call("tess_peer_allreduce", self.ctx, int(world), int(rank), peer_ptrs,
                       multicast_ptr if multicast_ptr else None, int(n_doubles), self._stream())
 
+    def peer_publish_range(self):
+        """First / last bin with a non-zero local count -> the two slots behind the caller's moment
+        buffer (tess_peer_publish_range); read by the peers' sparse exchange."""
+        self.api.call("tess_peer_publish_range", self.ctx, self._stream())
+
+    def peer_allreduce_sparse(self, world, rank, peer_ptrs, n_doubles):
+        """tess_peer_allreduce_sparse: rows are read only from the peers whose published range holds them."""
+        self.api.call("tess_peer_allreduce_sparse", self.ctx, int(world), int(rank), peer_ptrs, int(n_doubles),
+                      self._stream())
+
     def moments_view(self):
         """The library's packed local moment vector [k*M | tail] as a tensor ALIASING device memory:
         what a multi-GPU driver all-reduces between accumulate() and update()."""

@@ -30,9 +30,10 @@ def shard_rows(H, world, align=64):
 def balanced_row_shards(generators, H, W, world, x0=0.0, y0=0.0, align=64):
     """Row ranges whose estimated cost is equal: the time per pixel of one accumulate (list building +
     image kernel) grows with the local generator density rho (generators per pixel) like
-    3.2 + 42 rho^0.256 ps/px -- a least-squares fit to the per-rank accumulate times of the C4 map on
-    8 GPUs (residuals <= 1 %), consistent with tools/regime_bench.py -- so equal-height shards of a
-    centrally concentrated map would leave the central ranks 2-3x slower than the outer ones.
+    3.2 + 47 rho^0.454 ps/px -- a least-squares fit to tools/regime_bench.py on the round-2 kernels
+    (80 ... 150 000 px per bin, residuals <= 6 %) plus ~1 ps/px of list building -- so equal-height
+    shards of a centrally concentrated map would leave the central ranks 2-3x slower than the outer
+    ones.
     `generators` is the (k, 2) table (host array); boundaries fall on multiples of `align` rows."""
     import numpy as np
     g = np.asarray(generators, dtype=np.float64)
@@ -43,7 +44,7 @@ def balanced_row_shards(generators, H, W, world, x0=0.0, y0=0.0, align=64):
     iy = np.clip(((g[:, 1] - y0) // align).astype(np.int64), 0, nty - 1)
     cnt = np.bincount(iy * ntx + ix, minlength=nty * ntx).reshape(nty, ntx).astype(np.float64)
     tile_px = float(align * align)
-    cost = (tile_px * (3.2 + 42.0 * (cnt / tile_px) ** 0.256)).sum(axis=1)     # per tile row
+    cost = (tile_px * (3.2 + 47.0 * (cnt / tile_px) ** 0.454)).sum(axis=1)     # per tile row
     cum = np.concatenate(([0.0], np.cumsum(cost)))
     cuts = [0]
     for r in range(1, world):
@@ -57,8 +58,14 @@ def balanced_row_shards(generators, H, W, world, x0=0.0, y0=0.0, align=64):
 class ShardedLloyd(object):
     """Drives one `Engine` per rank; `dist` is torch.distributed (already initialised)."""
 
-    def __init__(self, engine, group=None, exchange="auto"):
-        """`exchange`: how the moment vector is summed over the ranks each iteration --
+    def __init__(self, engine, group=None, exchange="auto", renumber=True):
+        """`renumber`: number the generators in spatial (row-major 64-px cell) order inside the engine,
+        so that the bins a rank's rows touch are one short range of ids and the exchange can skip the
+        rest (tess_peer_allreduce_sparse); `generators()`, `moments()`, `local_labels()` and
+        `gather_labels()` translate back to the caller's numbering.  An exact distance tie then goes to
+        the lower SPATIAL index, not the lower caller index (ties need structured input: generators on
+        a lattice).
+        `exchange`: how the moment vector is summed over the ranks each iteration --
         "peer": this library's own kernel over symmetric (peer-mapped) memory, the reduction done in
         the NVSwitch when a multicast mapping exists (tess_peer_allreduce); "nccl": one
         `all_reduce`; "auto": "peer" on CUDA when symmetric memory can be set up, else "nccl".
@@ -74,6 +81,10 @@ class ShardedLloyd(object):
         self.world = dist.get_world_size(group)
         self._view = None
         self._want = os.environ.get("TESS_EXCHANGE", exchange)
+        self._renumber = bool(renumber) and os.environ.get("TESS_NO_RENUMBER", "") != "1"
+        self._perm = None        # internal id -> caller id (None: identity)
+        self._inv = None         # caller id -> internal id
+        self._sparse = False
         self._peer = None
         self.exchange = "backend all_reduce (NCCL on GPUs)" if self._want == "nccl" else "undecided"
 
@@ -87,8 +98,34 @@ class ShardedLloyd(object):
             self.eng.set_domain(float(x0), float(y0), float(x0) + W, float(y0) + float(total_rows))
         self._view = None
 
+    def _spatial_order(self, node):
+        """Stable order of the generators by (row, column) of their 64-px cell: the same on every rank."""
+        if isinstance(node, self.torch.Tensor):
+            t = self.torch
+            cy = t.floor(node[:, 1] / 64.0).clamp_(-2.0 ** 20, 2.0 ** 20).to(t.int64)
+            cx = t.floor(node[:, 0] / 64.0).clamp_(-2.0 ** 20, 2.0 ** 20).to(t.int64)
+            perm = t.argsort(cy * (1 << 22) + cx, stable=True)
+            inv = t.empty_like(perm)
+            inv[perm] = t.arange(perm.numel(), device=perm.device)
+            return perm, inv
+        import numpy as np
+        node = np.asarray(node)
+        cy = np.clip(np.floor(node[:, 1] / 64.0), -2.0 ** 20, 2.0 ** 20).astype(np.int64)
+        cx = np.clip(np.floor(node[:, 0] / 64.0), -2.0 ** 20, 2.0 ** 20).astype(np.int64)
+        perm = np.argsort(cy * (1 << 22) + cx, kind="stable")
+        inv = np.empty_like(perm)
+        inv[perm] = np.arange(perm.size)
+        return perm, inv
+
     def set_generators(self, node_xy, scale=None):
         """Same table on every rank (replicated)."""
+        self._perm = self._inv = None
+        if self._renumber and self.world > 1:
+            node = self.eng._to_dev(node_xy)
+            self._perm, self._inv = self._spatial_order(node)
+            node_xy = node[self._perm]
+            if scale is not None:
+                scale = self.eng._to_dev(scale)[self._perm]
         self.eng.set_generators(node_xy, scale)
         self._view = None
         if self._want != "nccl":
@@ -97,7 +134,7 @@ class ShardedLloyd(object):
     def _setup_peer_exchange(self):
         """Moment vector in a symmetric allocation (torch.distributed._symmetric_memory: peer-mapped
         on every rank of the node, multicast-mapped when the fabric supports NVLS)."""
-        need = 6 * self.eng.k + 2
+        need = 6 * self.eng.k + 2 + 2      # vector (6 moments at most) + tail + the two range slots of the sparse exchange
         if self._peer is not None and self._peer["n"] >= need:
             return
         if self._peer is not None:          # outgrown: back to a library-owned vector until replaced
@@ -152,8 +189,13 @@ class ShardedLloyd(object):
             self.eng.set_moment_buffer(peer["buf"], need)
             self._peer = peer
             self._view = None
-            self.exchange = ("own kernel, NVLS multicast reduction (multimem.ld_reduce/st)" if peer["mc"]
-                             else "own kernel, two-shot over NVLink peer memory")
+            import os
+            self._sparse = self._perm is not None and os.environ.get("TESS_PEER_DENSE", "") != "1"
+            if self._sparse:
+                self.exchange = "own kernel, two-shot over NVLink peer memory, sparse reduce (spatially numbered bins)"
+            else:
+                self.exchange = ("own kernel, NVLS multicast reduction (multimem.ld_reduce/st)" if peer["mc"]
+                                 else "own kernel, two-shot over NVLink peer memory")
             return
         err = err or "a peer rank could not set up symmetric memory"
         if self._want == "peer":
@@ -183,8 +225,13 @@ class ShardedLloyd(object):
             return
         p = self._peer
         n = self.eng.api.moments_ptr(self.eng.ctx)[1]
+        if self._sparse:
+            self.eng.peer_publish_range()      # which rows of this rank's vector are non-zero
         p["hdl"].barrier(channel=0)            # every rank's local sums are final (stream-ordered)
-        self.eng.peer_allreduce(self.world, self.rank, p["ptrs"], p["mc"], n)
+        if self._sparse:
+            self.eng.peer_allreduce_sparse(self.world, self.rank, p["ptrs"], n)
+        else:
+            self.eng.peer_allreduce(self.world, self.rank, p["ptrs"], p["mc"], n)
         p["hdl"].barrier(channel=1)            # every rank's slice has been broadcast
 
     def run(self, max_iters, check_every=4):
@@ -207,15 +254,23 @@ class ShardedLloyd(object):
 
     # ------------------------------------------------------------------ results
     def generators(self):
-        return self.eng.generators()
+        g = self.eng.generators()
+        return g if self._inv is None else g[self._inv]
 
     def local_labels(self):
-        """Labels of this rank's rows (they never leave the GPU unless asked for)."""
-        return self.eng.labels()
+        """Labels of this rank's rows, in the caller's numbering (they never leave the GPU unless
+        asked for)."""
+        lab = self.eng.labels()
+        if self._perm is None:
+            return lab
+        if isinstance(lab, self.torch.Tensor):
+            return self._perm[lab.long()].to(lab.dtype)
+        return self._perm[lab].astype(lab.dtype)
 
     def moments(self):
         """Global per-bin moments [k, 6] (identical on all ranks after a step)."""
-        return self.eng.moments()
+        m = self.eng.moments()
+        return m if self._inv is None else m[self._inv]
 
     def gather_labels(self, dst=0):
         """Full label map on rank `dst` (None elsewhere); rows are concatenated in rank order."""
