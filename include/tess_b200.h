@@ -162,13 +162,15 @@ int tess_peer_allreduce(tess_ctx* ctx, int world, int rank, double* const* peer_
 
 /*
  * Sparse form of the same exchange, for generator tables numbered in spatial order (rows of a rank's
- * pixel shard then touch one short range of bins).  tess_peer_publish_range (after
- * tess_lloyd_accumulate, before the first barrier) writes the first and last bin with a non-zero
- * local count into the LAST TWO doubles of the caller's buffer (which must therefore hold
- * >= k*M + 2 + 2 doubles; its size must be the same on every rank); tess_peer_allreduce_sparse
- * then reads a row only from the peers whose published range holds it and broadcasts the totals
- * to all -- bit-identical to the dense sum, since the skipped rows are exact zeros.  The range
- * is reset by tess_lloyd_update.  `n_doubles` is the summed length (tess_moments_ptr).
+ * pixel shard then touch one short range of bins).  The caller's buffer must hold 34 more doubles
+ * than the vector (>= k*M + 2 + 34, the same size on every rank): 32 barrier words and the range
+ * [first, last + 1) of bins with a non-zero local count, which tess_lloyd_accumulate publishes there
+ * (tess_peer_publish_range does it again on request).  tess_peer_allreduce_sparse is ONE kernel that
+ * carries its own cross-rank barriers (so it needs no barrier from the caller; every rank must launch
+ * it once per iteration): it reads a row only from the peers whose published range holds it, adds in
+ * rank order and stores the totals into every rank's copy -- bit-identical to the dense sum, since
+ * the skipped rows are exact zeros.  The range is reset by tess_lloyd_update.  `n_doubles` is the
+ * summed length (tess_moments_ptr).
  */
 int tess_peer_publish_range(tess_ctx* ctx, void* stream);
 int tess_peer_allreduce_sparse(tess_ctx* ctx, int world, int rank, double* const* peer_ptrs, long n_doubles, void* stream);

@@ -101,6 +101,7 @@ struct tess_ctx {
     int tmap_ok;
     const double* tmap_src[2];
     long tmap_hw[2];
+    unsigned long long exchange_epoch;   // sparse exchanges launched so far (the barrier word of the next one)
     int index_valid;   // the generator grid in the workspace is that of the CURRENT nodes for index_geo
     TessGrid index_geo;
     int phase_grid;    // CTAs of k_iteration_phases (all resident: cooperative launch); 0 = not decided
@@ -144,6 +145,7 @@ extern "C" int tess_ctx_create(int device, tess_ctx** out) {
         cudaMemset(c->st, 0, sizeof(TessState));
         e = cudaMalloc((void**)&c->scratch, 8 * sizeof(double));
         if (e != cudaSuccess) { r = tess_fail(TESS_ERR_NOMEM, "cudaMalloc(scratch): %s", cudaGetErrorString(e)); break; }
+        cudaMemset(c->scratch, 0, 8 * sizeof(double));      // [6]: "CTAs done" counter of the sparse exchange
         e = cudaMalloc((void**)&c->delta_part, sizeof(double) * (size_t)(c->sm_count * 16 + 16));
         if (e != cudaSuccess) { r = tess_fail(TESS_ERR_NOMEM, "cudaMalloc(delta_part): %s", cudaGetErrorString(e)); break; }
         e = cudaMallocHost((void**)&c->h_st, sizeof(TessState) + 8 * sizeof(double));
@@ -611,6 +613,7 @@ static bool same_grid(const TessGrid& a, const TessGrid& b) {
 }
 
 static int n_moments(const tess_ctx* c);
+static unsigned long long* range_slots(tess_ctx* c);
 
 static void phase_args(tess_ctx* c, const Geometry& q, TessPhaseArgs* a) {
     memset(a, 0, sizeof(*a));
@@ -622,6 +625,7 @@ static void phase_args(tess_ctx* c, const Geometry& q, TessPhaseArgs* a) {
     a->inv_in = c->has_scale ? c->inv_s2 : nullptr;
     a->wvt_update = c->wvt_update;
     a->delta_part = c->delta_part;
+    a->range = range_slots(c);
     a->mask_mode = (c->source == SRC_IMAGE) ? c->img_mode : 0;
     a->lab0 = c->lab[0]; a->lab1 = c->lab[1];
     a->n = (c->source == SRC_IMAGE) ? c->H * c->W : c->n_pts;
@@ -919,8 +923,9 @@ extern "C" int tess_set_moment_buffer(tess_ctx* c, double* buf, long n_doubles) 
     c->mom = buf;
     c->mom_cap = n_doubles;
     c->mom_external = 1;
-    // the two slots behind the vector that tess_peer_publish_range fills (sparse exchange): empty range
-    TESS_LAUNCH((k_reset_range), 1, 1, nullptr, reinterpret_cast<unsigned long long*>(buf + n_doubles - TESS_RANGE_SLOTS));
+    // the slots behind the vector that the sparse exchange uses (barrier flags, published range)
+    if (n_doubles >= TESS_SPARSE_EXTRA + TESS_TAIL + 6)
+        TESS_LAUNCH((k_reset_sparse_slots), 1, 64, nullptr, reinterpret_cast<unsigned long long*>(buf + n_doubles - TESS_SPARSE_EXTRA));
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaStreamSynchronize(nullptr));
     return TESS_OK;
@@ -930,7 +935,7 @@ extern "C" int tess_set_moment_buffer(tess_ctx* c, double* buf, long n_doubles) 
 static unsigned long long* range_slots(tess_ctx* c) {
     if (!c->mom_external || !c->mom) return nullptr;
     const long used = (long)c->k * n_moments(c) + TESS_TAIL;
-    if (c->mom_cap < used + TESS_RANGE_SLOTS || ((c->mom_cap - TESS_RANGE_SLOTS) & 1)) return nullptr;
+    if (c->mom_cap < used + TESS_SPARSE_EXTRA || (c->mom_cap & 1)) return nullptr;
     return reinterpret_cast<unsigned long long*>(c->mom + c->mom_cap - TESS_RANGE_SLOTS);
 }
 
@@ -973,7 +978,7 @@ static int peer_allreduce(tess_ctx* c, int world, int rank, double* const* peer_
     long per = (n_doubles + world - 1) / world;
     per += per & 1;
     const long lo = per * rank, hi = (lo + per < n_doubles) ? lo + per : n_doubles;
-    if (hi <= lo) return TESS_OK;
+    if (hi <= lo && !sparse) return TESS_OK;     // (the sparse kernel carries the cross-rank barriers: always launched)
     long nb = (hi - lo + 255) / 256;
     if (nb > c->sm_count * 8) nb = c->sm_count * 8;
     if (multicast_ptr) {
@@ -994,8 +999,14 @@ static int peer_allreduce(tess_ctx* c, int world, int rank, double* const* peer_
             unsigned long long* rs = range_slots(c);
             if (!rs) return tess_fail(TESS_ERR_STATE, "tess_peer_allreduce_sparse: no published range (tess_peer_publish_range)");
             const int M = n_moments(c);
+            const long range_off = (long)(reinterpret_cast<double*>(rs) - c->mom);
+            static const int peer_ctas = getenv("TESS_PEER_CTAS") ? atoi(getenv("TESS_PEER_CTAS")) : 2;   // tuning aid
+            nb = (hi - lo + TESS_PEER_CHUNK - 1) / TESS_PEER_CHUNK;          // one 16 KB chunk per CTA and trip
+            if (nb > c->sm_count * peer_ctas) nb = c->sm_count * peer_ctas;
+            if (nb < 1) nb = 1;
             TESS_LAUNCH((k_peer_sum_p2p_sparse), (int)nb, 256, S(stream), P, lo, hi, M, (long)c->k * M,
-                        (long)(reinterpret_cast<double*>(rs) - c->mom));
+                        range_off - TESS_FLAG_SLOTS, range_off, (unsigned long long)(++c->exchange_epoch),
+                        reinterpret_cast<unsigned*>(c->scratch + 6));
         } else {
             TESS_LAUNCH((k_peer_sum_p2p), (int)nb, 256, S(stream), P, lo, hi);
         }
@@ -1016,10 +1027,6 @@ extern "C" int tess_lloyd_update(tess_ctx* c, void* stream) {
     TRY(run_phases(c, q, TESS_PH_UPDATE, TESS_PH_SCATTER, 1, s));
     c->index_valid = 1;
     c->index_geo = q.g;
-    if (unsigned long long* rs = range_slots(c)) {       // the published row range of this iteration is spent
-        TESS_LAUNCH((k_reset_range), 1, 1, s, rs);
-        CU_TRY(cudaGetLastError());
-    }
     return TESS_OK;
 }
 

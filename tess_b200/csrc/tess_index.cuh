@@ -22,12 +22,22 @@ TESS_DEVFN void tess_p_cell_count(TessGrid g, const double* node, int k, int* ce
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long stride = (long)gridDim.x * blockDim.x;
     for (long j = i; j < n_mom; j += stride) mom[j] = 0.0;
-    for (long j = i; j < k; j += stride) {
-        int ci = tess_cell_coord(node[2 * j], g.ox, g.inv_cs, g.gw);
-        int cj = tess_cell_coord(node[2 * j + 1], g.oy, g.inv_cs, g.gh);
-        int c = cj * g.gw + ci;
-        cell_of[j] = c;
-        atomicAdd(&cell_cnt[c], 1);
+    for (long j0 = i; j0 < k; j0 += 4 * stride) {          // four independent generators per trip
+        double2 xy[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long j = j0 + u * stride;
+            xy[u] = (j < k) ? *reinterpret_cast<const double2*>(node + 2 * j) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long j = j0 + u * stride;
+            if (j < k) {
+                const int c = tess_cell_coord(xy[u].y, g.oy, g.inv_cs, g.gh) * g.gw + tess_cell_coord(xy[u].x, g.ox, g.inv_cs, g.gw);
+                cell_of[j] = c;
+                atomicAdd(&cell_cnt[c], 1);
+            }
+        }
     }
 }
 __global__ void __launch_bounds__(256)
@@ -173,12 +183,30 @@ k_cell_scan(TessState* st, int honor, const int* cell_cnt, int* cell_start, int 
 
 TESS_DEVFN void tess_p_cell_scatter(const int* cell_of, int k, const int* cell_start, int* cell_cnt, const double* node,
                                     const double* inv_s2, int* cell_items, double2* cell_xy, double* cell_inv) {
-    for (long j = (long)blockIdx.x * blockDim.x + threadIdx.x; j < k; j += (long)gridDim.x * blockDim.x) {
-        const int c = cell_of[j];
-        const int pos = cell_start[c] + atomicSub(&cell_cnt[c], 1) - 1;
-        cell_items[pos] = (int)j;
-        cell_xy[pos] = make_double2(node[2 * j], node[2 * j + 1]);
-        if (inv_s2) cell_inv[pos] = inv_s2[j];
+    // four generators per thread and trip: the slot atomics (with return) and the loads behind them are
+    // ~1 us round trips each; issued four at a time they overlap instead of queueing up
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long j0 = (long)blockIdx.x * blockDim.x + threadIdx.x; j0 < k; j0 += 4 * stride) {
+        int c[4], pos[4];
+        double2 xy[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long j = j0 + u * stride;
+            c[u] = (j < k) ? cell_of[j] : 0;
+            xy[u] = (j < k) ? *reinterpret_cast<const double2*>(node + 2 * j) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (j0 + u * stride < k) pos[u] = cell_start[c[u]] + atomicSub(&cell_cnt[c[u]], 1) - 1;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long j = j0 + u * stride;
+            if (j < k) {
+                cell_items[pos[u]] = (int)j;
+                cell_xy[pos[u]] = xy[u];
+                if (inv_s2) cell_inv[pos[u]] = inv_s2[j];
+            }
+        }
     }
 }
 __global__ void __launch_bounds__(256)

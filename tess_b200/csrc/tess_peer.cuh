@@ -33,6 +33,12 @@ struct TessPeers {
 // zeros of the others would not change a bit -- so the reduce half of the exchange moves ~1/world of the
 // dense traffic.  The broadcast half stays dense: every rank updates the whole (replicated) node table.
 #define TESS_RANGE_SLOTS 2
+// Behind the vector, in this order: 2 x TESS_PEER_MAX 64-bit flags (the opening and the closing
+// cross-rank barrier of k_peer_sum_p2p_sparse: flag[b][r] = last exchange number rank r signalled),
+// then the two range slots.
+#define TESS_FLAG_SLOTS (2 * TESS_PEER_MAX)
+#define TESS_SPARSE_EXTRA (TESS_FLAG_SLOTS + TESS_RANGE_SLOTS)
+#define TESS_PEER_CHUNK 2048      // doubles per bulk copy (16 KB)
 
 // range[0] = first row with a non-zero count, range[1] = last such row + 1 (empty: ~0, 0)
 __global__ void __launch_bounds__(256)
@@ -61,37 +67,95 @@ __global__ void k_reset_range(unsigned long long* range) {
     range[0] = ~0ull;
     range[1] = 0ull;
 }
+// flags (zero: no exchange signalled yet) and range of a fresh caller buffer
+__global__ void k_reset_sparse_slots(unsigned long long* extra) {
+    for (int i = threadIdx.x; i < TESS_FLAG_SLOTS; i += blockDim.x) extra[i] = 0ull;
+    if (threadIdx.x == 0) { extra[TESS_FLAG_SLOTS] = ~0ull; extra[TESS_FLAG_SLOTS + 1] = 0ull; }
+}
 
 #ifndef TESS_EMU
+TESS_DEVFN void tess_flag_store(double* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+TESS_DEVFN unsigned long long tess_flag_load(const double* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// The whole exchange in ONE kernel, its two cross-rank barriers included (one process and one GPU
+// per rank; every rank launches it once per iteration with the same `epoch`):
+//   open   every rank tells every peer "my local sums (and my range) are final" and waits for the
+//          same word from all of them -- every CTA waits by itself, no CTA waits for another CTA;
+//   sum    rank r reads slice r from the peers whose published range holds the row, adds in rank
+//          order, stores the total into every rank's copy;
+//   close  the last CTA to finish tells every peer "my slice is everywhere" and waits for all peers
+//          to say so: when the kernel ends the whole vector of this rank is final.
 __global__ void __launch_bounds__(256)
-k_peer_sum_p2p_sparse(TessPeers P, long lo, long hi, int M, long n_rows_doubles, long range_off) {
+k_peer_sum_p2p_sparse(TessPeers P, long lo, long hi, int M, long n_rows_doubles, long flag_off, long range_off,
+                      unsigned long long epoch, unsigned* done) {
     __shared__ unsigned long long s_lo[TESS_PEER_MAX], s_hi[TESS_PEER_MAX];
+    __shared__ int s_last;
     if (threadIdx.x < P.world) {
+        if (blockIdx.x == 0) tess_flag_store(P.ptr[threadIdx.x] + flag_off + P.rank, epoch);
+        while (tess_flag_load(P.ptr[P.rank] + flag_off + threadIdx.x) < epoch) { }
         unsigned long long a, b;
         asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(P.ptr[threadIdx.x] + range_off) : "memory");
         s_lo[threadIdx.x] = a;
         s_hi[threadIdx.x] = b;
     }
     __syncthreads();
-    const long stride = 2L * gridDim.x * blockDim.x;
-    for (long i = lo + 2L * ((long)blockIdx.x * blockDim.x + threadIdx.x); i < hi; i += stride) {
-        const bool tail = i >= n_rows_doubles;                                     // the tail is summed densely
-        const unsigned long long row = (unsigned long long)(i / M);
-        double sa = 0.0, sb = 0.0;
-        double a[TESS_PEER_MAX], b[TESS_PEER_MAX];
+    // Chunks of TESS_PEER_CHUNK doubles: the CTA sums a chunk into shared memory (predicated 16-byte
+    // peer loads), then ONE bulk copy of the TMA unit per destination rank sends it out
+    // (cp.async.bulk shared -> global: UBLKCP; 16 KB bursts over NVLink instead of 16-byte stores).
+    // Two buffers: the copies of a chunk drain while the next one is summed.
+    __shared__ __align__(128) double s_out[2][TESS_PEER_CHUNK];
+    int buf = 0;
+    for (long c0 = lo + (long)blockIdx.x * TESS_PEER_CHUNK; c0 < hi; c0 += (long)gridDim.x * TESS_PEER_CHUNK) {
+        const int len = (int)((hi - c0 < TESS_PEER_CHUNK) ? (hi - c0) : TESS_PEER_CHUNK);      // even
+        // the bulk copies that read this buffer two chunks ago are done reading it
+        if (threadIdx.x < P.world) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncthreads();
+        for (int o = 2 * threadIdx.x; o < len; o += 2 * blockDim.x) {
+            const long i = c0 + o;
+            const bool tail = i >= n_rows_doubles;                                 // the tail is summed densely
+            const unsigned long long row = (unsigned long long)(i / M);
+            double a[TESS_PEER_MAX], b[TESS_PEER_MAX];
 #pragma unroll
-        for (int r = 0; r < TESS_PEER_MAX; ++r) {
-            a[r] = 0.0; b[r] = 0.0;
-            if (r < P.world && (tail || (row >= s_lo[r] && row < s_hi[r])))
-                asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(a[r]), "=d"(b[r]) : "l"(P.ptr[r] + i) : "memory");
+            for (int r = 0; r < TESS_PEER_MAX; ++r) {
+                a[r] = 0.0; b[r] = 0.0;
+                if (r < P.world && (tail || (row >= s_lo[r] && row < s_hi[r])))
+                    asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(a[r]), "=d"(b[r]) : "l"(P.ptr[r] + i) : "memory");
+            }
+            double sa = 0.0, sb = 0.0;
+#pragma unroll
+            for (int r = 0; r < TESS_PEER_MAX; ++r)
+                if (r < P.world) { sa = __dadd_rn(sa, a[r]); sb = __dadd_rn(sb, b[r]); }
+            *reinterpret_cast<double2*>(&s_out[buf][o]) = make_double2(sa, sb);
         }
-#pragma unroll
-        for (int r = 0; r < TESS_PEER_MAX; ++r)
-            if (r < P.world) { sa = __dadd_rn(sa, a[r]); sb = __dadd_rn(sb, b[r]); }
-#pragma unroll
-        for (int r = 0; r < TESS_PEER_MAX; ++r)
-            if (r < P.world)
-                asm volatile("st.relaxed.sys.global.v2.f64 [%0], {%1, %2};" ::"l"(P.ptr[r] + i), "d"(sa), "d"(sb) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the TMA unit
+        __syncthreads();
+        if (threadIdx.x < P.world) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(P.ptr[threadIdx.x] + c0),
+                         "r"((unsigned)__cvta_generic_to_shared(&s_out[buf][0])), "r"(len * 8) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        buf ^= 1;
+    }
+    if (threadIdx.x < P.world) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // all copies of this CTA have landed
+    // ---- close
+    __threadfence_system();            // this thread's stores are ordered before the flag below
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(done, 1u);
+        s_last = (t == gridDim.x - 1) ? 1 : 0;
+        if (s_last) *done = 0u;
+        __threadfence();
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x < P.world) {
+        tess_flag_store(P.ptr[threadIdx.x] + flag_off + TESS_PEER_MAX + P.rank, epoch);
+        while (tess_flag_load(P.ptr[P.rank] + flag_off + TESS_PEER_MAX + threadIdx.x) < epoch) { }
     }
 }
 

@@ -46,6 +46,7 @@ struct TessPhaseArgs {
     const double* inv_in;   // inv_s2 when the metric is scaled, else null (copied into cell order)
     int wvt_update;
     double* delta_part;
+    unsigned long long* range;   // published row range of the sparse exchange, or null
     // label comparison
     int mask_mode;          // 0: all; 1: finite density; 2: finite signal, noise, weight
     int32_t *lab0, *lab1;
@@ -79,7 +80,7 @@ k_iteration_phases(const TESS_GRID_CONSTANT TessPhaseArgs a, int lo, int hi, int
         if (dirty) tess_grid_barrier();
         dirty = true;
         if (ph == TESS_PH_PREFILTER) {
-            if (!stopped0) tess_p_count_prefilter(st, a.mom, a.M, a.k, a.prev_count, tail);
+            if (!stopped0) tess_p_count_prefilter(st, a.mom, a.M, a.k, a.prev_count, tail, a.range);
         } else if (ph == TESS_PH_COMPARE) {
             // Labels are compared only when no population changed, i.e. a handful of times near
             // convergence.  Every CTA reads the same answer here (the barrier above published it), so
@@ -115,6 +116,7 @@ k_iteration_phases(const TESS_GRID_CONSTANT TessPhaseArgs a, int lo, int hi, int
                 if (blockIdx.x == 0 && threadIdx.x == 0) {
                     tail[TESS_TAIL_CHANGED] = 0.0;
                     tail[TESS_TAIL_SPARE] = 0.0;
+                    if (a.range) { a.range[0] = ~0ull; a.range[1] = 0ull; }     // the published row range is spent
                 }
             }
         }

@@ -23,7 +23,11 @@
 #define TESS_TAIL_CHANGED 0   // sum over ranks of (labels changed ? 1 : 0)
 #define TESS_TAIL_SPARE 1
 
-TESS_DEVFN void tess_p_count_prefilter(TessState* st, const double* mom, int M, int k, double* prev_count, double* mom_tail) {
+// `range` (nullable): first row / last row + 1 with a non-zero count go there (atomic min / max), for the
+// sparse multi-GPU exchange (tess_peer.cuh).
+TESS_DEVFN void tess_p_count_prefilter(TessState* st, const double* mom, int M, int k, double* prev_count, double* mom_tail,
+                                       unsigned long long* range = nullptr) {
+    unsigned long long lo = ~0ull, hi = 0ull;
     // whole warps walk the table together (the vote below), one store per warp at most (every writer
     // stores the same value; a store per thread would serialise in L2).  The tail slot was zeroed
     // together with the moments.
@@ -34,10 +38,27 @@ TESS_DEVFN void tess_p_count_prefilter(TessState* st, const double* mom, int M, 
             const double c = mom[j * M];
             diff = (c != prev_count[j]);
             prev_count[j] = c;
+            if (c != 0.0) {
+                const unsigned long long u = (unsigned long long)j;
+                lo = lo < u ? lo : u;
+                hi = hi > u + 1 ? hi : u + 1;
+            }
         }
         if (__any_sync(TESS_FULL, diff) && (threadIdx.x & 31) == 0) {
             st->count_changed = 1;
             mom_tail[TESS_TAIL_CHANGED] = 1.0;
+        }
+    }
+    if (range) {
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            const unsigned long long l2 = __shfl_xor_sync(TESS_FULL, lo, m), h2 = __shfl_xor_sync(TESS_FULL, hi, m);
+            lo = lo < l2 ? lo : l2;
+            hi = hi > h2 ? hi : h2;
+        }
+        if ((threadIdx.x & 31) == 0 && hi > 0ull) {
+            atomicMin(range, lo);
+            atomicMax(range + 1, hi);
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -114,14 +135,21 @@ TESS_DEVFN void tess_p_update_nodes(TessState* st, const double* mom, const doub
     const bool changed = mom_tail[TESS_TAIL_CHANGED] != 0.0;
     if (changed) {
         double d = 0.0;
-        for (long j = (long)blockIdx.x * blockDim.x + threadIdx.x; j < k; j += (long)gridDim.x * blockDim.x) {
+        const long stride = (long)gridDim.x * blockDim.x;
+        long j = (long)blockIdx.x * blockDim.x + threadIdx.x;
+        // the three 16-byte operands of a generator (moment row as 128-bit loads -- rows are 32 or 48
+        // bytes, 16-byte aligned -- and the old node) are loaded together, and those of the thread's
+        // NEXT generator are requested before this one is worked on: issued after the divide (one more
+        // dependent DRAM round trip, interleaved with the node stores) the kernel measured 5x slower
+        double2 n01 = make_double2(0.0, 0.0), n23 = n01, nold = n01;
+        if (j < k) { n01 = tess_ld2(mom + j * M); n23 = tess_ld2(mom + j * M + 2); nold = tess_ld2(node + 2 * j); }
+        for (; j < k; j += stride) {
             const double* m = mom + j * M;
-            // the moment row as 128-bit loads (rows are 32 or 48 bytes, 16-byte aligned)
-            const double2 m01 = tess_ld2(m), m23 = tess_ld2(m + 2);
-            // the old node is loaded together with the moments: issued after the divide (one more
-            // dependent DRAM round trip, interleaved with the node stores) the kernel measured 5x slower
+            const double2 m01 = n01, m23 = n23, old = nold;
+            if (j + stride < k) {
+                n01 = tess_ld2(mom + (j + stride) * M); n23 = tess_ld2(mom + (j + stride) * M + 2); nold = tess_ld2(node + 2 * (j + stride));
+            }
             double2* np = reinterpret_cast<double2*>(node) + j;
-            const double2 old = tess_ld2(node + 2 * j);
             double nx = 0.0, ny = 0.0;
             if (m01.x > 0.0) {   // population test, not weight (lloyd.pyx:68)
                 nx = __ddiv_rn(m23.x, m01.y);

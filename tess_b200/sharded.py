@@ -30,10 +30,10 @@ def shard_rows(H, world, align=64):
 def balanced_row_shards(generators, H, W, world, x0=0.0, y0=0.0, align=64):
     """Row ranges whose estimated cost is equal: the time per pixel of one accumulate (list building +
     image kernel) grows with the local generator density rho (generators per pixel) like
-    3.2 + 47 rho^0.454 ps/px -- a least-squares fit to tools/regime_bench.py on the round-2 kernels
-    (80 ... 150 000 px per bin, residuals <= 6 %) plus ~1 ps/px of list building -- so equal-height
-    shards of a centrally concentrated map would leave the central ranks 2-3x slower than the outer
-    ones.
+    2.56 + 39.1 rho^0.40 ps/px -- a least-squares fit to the per-rank accumulate times of the C4 map
+    on 8 GPUs under two different shardings (round-2 kernels; residuals <= 3 %; the fixed ~0.05 ms per
+    rank does not matter for the cuts) -- so equal-height shards of a centrally concentrated map
+    would leave the central ranks 2x slower than the outer ones.
     `generators` is the (k, 2) table (host array); boundaries fall on multiples of `align` rows."""
     import numpy as np
     g = np.asarray(generators, dtype=np.float64)
@@ -44,7 +44,7 @@ def balanced_row_shards(generators, H, W, world, x0=0.0, y0=0.0, align=64):
     iy = np.clip(((g[:, 1] - y0) // align).astype(np.int64), 0, nty - 1)
     cnt = np.bincount(iy * ntx + ix, minlength=nty * ntx).reshape(nty, ntx).astype(np.float64)
     tile_px = float(align * align)
-    cost = (tile_px * (3.2 + 47.0 * (cnt / tile_px) ** 0.454)).sum(axis=1)     # per tile row
+    cost = (tile_px * (2.56 + 39.1 * (cnt / tile_px) ** 0.40)).sum(axis=1)     # per tile row
     cum = np.concatenate(([0.0], np.cumsum(cost)))
     cuts = [0]
     for r in range(1, world):
@@ -134,7 +134,7 @@ class ShardedLloyd(object):
     def _setup_peer_exchange(self):
         """Moment vector in a symmetric allocation (torch.distributed._symmetric_memory: peer-mapped
         on every rank of the node, multicast-mapped when the fabric supports NVLS)."""
-        need = 6 * self.eng.k + 2 + 2      # vector (6 moments at most) + tail + the two range slots of the sparse exchange
+        need = 6 * self.eng.k + 2 + 34     # vector (6 moments at most) + tail + barrier flags and range slots of the sparse exchange
         if self._peer is not None and self._peer["n"] >= need:
             return
         if self._peer is not None:          # outgrown: back to a library-owned vector until replaced
@@ -226,12 +226,12 @@ class ShardedLloyd(object):
         p = self._peer
         n = self.eng.api.moments_ptr(self.eng.ctx)[1]
         if self._sparse:
-            self.eng.peer_publish_range()      # which rows of this rank's vector are non-zero
-        p["hdl"].barrier(channel=0)            # every rank's local sums are final (stream-ordered)
-        if self._sparse:
+            # one kernel: its own cross-rank barriers around the sparse reduce + broadcast (the range of
+            # non-zero rows was published by the accumulate)
             self.eng.peer_allreduce_sparse(self.world, self.rank, p["ptrs"], n)
-        else:
-            self.eng.peer_allreduce(self.world, self.rank, p["ptrs"], p["mc"], n)
+            return
+        p["hdl"].barrier(channel=0)            # every rank's local sums are final (stream-ordered)
+        self.eng.peer_allreduce(self.world, self.rank, p["ptrs"], p["mc"], n)
         p["hdl"].barrier(channel=1)            # every rank's slice has been broadcast
 
     def run(self, max_iters, check_every=4):
