@@ -63,6 +63,11 @@ struct tess_ctx {
     const double *dens, *sig, *noise;
     long n_pts;
     const double *pts_xy, *pts_w;
+    // the point set in spatial order (owned; built by tess_set_points)
+    int* pts_perm;
+    double2* pts_xy_s;
+    double* pts_w_s;
+    long pts_cap;
     double pb[4];   // bounding box of the points (x0, x1, y0, y1)
     double gb[4];   // bounding box of the generator table at tess_set_generators
     int gb_valid;
@@ -165,7 +170,8 @@ extern "C" int tess_ctx_destroy(tess_ctx* c) {
     cudaDeviceSynchronize();
     void* ptrs[] = {c->node, c->scale, c->inv_s2, c->st, c->cell_cnt, c->cell_start, c->block_sum, c->cell_of, c->cell_items,
                     c->cell_xy, c->cell_inv, c->ql.q_off, c->ql.q_cnt, c->ql.ring_q, c->ql.xy, c->ql.gid, c->ql.inv, c->tile_ring, c->lab[0], c->lab[1],
-                    c->mom_external ? nullptr : c->mom, c->prev_count, c->scratch, c->delta_part};
+                    c->mom_external ? nullptr : c->mom, c->prev_count, c->scratch, c->delta_part, c->pts_perm, c->pts_xy_s,
+                    c->pts_w_s};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (c->h_st) cudaFreeHost(c->h_st);
@@ -312,6 +318,50 @@ static int points_bbox(tess_ctx* c, long n, const double* xy, double* box, cudaS
     return TESS_OK;
 }
 
+static int ensure_cells(tess_ctx* c, int n_cells);
+
+// The point set in spatial order (counting sort over a grid of its own, ~16 points per cell): done
+// once, the points never move.  The Lloyd kernel then walks neighbouring points with neighbouring
+// threads (shared generator cells, shared bins).  Uses the generator-grid workspace as scratch.
+static int sort_points(tess_ctx* c, cudaStream_t s) {
+    const long n = c->n_pts;
+    if (n > c->pts_cap) {
+        void** ps[] = {(void**)&c->pts_perm, (void**)&c->pts_xy_s, (void**)&c->pts_w_s};
+        for (void** p : ps) { if (*p) cudaFree(*p); *p = nullptr; }
+        c->pts_cap = 0;
+        CU_TRY(cudaMalloc((void**)&c->pts_perm, sizeof(int) * (size_t)n));
+        CU_TRY(cudaMalloc((void**)&c->pts_xy_s, sizeof(double2) * (size_t)n));
+        CU_TRY(cudaMalloc((void**)&c->pts_w_s, sizeof(double) * (size_t)n));
+        c->pts_cap = n;
+    }
+    TessGrid g;
+    const double w = fmax(c->pb[1] - c->pb[0], 0.0), h = fmax(c->pb[3] - c->pb[2], 0.0);
+    double cs = (w > 0.0 && h > 0.0) ? sqrt(w * h * 16.0 / (double)n) : fmax(w, h) * 16.0 / (double)n;
+    if (!(cs > 0.0) || !isfinite(cs)) cs = 1.0;
+    cs = fmax(cs, fmax(w, h) / 2048.0);
+    g.ox = c->pb[0]; g.oy = c->pb[2]; g.cs = cs; g.inv_cs = 1.0 / cs; g.tol = 0.0;
+    g.gw = (int)fmin(floor(w / cs) + 1.0, 2049.0); g.gh = (int)fmin(floor(h / cs) + 1.0, 2049.0);
+    if (g.gw < 1) g.gw = 1;
+    if (g.gh < 1) g.gh = 1;
+    const int n_cells = g.gw * g.gh;
+    TRY(ensure_cells(c, n_cells));
+    int* cell_of = nullptr;
+    CU_TRY(cudaMalloc((void**)&cell_of, sizeof(int) * (size_t)n));
+    int nb = (int)((n + 255) / 256);
+    if (nb > c->sm_count * 16) nb = c->sm_count * 16;
+    TESS_LAUNCH((k_pts_cell), nb, 256, s, g, c->pts_xy, n, cell_of, c->cell_cnt);
+    const int nsb = (n_cells + TESS_SCAN_BLOCK - 1) / TESS_SCAN_BLOCK;
+    TESS_LAUNCH((k_cell_blocksum), nsb, TESS_SCAN_THREADS, s, c->st, 0, c->cell_cnt, n_cells, c->block_sum);
+    TESS_LAUNCH((k_cell_scan), nsb, TESS_SCAN_THREADS, s, c->st, 0, c->cell_cnt, c->cell_start, n_cells, c->block_sum);
+    TESS_LAUNCH((k_pts_scatter), nb, 256, s, cell_of, c->cell_start, c->cell_cnt, c->pts_xy, c->pts_w, n, c->pts_perm,
+                c->pts_xy_s, c->pts_w_s);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(s));
+    cudaFree(cell_of);
+    c->index_valid = 0;
+    return TESS_OK;
+}
+
 extern "C" int tess_set_points(tess_ctx* c, long n, const double* xy, const double* w, void* stream) {
     TRY(bind(c));
     if (n <= 0 || !xy || !w) return tess_fail(TESS_ERR_ARG, "tess_set_points: need n > 0, xy and w");
@@ -323,6 +373,7 @@ extern "C" int tess_set_points(tess_ctx* c, long n, const double* xy, const doub
     c->dens = c->sig = c->noise = nullptr;
     TRY(points_bbox(c, n, xy, c->pb, S(stream)));
     TRY(ensure_labels(c, n));
+    TRY(sort_points(c, S(stream)));
     TRY(restart(c, S(stream)));
     return TESS_OK;
 }
@@ -777,22 +828,22 @@ static int run_image(tess_ctx* c, const Geometry& q, int mode, int honor, int32_
 }
 
 static int run_points(tess_ctx* c, const Geometry& q, int mode, int honor, long n, const double* xy, const double* w,
-                      int32_t* labels_ext, cudaStream_t s) {
+                      const int* perm, int32_t* labels_ext, cudaStream_t s) {
     const int nb = (int)((n + 255) / 256);
     if (mode == 1) {
         if (c->has_scale)
             TESS_LAUNCH((k_points_main<1, true>), nb, 256, s, c->st, honor, q.g, c->cell_start, c->cell_items, c->cell_xy,
-                                                     c->cell_inv, n, xy, w, labels_ext, c->lab[0], c->lab[1], c->mom);
+                                                     c->cell_inv, n, xy, w, perm, labels_ext, c->lab[0], c->lab[1], c->mom);
         else
             TESS_LAUNCH((k_points_main<1, false>), nb, 256, s, c->st, honor, q.g, c->cell_start, c->cell_items, c->cell_xy,
-                                                      c->cell_inv, n, xy, w, labels_ext, c->lab[0], c->lab[1], c->mom);
+                                                      c->cell_inv, n, xy, w, perm, labels_ext, c->lab[0], c->lab[1], c->mom);
     } else {
         if (c->has_scale)
             TESS_LAUNCH((k_points_main<0, true>), nb, 256, s, c->st, honor, q.g, c->cell_start, c->cell_items, c->cell_xy,
-                                                     c->cell_inv, n, xy, w, labels_ext, c->lab[0], c->lab[1], c->mom);
+                                                     c->cell_inv, n, xy, w, perm, labels_ext, c->lab[0], c->lab[1], c->mom);
         else
             TESS_LAUNCH((k_points_main<0, false>), nb, 256, s, c->st, honor, q.g, c->cell_start, c->cell_items, c->cell_xy,
-                                                      c->cell_inv, n, xy, w, labels_ext, c->lab[0], c->lab[1], c->mom);
+                                                      c->cell_inv, n, xy, w, perm, labels_ext, c->lab[0], c->lab[1], c->mom);
     }
     CU_TRY(cudaGetLastError());
     return TESS_OK;
@@ -883,7 +934,7 @@ static int accumulate_core(tess_ctx* c, const Geometry& q, cudaStream_t s) {
         if (grid > c->sm_count * 8) grid = c->sm_count * 8;
         TESS_LAUNCH((k_clear_moments), grid, 256, s, c->st, 1, c->mom, n_rows);
         timing_mark(c, s, 0);
-        TRY(run_points(c, q, 1, 1, c->n_pts, c->pts_xy, c->pts_w, nullptr, s));
+        TRY(run_points(c, q, 1, 1, c->n_pts, reinterpret_cast<const double*>(c->pts_xy_s), c->pts_w_s, c->pts_perm, nullptr, s));
         timing_mark(c, s, 1);
     }
     CU_TRY(cudaGetLastError());
@@ -1176,7 +1227,7 @@ extern "C" int tess_assign_points(tess_ctx* c, long m, const double* xy, int32_t
     TRY(generator_bbox(c, s));
     Geometry q = box_geometry(c, box);
     TRY(build_index(c, q, 0, nullptr, 0, s));
-    TRY(run_points(c, q, 0, 0, m, xy, nullptr, out, s));
+    TRY(run_points(c, q, 0, 0, m, xy, nullptr, nullptr, out, s));
     return TESS_OK;
 }
 

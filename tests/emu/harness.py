@@ -18,6 +18,10 @@ OUT = os.path.join(HERE, "_build", "libtess_emu.so")
 
 
 def build(force=False):
+    # TESS_EMU_LIB: a pre-built emulator library (e.g. one compiled with -fsanitize=address,undefined by
+    # tools/emu_sanitize.sh, which also preloads the sanitizer runtime)
+    if os.environ.get("TESS_EMU_LIB"):
+        return os.environ["TESS_EMU_LIB"]
     srcs = [os.path.join(SRC, f) for f in os.listdir(SRC)] + [os.path.join(HERE, "cuda_emu.h"),
                                                               os.path.join(ROOT, "include", "tess_b200.h")]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(s) for s in srcs):

@@ -1,0 +1,18 @@
+#!/bin/bash
+# tools/emu_sanitize.sh [address|thread] -- the kernel logic under a sanitizer on the CPU.
+# compute-sanitizer is closed on this GPU pool, so the memcheck / racecheck evidence comes from the SIMT
+# emulator build of the very same kernel sources (tests/emu): every CUDA thread is an OS thread there,
+# shared memory and "device" memory are ordinary host memory, so AddressSanitizer sees every out-of-bounds
+# or use-after-free access of the kernels and ThreadSanitizer every unsynchronised conflicting access
+# between lanes.  Runs the emulator test-suite; the log goes to stdout.
+KIND=${1:-address}
+ROOT=$(cd "$(dirname "$0")/.." && pwd)
+OUT=/tmp/tess_emu_$KIND
+mkdir -p $OUT
+if [ "$KIND" = address ]; then FLAGS="-fsanitize=address,undefined -fno-sanitize-recover=undefined"; RT=$(g++ -print-file-name=libasan.so)
+else FLAGS="-fsanitize=thread"; RT=$(g++ -print-file-name=libtsan.so); fi
+g++ -std=c++20 -O1 -g -pthread $FLAGS -fno-omit-frame-pointer -DTESS_EMU -include $ROOT/tests/emu/cuda_emu.h -x c++ \
+    $ROOT/tess_b200/csrc/tess_b200.cu -shared -fPIC -o $OUT/libtess_emu.so || exit 1
+export TESS_EMU_LIB=$OUT/libtess_emu.so
+export ASAN_OPTIONS=detect_leaks=0:abort_on_error=0:halt_on_error=1 TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0"
+LD_PRELOAD=$RT python -m pytest $ROOT/tests/test_emu_kernels.py -x -q -p no:cacheprovider "${@:2}" 2>&1 | tail -40
