@@ -239,6 +239,16 @@ int tess_label_sums(tess_ctx* ctx, long n, const int32_t* labels, const double* 
                     double* out, void* stream);
 
 /*
+ * Per-label moments of a row-major [H][W] label image in one pass, pixel coordinates implicit:
+ * out[l] = (count, sum w, sum w*row, sum w*col) for labels 0 <= l < k (others ignored).  A pixel
+ * always counts; its weight only if finite; weights == NULL means w = 1.  This is the sum behind
+ * PixelAccretor.centroids (reference tess/pixel_accretion.py:212-240) -- no product array w*row /
+ * w*col is ever built.  out is [k][4] device memory.
+ */
+int tess_label_moments(tess_ctx* ctx, long H, long W, const int32_t* labels, const double* weights, long k,
+                       double* out, void* stream);
+
+/*
  * Validation aids: exhaustive O(n*k) assignment on the GPU with the same pinned arithmetic,
  * no index, no pruning.  Used by the tests to check the tiled kernels at sizes the CPU oracle
  * cannot reach.  Not a fallback: nothing in the library calls them.

@@ -58,6 +58,7 @@ SIGNATURES = {
     "tess_assign_grid": (_i, [_vp, _d, _d, _l, _l, _vp, _vp]),
     "tess_assign_points": (_i, [_vp, _l, _vp, _vp, _vp]),
     "tess_label_sums": (_i, [_vp, _l, _vp, _vp, _l, _vp, _vp]),
+    "tess_label_moments": (_i, [_vp, _l, _l, _vp, _vp, _l, _vp, _vp]),
     "tess_assign_grid_exhaustive": (_i, [_vp, _d, _d, _l, _l, _vp, _vp]),
     "tess_assign_points_exhaustive": (_i, [_vp, _l, _vp, _vp, _vp]),
 }

@@ -24,20 +24,13 @@ def _engine(engine, device):
 
 
 def _label_moments(eng, seg, weights, n_bins):
-    """count, sum w, sum w*row, sum w*col per label 0..n_bins-1; pixels with non-finite weight are
-    counted but carry no weight (pixel_accretion.py:229-232)."""
-    H, W = seg.shape
-    lab = eng._to_dev(np.ascontiguousarray(seg, dtype=np.int32), "int32")
-    cnt = eng._to_host(eng.label_sums(lab, None, n_bins))
-    w = np.ones((H, W)) if weights is None else np.asarray(weights, dtype=np.float64)
-    good = np.isfinite(w)
-    w0 = np.where(good, w, 0.0)
-    labw = eng._to_dev(np.where(good, seg, -1).astype(np.int32), "int32")
-    rows, cols = np.meshgrid(np.arange(H, dtype=np.float64), np.arange(W, dtype=np.float64), indexing="ij")
-    sw = eng._to_host(eng.label_sums(labw, eng._to_dev(w0), n_bins))
-    swr = eng._to_host(eng.label_sums(labw, eng._to_dev(w0 * rows), n_bins))
-    swc = eng._to_host(eng.label_sums(labw, eng._to_dev(w0 * cols), n_bins))
-    return cnt, sw, swr, swc
+    """count, sum w, sum w*row, sum w*col per label 0..n_bins-1 in one device pass with implicit pixel
+    coordinates (tess_label_moments); pixels with non-finite weight are counted but carry no weight
+    (pixel_accretion.py:229-232)."""
+    lab = np.ascontiguousarray(seg, dtype=np.int32)
+    w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+    m = eng._to_host(eng.label_moments(lab, w, n_bins))
+    return m[:, 0], m[:, 1], m[:, 2], m[:, 3]
 
 
 def segmap_centroids(segmap, weightmap=None, engine=None, device=None):

@@ -1245,6 +1245,20 @@ extern "C" int tess_label_sums(tess_ctx* c, long n, const int32_t* labels, const
     return TESS_OK;
 }
 
+extern "C" int tess_label_moments(tess_ctx* c, long H, long W, const int32_t* labels, const double* weights, long k,
+                                  double* out, void* stream) {
+    TRY(bind(c));
+    if (H < 0 || W < 0 || k <= 0 || !out || (H * W > 0 && !labels)) return tess_fail(TESS_ERR_ARG, "tess_label_moments: bad arguments");
+    cudaStream_t s = S(stream);
+    CU_TRY(cudaMemsetAsync(out, 0, sizeof(double) * 4 * (size_t)k, s));
+    if (H * W > 0) {
+        const long threads = H * ((W + TESS_RUN - 1) / TESS_RUN);
+        TESS_LAUNCH((k_label_moments), (int)((threads + 255) / 256), 256, s, labels, weights, H, W, k, out);
+        CU_TRY(cudaGetLastError());
+    }
+    return TESS_OK;
+}
+
 extern "C" int tess_assign_grid_exhaustive(tess_ctx* c, double x0, double y0, long H, long W, int32_t* labels_out,
                                            void* stream) {
     TRY(bind(c));

@@ -317,3 +317,38 @@ k_label_sums(const int32_t* labels, const double* w, long n, long k, double* out
     }
     if (cur >= 0 && cur < k) atomicAdd(out + cur, acc);
 }
+
+// Per-label count, sum w, sum w*row, sum w*col over a row-major [H][W] label image in ONE pass, pixel
+// coordinates implicit (PixelAccretor.centroids, tess/pixel_accretion.py:212-240: a pixel always counts,
+// its weight only if finite; w == nullptr means w = 1).  Same run aggregation as k_label_sums; a run
+// ends with the row.  out is [k][4], zeroed by the caller.
+__global__ void __launch_bounds__(256)
+k_label_moments(const int32_t* labels, const double* w, long H, long W, long k, double* out) {
+    const long per_row = (W + TESS_RUN - 1) / TESS_RUN;
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= H * per_row) return;
+    const long row = t / per_row, c0 = (t - row * per_row) * TESS_RUN;
+    const long c1 = (c0 + TESS_RUN < W) ? c0 + TESS_RUN : W;
+    int cur = -1;
+    double n = 0.0, sw = 0.0, swc = 0.0;
+    auto flush = [&]() {
+        if (cur >= 0 && cur < k) {
+            double* m = out + 4 * (long)cur;
+            atomicAdd(m, n);
+            atomicAdd(m + 1, sw);
+            atomicAdd(m + 2, __dmul_rn(sw, (double)row));
+            atomicAdd(m + 3, swc);
+        }
+    };
+    for (long c = c0; c < c1; ++c) {
+        const int l = labels[row * W + c];
+        if (l != cur) {
+            flush();
+            cur = l; n = 0.0; sw = 0.0; swc = 0.0;
+        }
+        const double wv = w ? w[row * W + c] : 1.0;
+        n += 1.0;
+        if (isfinite(wv)) { sw = __dadd_rn(sw, wv); swc = __dadd_rn(swc, __dmul_rn(wv, (double)c)); }
+    }
+    flush();
+}

@@ -259,6 +259,22 @@ class Engine(object):
         self._keep["query"] = xy
         return out
 
+    def label_moments(self, labels, weights=None, k=None):
+        """(count, sum w, sum w*row, sum w*col) per label of a 2-D int32 label image, pixel coordinates
+        implicit, one pass (tess_label_moments; PixelAccretor.centroids, pixel_accretion.py:212-240)."""
+        lab = self._to_dev(labels, "int32")
+        if lab.ndim != 2:
+            raise ValueError("label_moments: labels must be a 2-D image")
+        w = None if weights is None else self._to_dev(weights)
+        if w is not None and tuple(w.shape) != tuple(lab.shape):
+            raise ValueError("label_moments: weights and labels differ in shape")
+        k = self.k if k is None else int(k)
+        out = self._empty((k, 4))
+        self.api.call("tess_label_moments", self.ctx, int(lab.shape[0]), int(lab.shape[1]), self._ptr(lab), self._ptr(w), k,
+                      self._ptr(out), self._stream())
+        self._keep["sums"] = (lab, w)
+        return out
+
     def label_sums(self, labels, weights=None, k=None):
         """Per-bin sums of `weights` (or counts) over an int32 label array -- np.bincount of the
         reference's compute_cell_areas / sum_cell_point_mass (tess/voronoi.py:150,195)."""

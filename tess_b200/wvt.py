@@ -36,15 +36,31 @@ def sn_scatter(sn, target=None):
     return float(np.sqrt(np.mean((s / t - 1.0) ** 2)))
 
 
+def suggest_k(k, median_sn, target_sn):
+    """Number of generators that would bring the median bin S/N to `target_sn`: the S/N of a bin grows
+    like the square root of its area (sum S / sqrt(sum N^2) over ~equal pixels), i.e. like k^-1/2."""
+    if not (np.isfinite(median_sn) and median_sn > 0 and target_sn and target_sn > 0):
+        return None
+    return max(1, int(round(k * (float(median_sn) / float(target_sn)) ** 2)))
+
+
 def wvt_binning(signal, noise, generators, target_sn=None, max_iters=300, check_every=4, tol=1e-3,
-                scale_update=True, uniform_weight=True, scale=None, engine=None, device=None, verbose=False):
+                scale_update=True, uniform_weight=True, scale=None, engine=None, device=None, verbose=False,
+                sn_tol=0.05, scatter_goal=None):
     """Iterate generators on a signal/noise map until the tessellation stops changing (the Lloyd
     latch, tess/lloyd.pyx:85-86), the S/N scatter about `target_sn` stops improving by more than `tol`
     (relative) between two checks, or `max_iters` + 2 iterations have run (the reference's budget,
     lloyd.pyx:87-90).
 
+    `target_sn` is acted on: the loop also stops as soon as the target is MET -- the median bin S/N
+    within `sn_tol` (relative) of it and, if `scatter_goal` is given, the fractional scatter about it at
+    most that -- and when it cannot be met with this many generators the result says so:
+    `target_met` False and `k_suggested`, the number of generators that would put the median on target
+    (the reference's demo gets its k from the accretor run at the target, scripts/demo_iso_sn_voronoi.py:29).
+
     Returns a dict: nodes (k,2), scales (k,) or None, labels (H,W) int64, moments (k,6), bin_sn (k,),
-    sn_scatter, n_iters, converged (latch closed), history [(iteration, scatter)]."""
+    sn_scatter, median_sn, target_met (None without a target), k_suggested, n_iters, converged (latch
+    closed), history [(iteration, scatter, median S/N)]."""
     eng = engine if engine is not None else Engine(device)
     eng.set_option(_capi.OPT_WVT_SCALE_UPDATE, 1 if scale_update else 0)
     eng.set_option(_capi.OPT_UNIFORM_WEIGHT, 1 if uniform_weight else 0)
@@ -60,15 +76,28 @@ def wvt_binning(signal, noise, generators, target_sn=None, max_iters=300, check_
             conv, bad = eng.status()
             if bad:
                 raise _capi.TessNonFinite(-4, "a bin with pixels has zero total weight after iteration %d" % done)
-            sc = sn_scatter(bin_sn(eng._to_host(eng.moments())), target_sn)
-            history.append((done, sc))
+            sn_now = bin_sn(eng._to_host(eng.moments()))
+            sc = sn_scatter(sn_now, target_sn)
+            med = float(np.nanmedian(sn_now)) if np.isfinite(sn_now).any() else np.nan
+            history.append((done, sc, med))
             if verbose:
-                print("WVT %03d  S/N scatter %.4f" % (done, sc))
+                print("WVT %03d  S/N scatter %.4f  median %.3f" % (done, sc, med))
+            if target_sn is not None and np.isfinite(med) and abs(med / float(target_sn) - 1.0) <= sn_tol and \
+                    (scatter_goal is None or sc <= scatter_goal):
+                break                                  # on target
             if prev is not None and np.isfinite(sc) and abs(prev - sc) <= tol * max(prev, 1e-300):
                 break
             prev = sc
         mom = eng._to_host(eng.moments())
-        return dict(nodes=eng._to_host(eng.generators()),
+        sn_fin = bin_sn(mom)
+        med = float(np.nanmedian(sn_fin)) if np.isfinite(sn_fin).any() else np.nan
+        met = None
+        if target_sn is not None:
+            met = bool(np.isfinite(med) and abs(med / float(target_sn) - 1.0) <= sn_tol and
+                       (scatter_goal is None or sn_scatter(sn_fin, target_sn) <= scatter_goal))
+        return dict(median_sn=med, target_met=met,
+                    k_suggested=None if target_sn is None else suggest_k(int(mom.shape[0]), med, target_sn),
+                    nodes=eng._to_host(eng.generators()),
                     scales=eng._to_host(eng.scales()) if (scale_update or scale is not None) else None,
                     labels=eng._to_host(eng.labels()).astype(np.int64), moments=mom, bin_sn=bin_sn(mom),
                     sn_scatter=sn_scatter(bin_sn(mom), target_sn), n_iters=int(done), converged=bool(conv),

@@ -108,6 +108,12 @@ def check_wvt_binning(make_engine, N=72, k=14):
     # at least they are finite, positive and the labels match the oracle's scaled assignment
     assert np.all(np.isfinite(wvt["scales"])) and np.all(wvt["scales"] > 0)
     assert wvt["history"][0][0] == 4 and wvt["n_iters"] <= 32
+    # the target is acted on: far off with this k -> not met, and the suggested k moves the median onto it
+    med = wvt["median_sn"]
+    off = wvt_binning(sig, noise, seeds, target_sn=3.0 * med, max_iters=12, check_every=4, engine=make_engine())
+    assert off["target_met"] is False and off["k_suggested"] < k // 4
+    on = wvt_binning(sig, noise, seeds, target_sn=med, max_iters=30, check_every=4, sn_tol=0.1, engine=make_engine())
+    assert on["target_met"] is True and on["n_iters"] <= wvt["n_iters"] and abs(on["k_suggested"] - k) <= max(2, k // 4)
     return wvt
 
 
@@ -129,3 +135,19 @@ def check_flagmap(vt, g):
         np.testing.assert_allclose(_host(dens)[:n], g["cell_mass"][:n] / want[:n], rtol=1e-13)
     vt._cell_areas = None
     assert np.array_equal(_host(vt.compute_cell_areas()), np.bincount(seg.ravel()))
+
+
+def check_accretor_fixture(make_engine):
+    """tess_b200.accretion against OUTPUTS OF THE REFERENCE's EqualSNAccretor (tests/golden/accretor.npz,
+    written by make_golden.py from the shimmed tess/pixel_accretion.py): centroids (:212-240), bin_sn
+    (:501-517) and the segmentation image after cleanup() (:485-499)."""
+    from tess_b200 import accretion as A
+    from conftest import golden
+    g = golden("accretor.npz")
+    after = A.cleanup_reassign(g["seg_before"], g["bin_centroids_rc"], g["valid_bins"], engine=make_engine())
+    assert np.array_equal(after, g["seg_after"])
+    cen = A.segmap_centroids(g["seg_after"], g["weightmap"], engine=make_engine())
+    assert cen.shape == g["centroids"].shape
+    np.testing.assert_allclose(cen, g["centroids"], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(A.segmap_bin_sn(g["seg_after"], g["image"], g["noise"], engine=make_engine()),
+                               g["bin_sn"], rtol=1e-12)

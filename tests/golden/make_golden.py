@@ -21,6 +21,12 @@ Fixtures (all tie-free by construction: integer pixel coordinates, jittered gene
   lloyd_points.npz    config C2 shape (small): 20000-point Gaussian starfield, EqualMassAccretor seeds
   segmap.npz          VoronoiTessellation.segmap / partition_points / sum_cell_point_mass
   from_image_nan.npz  CVTessellation.from_image on a map with NaN pixels (membership, nodes, node_weights)
+  accretor.npz        the shimmed EqualSNAccretor on a 40x40 map: segmentation image before and after
+                      cleanup(), _valid_bins, _current_bin_centroids, centroids, bin_sn
+                      (PointAccretor.bin_nums is a private cdef attribute of the compiled reference, so
+                      PointAccretor.nodes() cannot be pinned the same way)
+
+    python tests/golden/make_golden.py [name ...]     regenerates only the named fixtures
 """
 import builtins
 import io
@@ -101,8 +107,35 @@ def trajectory(ref_lloyd, xy, w, seeds, max_steps):
     return np.array(nodes), np.array(labels), conv_at
 
 
+def make_accretor(pa):
+    """EqualSNAccretor outputs (tess/pixel_accretion.py:212-240, 485-517) on a small map with a few
+    non-finite pixels; the accretion loop itself is out of scope (sequential), its products are not."""
+    rng = np.random.default_rng(17)
+    N = 40
+    img = gaussian_image(N, amp=6.0) + 0.3 + 0.05 * rng.normal(size=(N, N))
+    noise = np.ones((N, N)) + 0.1 * rng.uniform(size=(N, N))
+    (acc, _) = quiet(pa.EqualSNAccretor, img, noise, 12.0, start=(0, 0))
+    seg_before = np.array(acc.segmap, copy=True)
+    valid = np.array(acc._valid_bins, dtype=bool)
+    cen_rc = np.array(acc._current_bin_centroids, dtype=float)
+    quiet(acc.cleanup)
+    seg_after = np.array(acc.segmap, copy=True)
+    cent = np.asarray(acc.centroids, dtype=float)
+    sn = np.asarray(acc.bin_sn, dtype=float)
+    np.savez_compressed(os.path.join(HERE, "accretor.npz"), image=img, noise=noise, target_sn=12.0,
+                        seg_before=seg_before.astype(np.int32), valid_bins=valid, bin_centroids_rc=cen_rc,
+                        seg_after=seg_after.astype(np.int32), centroids=cent, bin_sn=sn,
+                        weightmap=np.asarray(acc.centroid_weightmap, dtype=float))
+    print("accretor: %d bins (%d failed), %d centroids" % (valid.size, int((~valid).sum()), cent.shape[0]))
+
+
 def main():
     ref_lloyd, vor, pa, pta = load_reference()
+    only = set(sys.argv[1:])
+    if only:
+        if "accretor" in only:
+            make_accretor(pa)
+        return
 
     # ------------------------------------------------------------------ lloyd_img64
     img = gaussian_image(64)
@@ -186,6 +219,8 @@ def main():
                         node_weights=np.asarray(cv.node_weights), segmap=np.asarray(cv.segmap).astype(np.int16),
                         n_iters=len(out.strip().splitlines()))
     print("from_image_nan: %d iterations" % len(out.strip().splitlines()))
+
+    make_accretor(pa)
 
 
 if __name__ == "__main__":

@@ -53,5 +53,9 @@ def test_accretion_helpers():
     frow_checks.check_accretion_helpers(EmuEngine)
 
 
+def test_accretion_helpers_against_reference_fixture():
+    frow_checks.check_accretor_fixture(EmuEngine)
+
+
 def test_wvt_binning_to_target_sn():
     frow_checks.check_wvt_binning(EmuEngine, N=56, k=10)

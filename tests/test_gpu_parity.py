@@ -565,6 +565,7 @@ def test_dense_centre_sparse_outskirts(eng):
 def test_accretion_helpers_gpu(engine_cls):
     import frow_checks
     frow_checks.check_accretion_helpers(lambda: engine_cls(0))
+    frow_checks.check_accretor_fixture(lambda: engine_cls(0))
 
 
 def test_wvt_binning_to_target_sn_gpu(engine_cls):
