@@ -132,6 +132,25 @@ TESS_DEVFN double tess_warp_sum(double v) {
 }
 TESS_DEVFN unsigned tess_lanemask_lt(int lane) { return (1u << lane) - 1u; }
 
+// Weight of a signal / noise pixel, w = (S / N)^2.  The quotient comes from a reciprocal seed of the
+// special-function unit refined by two Newton steps (~1 ulp): a correctly rounded fp64 division is
+// ~30 instructions, eight of them per lane and warp tile were a fifth of the S/N-mode kernel.  The
+// weight enters the per-bin SUMS only (tolerance 1e-12), never the labels.  N = 0, Inf or NaN (and
+// denormal N, flushed to zero by the seed) give a non-finite weight: the pixel is masked.
+TESS_DEVFN double tess_sn_weight(double S, double N) {
+#ifndef TESS_EMU
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(N));
+    r = fma(fma(-N, r, 1.0), r, r);
+    r = fma(fma(-N, r, 1.0), r, r);
+    const double q = S * r;
+    return q * q;
+#else
+    const double q = S / N;
+    return q * q;
+#endif
+}
+
 // The pinned squared distance: fl(fl(dx*dx) + fl(dy*dy)), never contracted to an FMA.
 TESS_DEVFN double tess_d2_pinned(double px, double py, double gx, double gy) {
     double dx = __dsub_rn(px, gx);

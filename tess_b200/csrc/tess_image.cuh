@@ -268,7 +268,7 @@ TESS_NOINLINE void tess_rows_scan(const TessImgArgs& a, int32_t* labels, long qx
             } else {
                 const double S = a.sig[idx], N = a.noise[idx];
                 double w = 1.0;
-                if (!a.uniform_weight) { const double q = __ddiv_rn(S, N); w = __dmul_rn(q, q); }
+                if (!a.uniform_weight) w = tess_sn_weight(S, N);
                 ok = isfinite(w) && isfinite(S) && isfinite(N);
                 val[0] = w; val[1] = __dmul_rn(w, X); val[2] = __dmul_rn(w, Y[j]);
                 val[NV - 2] = S; val[NV - 1] = __dmul_rn(N, N);
@@ -315,7 +315,7 @@ TESS_NOINLINE void tess_rows_ring(const TessImgArgs& a, int32_t* labels, long qx
             } else {
                 const double S = a.sig[idx], N = a.noise[idx];
                 double w = 1.0;
-                if (!a.uniform_weight) { const double q = __ddiv_rn(S, N); w = __dmul_rn(q, q); }
+                if (!a.uniform_weight) w = tess_sn_weight(S, N);
                 ok = isfinite(w) && isfinite(S) && isfinite(N);
                 val[0] = w; val[1] = __dmul_rn(w, X); val[2] = __dmul_rn(w, Y);
                 val[NV - 2] = S; val[NV - 1] = __dmul_rn(N, N);
@@ -754,7 +754,7 @@ TESS_DEVFN void tess_quadrant_body(const TessImgArgs& a, TessWarpSmem<MODE, HAS_
                 if (MODE == 2) {
                     const double S = w_[r][c], N = n_[r][c];
                     w = 1.0;
-                    if (!a.uniform_weight) { const double qq = __ddiv_rn(S, N); w = __dmul_rn(qq, qq); }
+                    if (!a.uniform_weight) w = tess_sn_weight(S, N);
                     // a non-finite signal or noise poisons the weight
                     if (!((fabs(S) <= 1.7976931348623157e308) && (fabs(N) <= 1.7976931348623157e308))) w = TESS_NAN;
                 }

@@ -93,7 +93,7 @@ TESS_DEVFN void tess_p_compare_labels(TessState* st, int mask_mode, int32_t* lab
         if (mask_mode == 2) {
             const double S = sig[i], N = noise[i];
             double wv = 1.0;
-            if (!uniform_weight) { const double q = __ddiv_rn(S, N); wv = __dmul_rn(q, q); }
+            if (!uniform_weight) wv = tess_sn_weight(S, N);
             ok = isfinite(S) && isfinite(N) && isfinite(wv);
         }
         if (ok && cur[i] != prev[i]) ++diff;
