@@ -332,133 +332,156 @@ TESS_NOINLINE void tess_rows_ring(const TessImgArgs& a, int32_t* labels, long qx
     __syncwarp();
 }
 
-// ---- lane groups of the list filters: 16 lanes (16x16 block: the lanes of eight adjacent
-// pixel-column pairs, both row halves) or 8 lanes (8x8 leaf)
-template <int GROUP>
-TESS_DEVFN int tess_group_rank(int lane) {
-    if (GROUP == 16) return (lane & 7) | ((lane >> 4) << 3);
-    return (lane & 3) | ((lane >> 4) << 2);
-}
-template <int GROUP>
-TESS_DEVFN unsigned tess_group_bits(unsigned bb, int lane) {
-    if (GROUP == 16) {
-        const int h = (lane >> 3) & 1;
-        return ((bb >> (8 * h)) & 0xFFu) | (((bb >> (16 + 8 * h)) & 0xFFu) << 8);
-    }
-    const int l = (lane >> 2) & 3;
-    return ((bb >> (4 * l)) & 0xFu) | (((bb >> (16 + 4 * l)) & 0xFu) << 4);
-}
-template <int GROUP>
-TESS_DEVFN double tess_group_min(double v) {
-    v = fmin(v, __shfl_xor_sync(TESS_FULL, v, 1));
-    v = fmin(v, __shfl_xor_sync(TESS_FULL, v, 2));
-    if (GROUP >= 16) v = fmin(v, __shfl_xor_sync(TESS_FULL, v, 4));
-    v = fmin(v, __shfl_xor_sync(TESS_FULL, v, 16));
-    return v;
-}
-
-// Centre + radius filter of a candidate list for the rectangle with centre (ccx, ccy) and
-// half-diagonal rho, done by a group of GROUP lanes:
+// ---- 16x16 block lists (quadrant lists longer than TESS_BLOCK_MIN only).  Centre + radius filter of
+// the quadrant list for two 16x16 blocks side by side, each done by 16 lanes (the lanes of eight
+// adjacent pixel-column pairs, both row halves):
 //   keep g  iff  u(c,g) <= min_h u(c,h) + 2 rho / s_min      (u = distance / scale)
-// The input list holds plen positions e_i = pident ? i : pl[i] of the quadrant list (qxy / qinv).
-// Order preserving.  Survivors' positions go to `out` (LEAF: also their coordinates to lg / li).
-// Returns the number of survivors (which may exceed `cap`: the caller then keeps using the parent
-// list).  plen may differ between groups of a warp; plen_max is its maximum over the warp.
-template <int GROUP, bool HAS_SCALE, bool LEAF>
-TESS_DEVFN int tess_filter(const double2* qxy, const double* qinv, const unsigned short* pl, bool pident, int plen,
-                           int plen_max, double ccx, double ccy, double rho, bool active, int lane, unsigned short* out,
-                           double2* lg, double* li, int cap) {
-    const int rank = tess_group_rank<GROUP>(lane);
+// Order preserving; the survivors' quadrant-list positions go to `out` (at most `cap` of them).
+// Returns the number of survivors of the lane's block (which may exceed `cap`).
+template <bool HAS_SCALE>
+TESS_DEVFN int tess_block_filter(const double2* qxy, const double* qinv, int plen, double ccx, double ccy, double rho,
+                                 bool active, int lane, unsigned short* out, int cap) {
+    const int rank = (lane & 7) | ((lane >> 4) << 3);
+    const int half = (lane >> 3) & 1;
     double umin = INFINITY, imax = 1.0;
-    int n = 0;
-    if (plen_max <= 3 * GROUP) {
-        // ---- short parent list (the common case): every lane holds its (at most three) centre
-        //      distances in registers, so the list is read and measured once
-        double dd[3];
-        int ee[3];
-#pragma unroll
-        for (int t = 0; t < 3; ++t) {
-            const int i = rank + GROUP * t;
-            dd[t] = INFINITY;
-            ee[t] = 0;
-            if (i < plen) {
-                const int e = pident ? i : (int)pl[i];
-                const double2 g = qxy[e];
-                const double dx = ccx - g.x, dy = ccy - g.y;
-                double d = dx * dx + dy * dy;
-                if (HAS_SCALE) { const double iv = qinv[e]; d *= iv; imax = fmax(imax, iv); }
-                dd[t] = d;
-                ee[t] = e;
-            }
-        }
-        umin = tess_group_min<GROUP>(fmin(fmin(dd[0], dd[1]), dd[2]));
-        double c = 2.0 * rho;
-        if (HAS_SCALE) {
-            imax = -tess_group_min<GROUP>(-imax);
-            c *= tess_sqrt_up(imax);
-        }
-        const double thr = tess_center_thr(umin, c);
-#pragma unroll
-        for (int t = 0; t < 3; ++t) {
-            if (GROUP * t < plen_max) {                          // warp-uniform (ballots inside)
-                const bool keep = active && (dd[t] <= thr);      // dd = inf beyond the list
-                const unsigned gb = tess_group_bits<GROUP>(__ballot_sync(TESS_FULL, keep), lane);
-                const int pos = n + __popc(gb & ((1u << rank) - 1u));
-                if (keep && pos < cap) {
-                    out[pos] = (unsigned short)ee[t];
-                    if (LEAF) {
-                        lg[pos] = qxy[ee[t]];
-                        if (HAS_SCALE) li[pos] = qinv[ee[t]];
-                    }
-                }
-                n += __popc(gb);
-            }
-        }
-        __syncwarp();
-        return n;
-    }
-    for (int i = rank; i < plen; i += GROUP) {
-        const int e = pident ? i : (int)pl[i];
-        const double2 g = qxy[e];
+#pragma unroll 2
+    for (int i = rank; i < plen; i += 16) {
+        const double2 g = qxy[i];
         const double dx = ccx - g.x, dy = ccy - g.y;
         double d = dx * dx + dy * dy;
-        if (HAS_SCALE) { const double iv = qinv[e]; d *= iv; imax = fmax(imax, iv); }
+        if (HAS_SCALE) { const double iv = qinv[i]; d *= iv; imax = fmax(imax, iv); }
         umin = fmin(umin, d);
     }
-    umin = tess_group_min<GROUP>(umin);
+    umin = fmin(umin, __shfl_xor_sync(TESS_FULL, umin, 1));
+    umin = fmin(umin, __shfl_xor_sync(TESS_FULL, umin, 2));
+    umin = fmin(umin, __shfl_xor_sync(TESS_FULL, umin, 4));
+    umin = fmin(umin, __shfl_xor_sync(TESS_FULL, umin, 16));
     double c = 2.0 * rho;
     if (HAS_SCALE) {
-        imax = -tess_group_min<GROUP>(-imax);
+        imax = fmax(imax, __shfl_xor_sync(TESS_FULL, imax, 1));
+        imax = fmax(imax, __shfl_xor_sync(TESS_FULL, imax, 2));
+        imax = fmax(imax, __shfl_xor_sync(TESS_FULL, imax, 4));
+        imax = fmax(imax, __shfl_xor_sync(TESS_FULL, imax, 16));
         c *= tess_sqrt_up(imax);
     }
     const double thr = tess_center_thr(umin, c);
-    for (int b0 = 0; b0 < plen_max; b0 += GROUP) {     // plen_max: warp-uniform bound (ballots inside)
+    int n = 0;
+#pragma unroll 2
+    for (int b0 = 0; b0 < plen; b0 += 16) {            // plen is warp-uniform (ballots inside)
         const int i = b0 + rank;
         bool keep = false;
-        int e = 0;
-        double2 g = make_double2(0.0, 0.0);
-        double iv = 1.0;
         if (i < plen) {
-            e = pident ? i : (int)pl[i];
-            g = qxy[e];
+            const double2 g = qxy[i];
             const double dx = ccx - g.x, dy = ccy - g.y;
             double d = dx * dx + dy * dy;
-            if (HAS_SCALE) { iv = qinv[e]; d *= iv; }
+            if (HAS_SCALE) d *= qinv[i];
             keep = active && (d <= thr);
         }
-        const unsigned gb = tess_group_bits<GROUP>(__ballot_sync(TESS_FULL, keep), lane);
+        const unsigned bb = __ballot_sync(TESS_FULL, keep);
+        const unsigned gb = ((bb >> (8 * half)) & 0xFFu) | (((bb >> (16 + 8 * half)) & 0xFFu) << 8);
         const int pos = n + __popc(gb & ((1u << rank) - 1u));
-        if (keep && pos < cap) {
-            out[pos] = (unsigned short)e;
-            if (LEAF) {
-                lg[pos] = g;
-                if (HAS_SCALE) li[pos] = iv;
-            }
-        }
+        if (keep && pos < cap) out[pos] = (unsigned short)i;
         n += __popc(gb);
     }
     __syncwarp();
     return n;
+}
+
+// ---- the candidate sets of all sixteen 8x8 leaves of a quadrant at once, as bit masks over a parent
+// list of at most 64 entries (the quadrant list itself, or the 16x16 block list of the leaf's block:
+// `pl`, positions in the quadrant list).  Leaf L = lane >> 1 is done by the lane pair (2L, 2L+1): each
+// lane measures every other entry of the parent list against the leaf's centre,
+//   keep g  iff  u(c,g) <= min_h u(c,h) + 2 rho / s_min      (u = distance / scale)
+// which can never drop the true nearest generator of any pixel of the leaf.  Bit i of (lo, hi) =
+// parent entry i survives; both lanes of the pair return the leaf's whole mask.  One shuffle for the
+// minimum and one for the mask per QUADRANT (the per-warp-tile filter this replaces cost four
+// fp64 shuffle rounds, a compaction with ballots and a rewrite of the survivors' records per tile).
+// The test is a bound, not a result, so it is done on fp32 copies of the fp64 centre distances that
+// err on the safe side only (distances rounded down, the minimum and the threshold rounded up): a
+// borderline candidate too many is evaluated exactly like every other survivor.
+template <bool HAS_SCALE>
+TESS_DEVFN float tess_center_d2_lo(const double2* qxy, const double* qinv, int e, double ccx, double ccy, double& imax) {
+    const double2 g = qxy[e];
+    const double dx = ccx - g.x, dy = ccy - g.y;
+    double d = dx * dx + dy * dy;
+    if (HAS_SCALE) { const double iv = qinv[e]; d *= iv; imax = fmax(imax, iv); }
+#ifndef TESS_EMU
+    return __double2float_rd(d);
+#else
+    float f = (float)d;
+    if ((double)f > d) f = nextafterf(f, -INFINITY);
+    return f;
+#endif
+}
+template <bool HAS_SCALE>
+TESS_DEVFN void tess_leaf_masks(const double2* qxy, const double* qinv, const unsigned short* pl, bool ident, int plen,
+                                double ccx, double ccy, double rho, int lane, unsigned& lo, unsigned& hi) {
+    const int h = lane & 1;
+    const int last = max(plen - 1, 0);
+    double imax = 1.0;
+    // the first sixteen parent entries (eight per lane): loads issued together (entries beyond the
+    // list re-read its last one and are discarded), distances kept in registers for the second pass
+    float dd[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const int i = 2 * t + h;
+        int e = min(i, last);
+        if (!ident) e = (plen > 0) ? (int)pl[e] : 0;
+        const float d = tess_center_d2_lo<HAS_SCALE>(qxy, qinv, e, ccx, ccy, imax);
+        dd[t] = (i < plen) ? d : INFINITY;
+    }
+    float fmn = fminf(fminf(fminf(dd[0], dd[1]), fminf(dd[2], dd[3])), fminf(fminf(dd[4], dd[5]), fminf(dd[6], dd[7])));
+    // longer parent lists: the rest is measured twice
+#pragma unroll 2
+    for (int i = 16 + h; i < plen; i += 2) {
+        const int e = ident ? i : (int)pl[i];
+        fmn = fminf(fmn, tess_center_d2_lo<HAS_SCALE>(qxy, qinv, e, ccx, ccy, imax));
+    }
+    fmn = fminf(fmn, __shfl_xor_sync(TESS_FULL, fmn, 1));
+    // an upper bound of the true minimum: the next float up (fmn is a rounded-down, non-negative value)
+    const double umin = (double)__int_as_float(__float_as_int(fmn) + 1);
+    double c = 2.0 * rho;
+    if (HAS_SCALE) {
+        imax = fmax(imax, __shfl_xor_sync(TESS_FULL, imax, 1));
+        c *= tess_sqrt_up(imax);
+    }
+#ifndef TESS_EMU
+    const float thr = __double2float_ru(tess_center_thr(umin, c));
+#else
+    const float thr = nextafterf((float)tess_center_thr(umin, c), INFINITY);
+#endif
+    unsigned m16 = 0u;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) m16 |= (dd[t] <= thr) ? (1u << (2 * t)) : 0u;     // (inf beyond the list)
+    unsigned long long mm = (unsigned long long)(m16 << h);
+#pragma unroll 2
+    for (int i = 16 + h; i < plen; i += 2) {
+        const int e = ident ? i : (int)pl[i];
+        double dummy = 1.0;
+        const float d = tess_center_d2_lo<HAS_SCALE>(qxy, qinv, e, ccx, ccy, dummy);
+        mm |= (d <= thr) ? (1ull << i) : 0ull;
+    }
+    const unsigned mlo = (unsigned)mm, mhi = (unsigned)(mm >> 32);
+    lo = mlo | __shfl_xor_sync(TESS_FULL, mlo, 1);
+    hi = mhi | __shfl_xor_sync(TESS_FULL, mhi, 1);
+}
+
+// Takes the lowest set bit out of the 64-bit mask (lo, hi): its parent-list entry is translated to
+// the quadrant-list position `e` (0 when the mask was empty: a harmless read).  Returns whether
+// there was a bit.
+TESS_DEVFN bool tess_mask_pop(unsigned& lo, unsigned& hi, const unsigned short* pl, bool ident, int& e) {
+    const bool have = (lo | hi) != 0u;
+    const bool in_lo = lo != 0u;
+    const unsigned w = in_lo ? lo : hi;
+    int idx = (__ffs((int)w) - 1) + (in_lo ? 0 : 32);
+    const unsigned w2 = w & (w - 1u);
+    lo = in_lo ? w2 : 0u;
+    hi = in_lo ? hi : w2;
+    idx = have ? idx : 0;
+    int ee = idx;
+    if (!ident) ee = (int)pl[idx];
+    e = have ? ee : 0;
+    return have;
 }
 
 // Loads the lane's 2x4 pixel patch whose first pixel is (px, py): weight (MODE 1) or signal and
@@ -497,11 +520,49 @@ struct TessWarpSmem {
     double2 qxy[2][QC];                                      // quadrant list (double buffered): coordinates,
     double qinv[HAS_SCALE ? 2 : 1][HAS_SCALE ? QC : 1];     //   1/scale^2,
     int qgid[2][QC];                                         //   generator index
-    double2 lg[4][TESS_LEAF_CAP + 1];                        // leaf lists (+1: read-ahead pad): coordinates,
-    double li[HAS_SCALE ? 4 : 1][HAS_SCALE ? TESS_LEAF_CAP + 1 : 1];   //   1/scale^2,
-    unsigned short ls[4][TESS_LEAF_CAP + 2];                 //   quadrant-list position
-    unsigned short bl[2][TESS_BCAP];                         // 16x16 block lists (positions)
+    unsigned short bl[4][TESS_BCAP];                         // 16x16 block lists (quadrant-list positions)
 };
+
+// A quadrant whose pixels all belong to generator `gid` (interior, MODE 1): constant labels and
+// closed-form patch sums that simply extend the lane's run.  Returns false (and leaves the run alone)
+// if some pixel is masked: the caller then takes the general path, which rewrites the labels.
+template <int NV>
+TESS_DEVFN bool tess_one_bin_quadrant(const TessImgArgs& a, int32_t* labels, const double* src, int gid, int px, int qy0,
+                                      int ry, double X0, double X1, int lane, TessRun<NV>& cur) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    bool clean = true;
+#pragma unroll
+    for (int step = 0; step < 4; ++step) {
+        const int py = qy0 + 8 * step + 4 * ry;
+        const long base0 = (long)py * a.W + px;
+        double2 v[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            v[r] = *reinterpret_cast<const double2*>(src + base0 + r * a.W);
+            *reinterpret_cast<int2*>(labels + base0 + r * a.W) = make_int2(gid, gid);
+        }
+        const double c0 = __dadd_rn(__dadd_rn(v[0].x, v[1].x), __dadd_rn(v[2].x, v[3].x));
+        const double c1 = __dadd_rn(__dadd_rn(v[0].y, v[1].y), __dadd_rn(v[2].y, v[3].y));
+        double sy = 0.0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) sy = __dadd_rn(sy, __dmul_rn(__dadd_rn(v[r].x, v[r].y), a.y0 + (double)(py + r)));
+        const double t = __dadd_rn(c0, c1);
+        clean = clean && (fabs(t) <= 1.7976931348623157e308);
+        s0 = __dadd_rn(s0, t);
+        s1 = __dadd_rn(s1, __dadd_rn(__dmul_rn(c0, X0), __dmul_rn(c1, X1)));
+        s2 = __dadd_rn(s2, sy);
+    }
+    if (!__all_sync(TESS_FULL, clean)) return false;
+    // the whole quadrant joins the lane's run (no shuffles, no reductions while the bin lasts)
+    const bool sw = (cur.key != gid);
+    tess_run_flush<NV>(sw && cur.n > 0, cur, a.mom, lane);
+    tess_run_switch<NV>(sw, gid, cur);
+    cur.n += 32;
+    cur.v[0] = __dadd_rn(cur.v[0], s0);
+    cur.v[1] = __dadd_rn(cur.v[1], s1);
+    cur.v[2] = __dadd_rn(cur.v[2], s2);
+    return true;
+}
 
 // One quadrant on the fast path (list of at most QCAP candidates staged in sm.q*[buf]).  INTERIOR:
 // every pixel access is in bounds and 16-byte aligned (128-bit loads, 64-bit label stores, constant
@@ -522,50 +583,59 @@ TESS_DEVFN void tess_quadrant_body(const TessImgArgs& a, TessWarpSmem<MODE, HAS_
     const int px = qx0 + 2 * cx;                     // first column of this lane
     const double X0 = a.x0 + (double)px, X1 = a.x0 + (double)(px + 1);
 
-    // ---- one-bin quadrant (a single candidate, interior, MODE 1): constant labels, closed-form
-    //      patch sums that simply extend the lane's run
-    if (MODE == 1 && c_q == 1 && interior) {
-        const int gid = gidv[0];
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-        bool clean = true;
-#pragma unroll
-        for (int step = 0; step < 4; ++step) {
-            const int py = qy0 + 8 * step + 4 * ry;
-            const long base0 = (long)py * a.W + px;
-            double2 v[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                v[r] = *reinterpret_cast<const double2*>(src + base0 + r * a.W);
-                *reinterpret_cast<int2*>(labels + base0 + r * a.W) = make_int2(gid, gid);
-            }
-            const double c0 = __dadd_rn(__dadd_rn(v[0].x, v[1].x), __dadd_rn(v[2].x, v[3].x));
-            const double c1 = __dadd_rn(__dadd_rn(v[0].y, v[1].y), __dadd_rn(v[2].y, v[3].y));
-            double sy = 0.0;
-#pragma unroll
-            for (int r = 0; r < 4; ++r) sy = __dadd_rn(sy, __dmul_rn(__dadd_rn(v[r].x, v[r].y), a.y0 + (double)(py + r)));
-            const double t = __dadd_rn(c0, c1);
-            clean = clean && (fabs(t) <= 1.7976931348623157e308);
-            s0 = __dadd_rn(s0, t);
-            s1 = __dadd_rn(s1, __dadd_rn(__dmul_rn(c0, X0), __dmul_rn(c1, X1)));
-            s2 = __dadd_rn(s2, sy);
-        }
-        if (__all_sync(TESS_FULL, clean)) {
-            // the whole quadrant joins the lane's run (no shuffles, no reductions while the bin lasts)
-            const bool sw = (cur.key != gid);
-            tess_run_flush<NV>(sw && cur.n > 0, cur, a.mom, lane);
-            tess_run_switch<NV>(sw, gid, cur);
-            cur.n += 32;
-            cur.v[0] = __dadd_rn(cur.v[0], s0);
-            cur.v[1] = __dadd_rn(cur.v[1], s1);
-            cur.v[2] = __dadd_rn(cur.v[2], s2);
-            return;
-        }
-        // a masked pixel somewhere: fall through to the general path (labels are rewritten there)
-    }
+    int one_gid = (c_q == 1) ? gidv[0] : -1;      // the quadrant's only bin, if it has one (warp-uniform)
 
-    const unsigned short* pl = nullptr;   // parent list of the leaf filter (quadrant-list positions)
-    bool p_ident = true;
-    int p_len = c_q;
+    // ---- candidate sets of the quadrant's sixteen 8x8 leaves, once per quadrant: lane pair
+    //      (2L, 2L+1) holds the mask of leaf L = 4 (leaf row) + (leaf column) over its parent list --
+    //      the quadrant list itself, or (long lists) the list of the leaf's 16x16 block
+    unsigned mlo = 0u, mhi = 0u;          // mask of leaf (lane >> 1)
+    bool ident = true;                    // parent lists are the quadrant list (warp-uniform)
+    bool slowq = false;                   // a block list overflowed: every pixel scans the quadrant list (rare)
+    if (c_q > 1) {
+        const int L = lane >> 1, lxi = L & 3, lyi = L >> 2;
+        int plen = c_q;
+        const unsigned short* plm = nullptr;
+        if (c_q > TESS_BLOCK_MIN) {
+            int nb[2];
+#pragma unroll
+            for (int hb = 0; hb < 2; ++hb) {              // top / bottom pair of blocks
+                const int bx0 = qx0 + 16 * blk, by0 = qy0 + 16 * hb;
+                const int bx1 = interior ? bx0 + 15 : min(bx0 + 15, Wi - 1), by1 = interior ? by0 + 15 : min(by0 + 15, Hi - 1);
+                const double hx = 0.5 * (double)(bx1 - bx0), hy = 0.5 * (double)(by1 - by0);
+                const double rho = interior ? 10.606602778 : sqrt(fmax(hx * hx + hy * hy, 0.0)) * 1.0000001;   // 7.5 sqrt 2
+                nb[hb] = tess_block_filter<HAS_SCALE>(qxy, qinv, c_q, a.x0 + 0.5 * (double)(bx0 + bx1),
+                                                      a.y0 + 0.5 * (double)(by0 + by1), rho,
+                                                      interior || (bx0 < Wi && by0 < Hi), lane, sm.bl[2 * hb + blk], TESS_BCAP);
+            }
+            // lengths of the four block lists (lane 0 sits in block column 0, lane 8 in column 1)
+            const int n00 = __shfl_sync(TESS_FULL, nb[0], 0), n01 = __shfl_sync(TESS_FULL, nb[0], 8);
+            const int n10 = __shfl_sync(TESS_FULL, nb[1], 0), n11 = __shfl_sync(TESS_FULL, nb[1], 8);
+            slowq = max(max(n00, n01), max(n10, n11)) > TESS_BCAP;
+            ident = false;
+            const int b = 2 * (lyi >> 1) + (lxi >> 1);
+            plen = (b == 0) ? n00 : (b == 1) ? n01 : (b == 2) ? n10 : n11;
+            plm = sm.bl[b];
+        }
+        if (!slowq) {
+            const int lx0 = qx0 + 8 * lxi, ly0 = qy0 + 8 * lyi;
+            const int lx1 = interior ? lx0 + 7 : min(lx0 + 7, Wi - 1), ly1 = interior ? ly0 + 7 : min(ly0 + 7, Hi - 1);
+            const double hx = 0.5 * (double)(lx1 - lx0), hy = 0.5 * (double)(ly1 - ly0);
+            const double rho = interior ? 4.9497479632 : sqrt(fmax(hx * hx + hy * hy, 0.0)) * 1.0000001;   // 3.5 sqrt 2
+            const bool active = interior || (lx0 < Wi && ly0 < Hi);
+            tess_leaf_masks<HAS_SCALE>(qxy, qinv, plm, ident, active ? plen : 0, a.x0 + 0.5 * (double)(lx0 + lx1),
+                                       a.y0 + 0.5 * (double)(ly0 + ly1), rho, lane, mlo, mhi);
+            // ---- all sixteen leaves ended with the same single candidate: the quadrant is one bin
+            if (MODE == 1 && interior && ident) {
+                const unsigned m0 = __shfl_sync(TESS_FULL, mlo, 0);
+                if (__all_sync(TESS_FULL, (mlo == m0) && (mhi == 0u)) && __popc(m0) == 1) one_gid = gidv[__ffs((int)m0) - 1];
+            }
+        }
+    }
+    // ---- one-bin quadrant (interior, MODE 1): constant labels, closed-form patch sums
+    if (MODE == 1 && interior && one_gid >= 0) {
+        if (tess_one_bin_quadrant<NV>(a, labels, src, one_gid, px, qy0, ry, X0, X1, lane, cur)) return;
+        // a masked pixel somewhere: the general path below rewrites the labels
+    }
 
     for (int step = 0; step < 4; ++step) {
         const int wy0 = qy0 + 8 * step;
@@ -582,61 +652,22 @@ TESS_DEVFN void tess_quadrant_body(const TessImgArgs& a, TessWarpSmem<MODE, HAS_
         double w_[4][2], n_[4][2];                     // MODE 1: weight; MODE 2: signal, noise
         if (MODE != 0) tess_load_patch<MODE>(a, src, interior, px, py, w_, n_);
 
-        // ---- 16x16 block lists (every other step), only where the quadrant list is long
-        if ((step & 1) == 0) {
-            pl = nullptr; p_ident = true; p_len = c_q;
-            if (c_q > TESS_BLOCK_MIN) {
-                const int bx0 = qx0 + 16 * blk;
-                const int bx1 = interior ? bx0 + 15 : min(bx0 + 15, Wi - 1), by1 = interior ? wy0 + 15 : min(wy0 + 15, Hi - 1);
-                const double hx = 0.5 * (double)(bx1 - bx0), hy = 0.5 * (double)(by1 - wy0);
-                const double rho = interior ? 10.606602778 : sqrt(hx * hx + hy * hy) * 1.0000001;   // 7.5 sqrt 2
-                const int n = tess_filter<16, HAS_SCALE, false>(qxy, qinv, nullptr, true, c_q, c_q,
-                                                                a.x0 + 0.5 * (double)(bx0 + bx1),
-                                                                a.y0 + 0.5 * (double)(wy0 + by1), rho, interior || bx0 < a.W, lane,
-                                                                sm.bl[blk], nullptr, nullptr, TESS_BCAP);
-                // both blocks must fit for the (warp-uniform) parent switch
-                if (__all_sync(TESS_FULL, n <= TESS_BCAP)) { pl = sm.bl[blk]; p_ident = false; p_len = n; }
-            }
-        }
-
-        // ---- candidates of this lane's 8x8 leaf
-        double2* const lg = sm.lg[leaf];
-        unsigned short* const ls = sm.ls[leaf];
-        double* const li = HAS_SCALE ? sm.li[leaf] : nullptr;
-        int len = 0;                                   // entries of this lane's leaf list (lg / ls / li)
-        bool slow = false;                             // leaf list overflowed: evaluate the parent list instead
+        // ---- candidates of this lane's 8x8 leaf: the mask computed above, from the lane pair that
+        //      holds leaf 4 step + leaf
+        const unsigned short* const pl = ident ? nullptr : sm.bl[2 * (step >> 1) + blk];
+        const unsigned m_lo = __shfl_sync(TESS_FULL, mlo, 2 * (4 * step + leaf));
+        const unsigned m_hi = __shfl_sync(TESS_FULL, mhi, 2 * (4 * step + leaf));
         bool uniform = (c_q == 1);                     // the whole warp tile belongs to one bin
         int ukey = 0;
-        if (!uniform) {
-            const int p_max = __reduce_max_sync(TESS_FULL, p_len);    // the two blocks' lists differ in length
-            if (p_max > TESS_LEAF_MIN) {
-                const int lx0 = qx0 + 8 * leaf;
-                const int lx1 = interior ? lx0 + 7 : min(lx0 + 7, Wi - 1), ly1 = interior ? wy0 + 7 : min(wy0 + 7, Hi - 1);
-                const double hx = 0.5 * (double)(lx1 - lx0), hy = 0.5 * (double)(ly1 - wy0);
-                const double rho = interior ? 4.9497479632 : sqrt(hx * hx + hy * hy) * 1.0000001;   // 3.5 sqrt 2
-                len = tess_filter<8, HAS_SCALE, true>(qxy, qinv, pl, p_ident, p_len, p_max,
-                                                      a.x0 + 0.5 * (double)(lx0 + lx1),
-                                                      a.y0 + 0.5 * (double)(wy0 + ly1), rho, interior || lx0 < a.W, lane, ls, lg, li,
-                                                      TESS_LEAF_CAP);
-                slow = (len > TESS_LEAF_CAP);
-                // all (in-image) leaves ended with the same single candidate?
-                const int one = (len == 1) ? (int)ls[0] : ((interior || lx0 < a.W) ? -1 : -3);
-                const int ref = __reduce_max_sync(TESS_FULL, one);
-                uniform = (ref >= 0) && __all_sync(TESS_FULL, one == ref || one == -3);
-                ukey = ref;
-            } else {
-                // a handful of candidates: they all go to the leaf arrays unfiltered, so that the
-                // evaluation loop below has a single, branch-free way of reading its list
-                const int rk = tess_group_rank<8>(lane);
-                if (rk < p_len) {
-                    const int e = p_ident ? rk : (int)pl[rk];
-                    ls[rk] = (unsigned short)e;
-                    lg[rk] = qxy[e];
-                    if (HAS_SCALE) li[rk] = qinv[e];
-                }
-                len = p_len;
-                __syncwarp();
-            }
+        if (c_q > 1 && !slowq) {
+            // all (in-image) leaves ended with the same single candidate?
+            const int len = __popc(m_lo) + __popc(m_hi);
+            int e0 = (m_lo != 0u) ? (__ffs((int)m_lo) - 1) : ((m_hi != 0u) ? 31 + __ffs((int)m_hi) : 0);
+            if (!ident) e0 = (int)pl[e0];
+            const int one = (len == 1) ? e0 : ((interior || qx0 + 8 * leaf < Wi) ? -1 : -3);
+            const int ref = __reduce_max_sync(TESS_FULL, one);
+            uniform = (ref >= 0) && __all_sync(TESS_FULL, one == ref || one == -3);
+            ukey = ref;
         }
 
         int bs[4][2];                                  // winner per pixel: quadrant-list position, then generator id
@@ -665,21 +696,21 @@ TESS_DEVFN void tess_quadrant_body(const TessImgArgs& a, TessWarpSmem<MODE, HAS_
             for (int r = 0; r < 4; ++r)
 #pragma unroll
                 for (int c = 0; c < 2; ++c) { bd[r][c] = INFINITY; bs[r][c] = 0; }
-            const int n_ev = slow ? 0 : len;
-            bool tied = slow;          // an overflowed leaf list is evaluated by the exact loop below
+            bool tied = slowq;         // (a quadrant with an overflowed block list is done by the exact loop below)
+            // (the record of the NEXT candidate is read while this one is evaluated)
+            unsigned lo = slowq ? 0u : m_lo, hi = slowq ? 0u : m_hi;
+            int en;
+            bool more = tess_mask_pop(lo, hi, pl, ident, en);
+            double2 gn = qxy[en];
+            double invn = HAS_SCALE ? qinv[en] : 1.0;
 #pragma unroll 1     // the compiler's own 2x unrolling costs 1.3 % (instruction cache)
-            // (the record of the NEXT candidate is read while this one is evaluated: the arrays are
-            //  padded by one entry, so the read past the list is harmless)
-            double2 gn = lg[0];
-            int en = ls[0];
-            double invn = HAS_SCALE ? li[0] : 1.0;
-            for (int j = 0; j < n_ev; ++j) {
+            while (more) {
                 const double2 g = gn;
                 const int e = en;
                 const double inv = invn;
-                gn = lg[j + 1];
-                en = ls[j + 1];
-                if (HAS_SCALE) invn = li[j + 1];
+                more = tess_mask_pop(lo, hi, pl, ident, en);
+                gn = qxy[en];
+                if (HAS_SCALE) invn = qinv[en];
                 const double dx0 = __dsub_rn(X0, g.x), dx1 = __dsub_rn(X1, g.x);
                 const double dxx0 = __dmul_rn(dx0, dx0), dxx1 = __dmul_rn(dx1, dx1);
 #pragma unroll
@@ -701,12 +732,13 @@ TESS_DEVFN void tess_quadrant_body(const TessImgArgs& a, TessWarpSmem<MODE, HAS_
                 for (int r = 0; r < 4; ++r)
 #pragma unroll
                     for (int c = 0; c < 2; ++c) { bd[r][c] = INFINITY; bs[r][c] = 0; bg[r][c] = 0x7fffffff; }
-                const int n_ex = slow ? p_len : len;
+                lo = m_lo; hi = m_hi;
+                int j = 0;
 #pragma unroll 1
-                for (int j = 0; j < n_ex; ++j) {
+                for (;;) {
                     int e;
-                    if (!slow) e = ls[j];
-                    else e = p_ident ? j : (int)pl[j];
+                    if (slowq) { if (j >= c_q) break; e = j++; }
+                    else if (!tess_mask_pop(lo, hi, pl, ident, e)) break;
                     const double2 g = qxy[e];
                     const double inv = HAS_SCALE ? qinv[e] : 1.0;
                     const int gid = gidv[e];

@@ -198,6 +198,8 @@ static inline double __dsqrt_rn(double a) { return std::sqrt(a); }
 static inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 static inline long long __double_as_longlong(double d) { long long r; std::memcpy(&r, &d, 8); return r; }
 static inline double __longlong_as_double(long long l) { double r; std::memcpy(&r, &l, 8); return r; }
+static inline float __int_as_float(int i) { float r; std::memcpy(&r, &i, 4); return r; }
+static inline int __float_as_int(float f) { int r; std::memcpy(&r, &f, 4); return r; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
