@@ -43,7 +43,7 @@
 #define TESS_BCAP 64        // 16x16 block list capacity
 #endif
 #ifndef TESS_BLOCK_MIN
-#define TESS_BLOCK_MIN 20   // quadrant lists longer than this get the intermediate 16x16 level
+#define TESS_BLOCK_MIN 64   // quadrant lists longer than this (the leaf masks hold 64 entries) get the intermediate 16x16 level
 #endif
 #ifndef TESS_LEAF_MIN
 #define TESS_LEAF_MIN 3     // parent lists up to this length are evaluated without a leaf filter
@@ -61,6 +61,9 @@
 #endif
 #ifndef TESS_MERGE_MIN
 #define TESS_MERGE_MIN 12   // smallest group worth a shuffle tree
+#endif
+#ifndef TESS_EARLY_LOAD
+#define TESS_EARLY_LOAD 0   // 1: the next warp tile's pixels are requested before the fold of the current one
 #endif
 #ifndef TESS_PREFETCH
 #define TESS_PREFETCH 1     // the next quadrant's pixel tile is prefetched into L2 by the TMA unit
@@ -528,24 +531,31 @@ struct TessWarpSmem {
 // if some pixel is masked: the caller then takes the general path, which rewrites the labels.
 template <int NV>
 TESS_DEVFN bool tess_one_bin_quadrant(const TessImgArgs& a, int32_t* labels, const double* src, int gid, int px, int qy0,
-                                      int ry, double X0, double X1, int lane, TessRun<NV>& cur) {
+                                      int ry, double X0, double X1, int lane, const double (&w0)[4][2], TessRun<NV>& cur) {
+    // the patches of warp tiles 1..3 are requested together (tile 0 was loaded by the caller)
+    double2 v[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) v[0][r] = make_double2(w0[r][0], w0[r][1]);
+#pragma unroll
+    for (int step = 1; step < 4; ++step) {
+        const long base0 = (long)(qy0 + 8 * step + 4 * ry) * a.W + px;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) v[step][r] = *reinterpret_cast<const double2*>(src + base0 + r * a.W);
+    }
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
     bool clean = true;
 #pragma unroll
     for (int step = 0; step < 4; ++step) {
         const int py = qy0 + 8 * step + 4 * ry;
         const long base0 = (long)py * a.W + px;
-        double2 v[4];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            v[r] = *reinterpret_cast<const double2*>(src + base0 + r * a.W);
-            *reinterpret_cast<int2*>(labels + base0 + r * a.W) = make_int2(gid, gid);
-        }
-        const double c0 = __dadd_rn(__dadd_rn(v[0].x, v[1].x), __dadd_rn(v[2].x, v[3].x));
-        const double c1 = __dadd_rn(__dadd_rn(v[0].y, v[1].y), __dadd_rn(v[2].y, v[3].y));
+        for (int r = 0; r < 4; ++r) *reinterpret_cast<int2*>(labels + base0 + r * a.W) = make_int2(gid, gid);
+        const double c0 = __dadd_rn(__dadd_rn(v[step][0].x, v[step][1].x), __dadd_rn(v[step][2].x, v[step][3].x));
+        const double c1 = __dadd_rn(__dadd_rn(v[step][0].y, v[step][1].y), __dadd_rn(v[step][2].y, v[step][3].y));
         double sy = 0.0;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) sy = __dadd_rn(sy, __dmul_rn(__dadd_rn(v[r].x, v[r].y), a.y0 + (double)(py + r)));
+        for (int r = 0; r < 4; ++r)
+            sy = __dadd_rn(sy, __dmul_rn(__dadd_rn(v[step][r].x, v[step][r].y), a.y0 + (double)(py + r)));
         const double t = __dadd_rn(c0, c1);
         clean = clean && (fabs(t) <= 1.7976931348623157e308);
         s0 = __dadd_rn(s0, t);
@@ -584,6 +594,12 @@ TESS_DEVFN void tess_quadrant_body(const TessImgArgs& a, TessWarpSmem<MODE, HAS_
     const double X0 = a.x0 + (double)px, X1 = a.x0 + (double)(px + 1);
 
     int one_gid = (c_q == 1) ? gidv[0] : -1;      // the quadrant's only bin, if it has one (warp-uniform)
+
+    // ---- pixel data of the first warp tile: requested before the candidate masks are computed, so that
+    //      its latency hides behind them.  Pixels outside the image read as NaN and drop out with the
+    //      masked ones.  The following tiles' data is requested at the end of the tile before.
+    double w_[4][2], n_[4][2];                     // MODE 1: weight; MODE 2: signal, noise
+    if (MODE != 0) tess_load_patch<MODE>(a, src, interior, px, qy0 + 4 * ry, w_, n_);
 
     // ---- candidate sets of the quadrant's sixteen 8x8 leaves, once per quadrant: lane pair
     //      (2L, 2L+1) holds the mask of leaf L = 4 (leaf row) + (leaf column) over its parent list --
@@ -633,7 +649,7 @@ TESS_DEVFN void tess_quadrant_body(const TessImgArgs& a, TessWarpSmem<MODE, HAS_
     }
     // ---- one-bin quadrant (interior, MODE 1): constant labels, closed-form patch sums
     if (MODE == 1 && interior && one_gid >= 0) {
-        if (tess_one_bin_quadrant<NV>(a, labels, src, one_gid, px, qy0, ry, X0, X1, lane, cur)) return;
+        if (tess_one_bin_quadrant<NV>(a, labels, src, one_gid, px, qy0, ry, X0, X1, lane, w_, cur)) return;
         // a masked pixel somewhere: the general path below rewrites the labels
     }
 
@@ -645,12 +661,6 @@ TESS_DEVFN void tess_quadrant_body(const TessImgArgs& a, TessWarpSmem<MODE, HAS_
         double Y[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) Y[r] = a.y0 + (double)(py + r);
-
-        // ---- pixel data of this warp tile.  Pixels outside the image read as NaN and drop out with
-        //      the masked ones.  (Requesting them one warp tile ahead -- in registers or as L2/L1
-        //      prefetches -- measured slower: 16 warps per SM already hide the latency.)
-        double w_[4][2], n_[4][2];                     // MODE 1: weight; MODE 2: signal, noise
-        if (MODE != 0) tess_load_patch<MODE>(a, src, interior, px, py, w_, n_);
 
         // ---- candidates of this lane's 8x8 leaf: the mask computed above, from the lane pair that
         //      holds leaf 4 step + leaf
@@ -772,6 +782,12 @@ TESS_DEVFN void tess_quadrant_body(const TessImgArgs& a, TessWarpSmem<MODE, HAS_
             }
         }
         if (MODE == 0) continue;
+#if TESS_EARLY_LOAD
+        // the next warp tile's pixel data is requested before this tile's fold
+        double wn_[4][2], nn_[4][2];
+        const bool more_tiles = step < 3 && (interior || wy0 + 8 < a.H);
+        if (more_tiles) tess_load_patch<MODE>(a, src, interior, px, py + 8, wn_, nn_);
+#endif
 
         // ---- moments.  Weights first.  The sum of the patch's weights is finite iff all of them
         //      are (up to a harmless false alarm on overflow), so one test per lane decides whether
@@ -879,9 +895,33 @@ TESS_DEVFN void tess_quadrant_body(const TessImgArgs& a, TessWarpSmem<MODE, HAS_
                 }
             }
         }
+        // ---- the next warp tile's pixel data (into the registers this tile's fold has just released)
+#if TESS_EARLY_LOAD
+        if (more_tiles) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) { w_[r][c] = wn_[r][c]; if (MODE == 2) n_[r][c] = nn_[r][c]; }
+        }
+#else
+        if (step < 3 && (interior || wy0 + 8 < a.H)) tess_load_patch<MODE>(a, src, interior, px, py + 8, w_, n_);
+#endif
     }   // steps
 
     // (the lanes' runs stay live: the next quadrant may continue them)
+}
+
+// One ticket from the quadrant queue.  Plain PTX: the compiler's own atomicAdd is warp-aggregated, with
+// a shuffle of the result right behind it -- the warp then waits a whole atomic round trip (3.8 % of
+// the kernel's stall samples), although the ticket is not needed before the next chunk boundary.
+TESS_DEVFN int tess_queue_take(int* counter) {
+#ifndef TESS_EMU
+    int t;
+    asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(counter) : "memory");
+    return t;
+#else
+    return atomicAdd(counter, 1);
+#endif
 }
 
 // MODE 0: labels only; 1: density map (4 moments); 2: signal + noise maps (6 moments).
@@ -921,14 +961,14 @@ k_image_main(const TESS_GRID_CONSTANT TessImgArgs a, int vec, int use_tma, const
     constexpr int G = TESS_CHUNK;
     int* const counter = EDGE ? reinterpret_cast<int*>(&a.st->spare_) : &a.st->tile_counter;
     int tok = 0;                                   // lane 0: the chunk after the current one
-    if (lane == 0) tok = stride + atomicAdd(counter, 1);
+    if (lane == 0) tok = stride + tess_queue_take(counter);
     auto next_q = [&](int qq) {
         if (qq >= n_q) return n_q;
         int nq = qq + 1;
         if ((nq % G) == 0) {                       // chunk exhausted
             const int t = __shfl_sync(TESS_FULL, tok, 0);
             const bool more = t < (n_q + G - 1) / G;
-            if (lane == 0 && more) tok = stride + atomicAdd(counter, 1);
+            if (lane == 0 && more) tok = stride + tess_queue_take(counter);
             nq = more ? t * G : n_q;
         }
         return min(nq, n_q);
@@ -951,13 +991,13 @@ k_image_main(const TESS_GRID_CONSTANT TessImgArgs a, int vec, int use_tma, const
     stage(0, off, cnt);
 
     while (q < n_q) {
+        tess_cp_async_wait();          // this quadrant's list has landed (waited for BEFORE any new load
+        __syncwarp();                  //  is issued: the wait covers every load in flight)
+        if (q1 < n_q) stage(buf ^ 1, off1, cnt1);
         // (offset, count) of the quadrant after the next: in flight during this quadrant
         const int q2 = next_q(q1);
         int cnt2 = 0, off2 = 0;
         if (q2 < n_q) { cnt2 = a.L.q_cnt[q2]; off2 = a.L.q_off[q2]; }
-        tess_cp_async_wait();          // this quadrant's list has landed
-        __syncwarp();
-        if (q1 < n_q) stage(buf ^ 1, off1, cnt1);
         const int qy = q / a.L.nqx, qx = q - qy * a.L.nqx;
         const int qx0 = 32 * qx, qy0 = 32 * qy;            // pixel coordinates fit 32 bits (host-checked)
         const bool interior = vec && (qx0 + 32 <= a.W) && (qy0 + 32 <= a.H);
