@@ -51,7 +51,7 @@
 // quadrant list capacity of the fast path (records staged in the warp's shared memory)
 #define TESS_QCAP(MODE) 128
 #ifndef TESS_CHUNK
-#define TESS_CHUNK 2        // consecutive quadrants per draw from the device queue (4: -5 %, 8: -17 %: wider chunks spread the streams)
+#define TESS_CHUNK 1        // consecutive quadrants per draw from the device queue (2: +0.5 %, 4: +6 %: wider chunks spread the streams)
 #endif
 #ifndef TESS_RING_ROWS
 #define TESS_RING_ROWS 2
@@ -911,16 +911,23 @@ TESS_DEVFN void tess_quadrant_body(const TessImgArgs& a, TessWarpSmem<MODE, HAS_
     // (the lanes' runs stay live: the next quadrant may continue them)
 }
 
-// One ticket from the quadrant queue.  Plain PTX: the compiler's own atomicAdd is warp-aggregated, with
-// a shuffle of the result right behind it -- the warp then waits a whole atomic round trip (3.8 % of
-// the kernel's stall samples), although the ticket is not needed before the next chunk boundary.
-TESS_DEVFN int tess_queue_take(int* counter) {
+// One ticket from the quadrant queue.  The ticket is not needed before the next chunk boundary, but
+// both the compiler and ptxas "warp-aggregate" an atomic add of a provably uniform value under a
+// divergent predicate (vote, leader election, ONE atomic, shuffle of its result) -- and the shuffle
+// right behind the atomic makes the warp wait a whole round trip (~900 cycles per chunk, 2.5-3.8 % of
+// the kernel's stall samples).  The addend therefore comes from a per-lane slot of a constant-memory
+// table of ones: nothing to prove, nothing aggregated, the result register is simply scoreboarded.
+#ifndef TESS_EMU
+__constant__ int c_tess_ones[32] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1,
+                                    1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};
+#endif
+TESS_DEVFN int tess_queue_take(int* counter, int one) {
 #ifndef TESS_EMU
     int t;
-    asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(counter) : "memory");
+    asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(t) : "l"(counter), "r"(one) : "memory");
     return t;
 #else
-    return atomicAdd(counter, 1);
+    return atomicAdd(counter, one);
 #endif
 }
 
@@ -961,17 +968,31 @@ k_image_main(const TESS_GRID_CONSTANT TessImgArgs a, int vec, int use_tma, const
     constexpr int G = TESS_CHUNK;
     int* const counter = EDGE ? reinterpret_cast<int*>(&a.st->spare_) : &a.st->tile_counter;
     int tok = 0;                                   // lane 0: the chunk after the current one
-    if (lane == 0) tok = stride + tess_queue_take(counter);
+    #ifndef TESS_EMU
+    const int one = c_tess_ones[lane];
+#else
+    const int one = 1;
+#endif
+    if (lane == 0) tok = tess_queue_take(counter, one);      // (raw ticket: nothing may depend on it yet)
     auto next_q = [&](int qq) {
         if (qq >= n_q) return n_q;
         int nq = qq + 1;
         if ((nq % G) == 0) {                       // chunk exhausted
-            const int t = __shfl_sync(TESS_FULL, tok, 0);
+            const int t = stride + __shfl_sync(TESS_FULL, tok, 0);
             const bool more = t < (n_q + G - 1) / G;
-            if (lane == 0 && more) tok = stride + tess_queue_take(counter);
+            if (lane == 0 && more) tok = tess_queue_take(counter, one);
             nq = more ? t * G : n_q;
         }
         return min(nq, n_q);
+    };
+    // (row, column) of quadrant qq without an integer division: estimate by a reciprocal multiply
+    // (at most one too small for qq < 2^31), one correction
+    const unsigned nqx_u = (unsigned)a.L.nqx, q_magic = 0xffffffffu / nqx_u;
+    auto row_col = [&](int qq, int& col, int& row) {
+        unsigned r = __umulhi((unsigned)qq, q_magic);
+        unsigned c = (unsigned)qq - r * nqx_u;
+        if (c >= nqx_u) { c -= nqx_u; ++r; }
+        col = (int)c; row = (int)r;
     };
     int q = min(((int)blockIdx.x * NW + wib) * G, n_q);
     if ((long)((int)blockIdx.x * NW + wib) * G >= n_q) q = n_q;
@@ -998,13 +1019,15 @@ k_image_main(const TESS_GRID_CONSTANT TessImgArgs a, int vec, int use_tma, const
         const int q2 = next_q(q1);
         int cnt2 = 0, off2 = 0;
         if (q2 < n_q) { cnt2 = a.L.q_cnt[q2]; off2 = a.L.q_off[q2]; }
-        const int qy = q / a.L.nqx, qx = q - qy * a.L.nqx;
+        int qx, qy;
+        row_col(q, qx, qy);
         const int qx0 = 32 * qx, qy0 = 32 * qy;            // pixel coordinates fit 32 bits (host-checked)
         const bool interior = vec && (qx0 + 32 <= a.W) && (qy0 + 32 <= a.H);
 #if TESS_PREFETCH
         // the NEXT quadrant's pixels start their trip from DRAM now: one 256-byte row per lane
         if (MODE != 0 && !EDGE && use_tma && q1 < n_q && cnt1 > 0 && lane == 0) {
-            const int qy1 = q1 / a.L.nqx, qx1 = q1 - qy1 * a.L.nqx;
+            int qx1, qy1;
+            row_col(q1, qx1, qy1);
             tess_prefetch_tile(&tm0, 32 * qx1, 32 * qy1);          // (clipped at the image edge by the unit)
             if (MODE == 2) tess_prefetch_tile(&tm1, 32 * qx1, 32 * qy1);
         }
