@@ -51,7 +51,7 @@
 // quadrant list capacity of the fast path (records staged in the warp's shared memory)
 #define TESS_QCAP(MODE) 128
 #ifndef TESS_CHUNK
-#define TESS_CHUNK 1        // consecutive quadrants per draw from the device queue (2: +0.5 %, 4: +6 %: wider chunks spread the streams)
+#define TESS_CHUNK 2        // consecutive quadrants per draw from the device queue (C3 / C4 kernel: 1: 0.233 / 3.88 ms, 2: 0.234 / 3.06, 4: 0.247 / 3.07)
 #endif
 #ifndef TESS_RING_ROWS
 #define TESS_RING_ROWS 2

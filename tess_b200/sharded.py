@@ -27,14 +27,23 @@ def shard_rows(H, world, align=64):
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
-def balanced_row_shards(generators, H, W, world, x0=0.0, y0=0.0, align=64):
+# time per pixel of one accumulate as a function of the local generator density rho (generators per
+# pixel): a + b rho^p picoseconds (see balanced_row_shards)
+COST_MODEL = (2.56, 39.1, 0.40)
+
+
+def balanced_row_shards(generators, H, W, world, x0=0.0, y0=0.0, align=64, model=None):
     """Row ranges whose estimated cost is equal: the time per pixel of one accumulate (list building +
     image kernel) grows with the local generator density rho (generators per pixel) like
     2.56 + 39.1 rho^0.40 ps/px -- a least-squares fit to the per-rank accumulate times of the C4 map
-    on 8 GPUs under two different shardings (round-2 kernels; residuals <= 3 %; the fixed ~0.05 ms per
-    rank does not matter for the cuts) -- so equal-height shards of a centrally concentrated map
-    would leave the central ranks 2x slower than the outer ones.
-    `generators` is the (k, 2) table (host array); boundaries fall on multiples of `align` rows."""
+    on 8 GPUs under two different shardings -- so equal-height shards of a centrally concentrated map
+    would leave the central ranks 2x slower than the outer ones.  Checked against the final round-2
+    kernels on one GPU (tools/shard_cost_probe.py: the eight shards of C4 take 0.46-0.49 ms each,
+    max / mean = 1.027; a refit to 96 strips of 512 and 2048 rows, 2.28 + 63.5 rho^0.50, predicts the
+    same cuts to within one tile row, i.e. the model is at the noise limit of the measurements).
+    `generators` is the (k, 2) table (host array); boundaries fall on multiples of `align` rows;
+    `model` = (a, b, p) overrides COST_MODEL."""
+    ca, cb, cp = model if model is not None else COST_MODEL
     import numpy as np
     g = np.asarray(generators, dtype=np.float64)
     nty, ntx = (H + align - 1) // align, (W + align - 1) // align
@@ -44,7 +53,7 @@ def balanced_row_shards(generators, H, W, world, x0=0.0, y0=0.0, align=64):
     iy = np.clip(((g[:, 1] - y0) // align).astype(np.int64), 0, nty - 1)
     cnt = np.bincount(iy * ntx + ix, minlength=nty * ntx).reshape(nty, ntx).astype(np.float64)
     tile_px = float(align * align)
-    cost = (tile_px * (2.56 + 39.1 * (cnt / tile_px) ** 0.40)).sum(axis=1)     # per tile row
+    cost = (tile_px * (ca + cb * (cnt / tile_px) ** cp)).sum(axis=1)     # per tile row
     cum = np.concatenate(([0.0], np.cumsum(cost)))
     cuts = [0]
     for r in range(1, world):
