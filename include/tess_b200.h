@@ -75,9 +75,17 @@ enum {
     TESS_OPT_UNIFORM_WEIGHT = 2,   /* signal/noise mode only. 0 (default): w = fl(fl(S/N)^2)  */
                                    /* (scripts/demo_iso_sn_voronoi.py:26,37). 1: w = 1         */
                                    /* (geometric centroids, WVT).                              */
-    TESS_OPT_KERNEL_TIMING = 3     /* 1: bracket the dominant kernel of tess_lloyd_accumulate  */
+    TESS_OPT_KERNEL_TIMING = 3,    /* 1: bracket the dominant kernel of tess_lloyd_accumulate  */
                                    /* (pixel / point assignment + sums) with CUDA events on    */
                                    /* its stream; read with tess_get_kernel_timing.            */
+    TESS_OPT_OWNER_UPDATE = 4      /* multi-GPU, tess_peer_allreduce_sparse. 1: the rank that    */
+                                   /* owns a slice of the moment vector forms the new nodes of  */
+                                   /* its bins from the totals (lloyd.pyx:66-74) and broadcasts */
+                                   /* 16 bytes per bin instead of the 32-byte row; the totals   */
+                                   /* stay in the owner's copy of its slice; tess_lloyd_update  */
+                                   /* takes the broadcast nodes.  Needs 2 k more doubles in the */
+                                   /* caller's buffer (>= 6 k + 2 + 34); applies to 4-moment    */
+                                   /* rows without WVT scale updates, else the rows travel.     */
 };
 
 int tess_version(void);
@@ -173,6 +181,14 @@ int tess_peer_allreduce(tess_ctx* ctx, int world, int rank, double* const* peer_
  * summed length (tess_moments_ptr).
  */
 int tess_peer_publish_range(tess_ctx* ctx, void* stream);
+/*
+ * Optional: `multicast_ptr` = an NVLS multicast mapping of the caller's moment buffer (same offset 0 as
+ * the buffer given to tess_set_moment_buffer).  The broadcast half of tess_peer_allreduce_sparse then
+ * goes through the switch (one multimem.st per pair of totals reaches every rank's copy) instead of
+ * one bulk copy per destination rank; the reduce half is unchanged, the sums are the same bits.
+ * NULL (the default) returns to peer-to-peer copies.
+ */
+int tess_peer_set_multicast(tess_ctx* ctx, double* multicast_ptr);
 int tess_peer_allreduce_sparse(tess_ctx* ctx, int world, int rank, double* const* peer_ptrs, long n_doubles, void* stream);
 
 /* n_steps iterations back to back, no host synchronisation (benchmarks, fixed-step use). */

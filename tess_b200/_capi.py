@@ -20,6 +20,7 @@ MOM_COUNT, MOM_W, MOM_WX, MOM_WY, MOM_S, MOM_N2 = range(6)
 OPT_WVT_SCALE_UPDATE = 1
 OPT_UNIFORM_WEIGHT = 2
 OPT_KERNEL_TIMING = 3
+OPT_OWNER_UPDATE = 4
 
 _vp = ctypes.c_void_p
 _l = ctypes.c_long
@@ -42,6 +43,7 @@ SIGNATURES = {
     "tess_set_moment_buffer": (_i, [_vp, _vp, _l]),
     "tess_peer_allreduce": (_i, [_vp, _i, _i, ctypes.POINTER(_vp), _vp, _l, _vp]),
     "tess_peer_publish_range": (_i, [_vp, _vp]),
+    "tess_peer_set_multicast": (_i, [_vp, _vp]),
     "tess_peer_allreduce_sparse": (_i, [_vp, _i, _i, ctypes.POINTER(_vp), _l, _vp]),
     "tess_lloyd_update": (_i, [_vp, _vp]),
     "tess_lloyd_step": (_i, [_vp, _l, _vp]),

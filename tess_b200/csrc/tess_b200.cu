@@ -107,6 +107,9 @@ struct tess_ctx {
     const double* tmap_src[2];
     long tmap_hw[2];
     unsigned long long exchange_epoch;   // sparse exchanges launched so far (the barrier word of the next one)
+    double* sparse_mc;                   // multicast mapping of the caller's moment buffer (tess_peer_set_multicast) or null
+    int owner_update;                    // TESS_OPT_OWNER_UPDATE: the sparse exchange broadcasts owner-computed nodes
+    int staged_valid;                    // the node area of the caller's buffer holds this iteration's new nodes
     int index_valid;   // the generator grid in the workspace is that of the CURRENT nodes for index_geo
     TessGrid index_geo;
     int phase_grid;    // CTAs of k_iteration_phases (all resident: cooperative launch); 0 = not decided
@@ -188,6 +191,7 @@ extern "C" int tess_set_option(tess_ctx* c, int option, long value) {
         case TESS_OPT_WVT_SCALE_UPDATE: c->wvt_update = value ? 1 : 0; return TESS_OK;
         case TESS_OPT_UNIFORM_WEIGHT: c->uniform_weight = value ? 1 : 0; return TESS_OK;
         case TESS_OPT_KERNEL_TIMING: c->timing = value ? 1 : 0; return TESS_OK;
+        case TESS_OPT_OWNER_UPDATE: c->owner_update = value ? 1 : 0; return TESS_OK;
         default: return tess_fail(TESS_ERR_ARG, "tess_set_option: unknown option %d", option);
     }
 }
@@ -666,6 +670,7 @@ static bool same_grid(const TessGrid& a, const TessGrid& b) {
 static int n_moments(const tess_ctx* c);
 static unsigned long long* range_slots(tess_ctx* c);
 
+static long staged_off(tess_ctx* c);
 static void phase_args(tess_ctx* c, const Geometry& q, TessPhaseArgs* a) {
     memset(a, 0, sizeof(*a));
     a->st = c->st;
@@ -677,6 +682,7 @@ static void phase_args(tess_ctx* c, const Geometry& q, TessPhaseArgs* a) {
     a->wvt_update = c->wvt_update;
     a->delta_part = c->delta_part;
     a->range = range_slots(c);
+    a->staged = (c->staged_valid && staged_off(c) >= 0) ? c->mom + staged_off(c) : nullptr;
     a->mask_mode = (c->source == SRC_IMAGE) ? c->img_mode : 0;
     a->lab0 = c->lab[0]; a->lab1 = c->lab[1];
     a->n = (c->source == SRC_IMAGE) ? c->H * c->W : c->n_pts;
@@ -921,6 +927,7 @@ static int source_geometry(tess_ctx* c, cudaStream_t s, Geometry* q) {
 // accumulate without its closing "did anything change" phases (the caller appends them)
 static int accumulate_core(tess_ctx* c, const Geometry& q, cudaStream_t s) {
     const long n_rows = (long)c->k * n_moments(c);
+    c->staged_valid = 0;
     // the generator grid: left behind by the previous update (phases 3-6 of its launch), else built now
     if (!(c->index_valid && same_grid(q.g, c->index_geo))) TRY(run_phases(c, q, TESS_PH_UPDATE, TESS_PH_SCATTER, 0, s));
     c->index_valid = 0;
@@ -966,6 +973,7 @@ extern "C" int tess_set_moment_buffer(tess_ctx* c, double* buf, long n_doubles) 
     TRY(bind(c));
     if (!buf) {                       // back to a library-owned vector
         if (c->mom_external) { c->mom = nullptr; c->mom_cap = 0; c->mom_external = 0; }
+        c->sparse_mc = nullptr;
         return TESS_OK;
     }
     if (n_doubles < TESS_TAIL + 6 || ((uintptr_t)buf & 15u))
@@ -980,6 +988,16 @@ extern "C" int tess_set_moment_buffer(tess_ctx* c, double* buf, long n_doubles) 
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaStreamSynchronize(nullptr));
     return TESS_OK;
+}
+
+// offset (doubles) of the node area of the caller's buffer -- 2 k doubles right behind the vector -- or -1
+// when owner-computed updates do not apply (option off, 6-moment rows or WVT scale updates: those need
+// the totals everywhere; no room in the buffer)
+static long staged_off(tess_ctx* c) {
+    if (!c->owner_update || !c->mom_external || !c->mom || n_moments(c) != 4 || c->wvt_update) return -1;
+    const long off = (long)c->k * 4 + TESS_TAIL;          // even
+    if (c->mom_cap < off + 2L * c->k + TESS_SPARSE_EXTRA) return -1;
+    return off;
 }
 
 // slots of the published row range, or null when the caller's buffer has no room for them
@@ -1010,6 +1028,12 @@ extern "C" int tess_peer_allreduce(tess_ctx* c, int world, int rank, double* con
     return peer_allreduce(c, world, rank, peer_ptrs, multicast_ptr, n_doubles, 0, stream);
 }
 
+extern "C" int tess_peer_set_multicast(tess_ctx* c, double* multicast_ptr) {
+    TRY(bind(c));
+    c->sparse_mc = multicast_ptr;
+    return TESS_OK;
+}
+
 extern "C" int tess_peer_allreduce_sparse(tess_ctx* c, int world, int rank, double* const* peer_ptrs, long n_doubles,
                                           void* stream) {
     return peer_allreduce(c, world, rank, peer_ptrs, nullptr, n_doubles, 1, stream);
@@ -1028,7 +1052,16 @@ static int peer_allreduce(tess_ctx* c, int world, int rank, double* const* peer_
     if (n_doubles & 1) return tess_fail(TESS_ERR_ARG, "tess_peer_allreduce: n_doubles must be even");
     long per = (n_doubles + world - 1) / world;
     per += per & 1;
-    const long lo = per * rank, hi = (lo + per < n_doubles) ? lo + per : n_doubles;
+    long lo = per * rank, hi = (lo + per < n_doubles) ? lo + per : n_doubles;
+    const long node_off = sparse ? staged_off(c) : -1;
+    if (node_off >= 0) {
+        // owner-computed update: slices start on rows (4 doubles), the last rank also owns the tail
+        const long rows_per = ((long)c->k + world - 1) / world;
+        const long r0 = (rows_per * rank < c->k) ? rows_per * rank : c->k;
+        const long r1 = (rows_per * (rank + 1) < c->k) ? rows_per * (rank + 1) : c->k;
+        lo = r0 * 4;
+        hi = (rank == world - 1) ? n_doubles : r1 * 4;
+    }
     if (hi <= lo && !sparse) return TESS_OK;     // (the sparse kernel carries the cross-rank barriers: always launched)
     long nb = (hi - lo + 255) / 256;
     if (nb > c->sm_count * 8) nb = c->sm_count * 8;
@@ -1055,8 +1088,14 @@ static int peer_allreduce(tess_ctx* c, int world, int rank, double* const* peer_
             nb = (hi - lo + TESS_PEER_CHUNK - 1) / TESS_PEER_CHUNK;          // one 16 KB chunk per CTA and trip
             if (nb > c->sm_count * peer_ctas) nb = c->sm_count * peer_ctas;
             if (nb < 1) nb = 1;
-            TESS_LAUNCH((k_peer_sum_p2p_sparse), (int)nb, 256, S(stream), P, lo, hi, M, (long)c->k * M,
-                        range_off - TESS_FLAG_SLOTS, range_off, (unsigned long long)(++c->exchange_epoch),
+            c->staged_valid = node_off >= 0 ? 1 : 0;
+            if (c->sparse_mc && node_off < 0) {              // register path: no 16 KB chunks, a pair of totals per thread and trip
+                nb = ((hi - lo) / 2 + 255) / 256;
+                if (nb > c->sm_count * 4) nb = c->sm_count * 4;
+                if (nb < 1) nb = 1;
+            }
+            TESS_LAUNCH((k_peer_sum_p2p_sparse), (int)nb, 256, S(stream), P, node_off >= 0 ? nullptr : c->sparse_mc, lo, hi, M,
+                        (long)c->k * M, range_off - TESS_FLAG_SLOTS, range_off, node_off, (unsigned long long)(++c->exchange_epoch),
                         reinterpret_cast<unsigned*>(c->scratch + 6));
         } else {
             TESS_LAUNCH((k_peer_sum_p2p), (int)nb, 256, S(stream), P, lo, hi);
@@ -1076,6 +1115,7 @@ extern "C" int tess_lloyd_update(tess_ctx* c, void* stream) {
     Geometry q;
     TRY(source_geometry(c, s, &q));
     TRY(run_phases(c, q, TESS_PH_UPDATE, TESS_PH_SCATTER, 1, s));
+    c->staged_valid = 0;
     c->index_valid = 1;
     c->index_geo = q.g;
     return TESS_OK;

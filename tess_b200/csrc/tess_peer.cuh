@@ -92,8 +92,8 @@ TESS_DEVFN unsigned long long tess_flag_load(const double* p) {
 //   close  the last CTA to finish tells every peer "my slice is everywhere" and waits for all peers
 //          to say so: when the kernel ends the whole vector of this rank is final.
 __global__ void __launch_bounds__(256)
-k_peer_sum_p2p_sparse(TessPeers P, long lo, long hi, int M, long n_rows_doubles, long flag_off, long range_off,
-                      unsigned long long epoch, unsigned* done) {
+k_peer_sum_p2p_sparse(TessPeers P, double* mc, long lo, long hi, int M, long n_rows_doubles, long flag_off, long range_off,
+                      long node_off, unsigned long long epoch, unsigned* done) {
     __shared__ unsigned long long s_lo[TESS_PEER_MAX], s_hi[TESS_PEER_MAX];
     __shared__ int s_last;
     if (threadIdx.x < P.world) {
@@ -111,6 +111,95 @@ k_peer_sum_p2p_sparse(TessPeers P, long lo, long hi, int M, long n_rows_doubles,
     // Two buffers: the copies of a chunk drain while the next one is summed.
     __shared__ __align__(128) double s_out[2][TESS_PEER_CHUNK];
     int buf = 0;
+    if (mc) {
+        // With a multicast mapping of the buffer (NVLS) the broadcast half is ONE 16-byte store per pair
+        // of totals: the switch replicates it into every rank's copy, so a rank sends its slice once
+        // instead of once per peer (multimem.st moves bits: the two doubles travel as four .f32 words).
+        for (long i = lo + 2L * ((long)blockIdx.x * blockDim.x + threadIdx.x); i < hi; i += 2L * gridDim.x * blockDim.x) {
+            const bool tail = i >= n_rows_doubles;
+            const unsigned long long row = (unsigned long long)(i / M);
+            double a[TESS_PEER_MAX], b[TESS_PEER_MAX];
+#pragma unroll
+            for (int r = 0; r < TESS_PEER_MAX; ++r) {
+                a[r] = 0.0; b[r] = 0.0;
+                if (r < P.world && (tail || (row >= s_lo[r] && row < s_hi[r])))
+                    asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(a[r]), "=d"(b[r]) : "l"(P.ptr[r] + i) : "memory");
+            }
+            double sa = 0.0, sb = 0.0;
+#pragma unroll
+            for (int r = 0; r < TESS_PEER_MAX; ++r)
+                if (r < P.world) { sa = __dadd_rn(sa, a[r]); sb = __dadd_rn(sb, b[r]); }
+            const long long ua = __double_as_longlong(sa), ub = __double_as_longlong(sb);
+            asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc + i),
+                         "r"((unsigned)ua), "r"((unsigned)(ua >> 32)), "r"((unsigned)ub), "r"((unsigned)(ub >> 32)) : "memory");
+        }
+    } else if (node_off >= 0) {
+        // OWNER-COMPUTED UPDATE (4-moment rows; slices start on rows).  What every rank needs from a bin's
+        // totals is its new node -- population > 0 ? (sum wx / sum w, sum wy / sum w) : (0, 0), reference
+        // tess/lloyd.pyx:66-74 -- so the owner of the slice forms it right here and broadcasts 16 bytes per
+        // bin instead of the 32-byte row: half the traffic in and out of every rank, and the replicated
+        // update reads half as much.  The totals themselves stay with the owner (its own copy of the
+        // slice); the tail (the summed "labels changed" flags) still goes to everyone.
+        for (long c0 = lo + (long)blockIdx.x * TESS_PEER_CHUNK; c0 < hi; c0 += (long)gridDim.x * TESS_PEER_CHUNK) {
+            const int len = (int)((hi - c0 < TESS_PEER_CHUNK) ? (hi - c0) : TESS_PEER_CHUNK);      // even
+            const long row_end = (c0 + len < n_rows_doubles) ? c0 + len : n_rows_doubles;
+            const int n_row = (row_end > c0) ? (int)((row_end - c0) / 4) : 0;
+            if (threadIdx.x < P.world) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncthreads();
+            for (int o = 2 * threadIdx.x; o < len; o += 2 * blockDim.x) {
+                const long i = c0 + o;
+                const bool tail = i >= n_rows_doubles;
+                const unsigned long long row = (unsigned long long)(i / M);
+                double a[TESS_PEER_MAX], b[TESS_PEER_MAX];
+#pragma unroll
+                for (int r = 0; r < TESS_PEER_MAX; ++r) {
+                    a[r] = 0.0; b[r] = 0.0;
+                    if (r < P.world && (tail || (row >= s_lo[r] && row < s_hi[r])))
+                        asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(a[r]), "=d"(b[r]) : "l"(P.ptr[r] + i) : "memory");
+                }
+                double sa = 0.0, sb = 0.0;
+#pragma unroll
+                for (int r = 0; r < TESS_PEER_MAX; ++r)
+                    if (r < P.world) { sa = __dadd_rn(sa, a[r]); sb = __dadd_rn(sb, b[r]); }
+                *reinterpret_cast<double2*>(&s_out[buf][o]) = make_double2(sa, sb);
+                if (!tail) {
+                    *reinterpret_cast<double2*>(P.ptr[P.rank] + i) = make_double2(sa, sb);      // the owner keeps the totals
+                } else {
+#pragma unroll
+                    for (int r = 0; r < TESS_PEER_MAX; ++r)
+                        if (r < P.world)
+                            asm volatile("st.relaxed.sys.global.v2.f64 [%0], {%1, %2};" ::"l"(P.ptr[r] + i), "d"(sa), "d"(sb) : "memory");
+                }
+            }
+            __syncthreads();
+            double2 nd[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int r = (int)threadIdx.x + u * (int)blockDim.x;
+                nd[u] = make_double2(0.0, 0.0);
+                if (r < n_row) {
+                    const double2 m01 = *reinterpret_cast<const double2*>(&s_out[buf][4 * r]);
+                    const double2 m23 = *reinterpret_cast<const double2*>(&s_out[buf][4 * r + 2]);
+                    if (m01.x > 0.0) nd[u] = make_double2(__ddiv_rn(m23.x, m01.y), __ddiv_rn(m23.y, m01.y));
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int r = (int)threadIdx.x + u * (int)blockDim.x;
+                if (r < n_row) *reinterpret_cast<double2*>(&s_out[buf][2 * r]) = nd[u];
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (threadIdx.x < P.world) {
+                if (n_row > 0)
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(P.ptr[threadIdx.x] + node_off + (c0 / 4) * 2),
+                                 "r"((unsigned)__cvta_generic_to_shared(&s_out[buf][0])), "r"(n_row * 16) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            buf ^= 1;
+        }
+    } else
     for (long c0 = lo + (long)blockIdx.x * TESS_PEER_CHUNK; c0 < hi; c0 += (long)gridDim.x * TESS_PEER_CHUNK) {
         const int len = (int)((hi - c0 < TESS_PEER_CHUNK) ? (hi - c0) : TESS_PEER_CHUNK);      // even
         // the bulk copies that read this buffer two chunks ago are done reading it
@@ -142,7 +231,7 @@ k_peer_sum_p2p_sparse(TessPeers P, long lo, long hi, int M, long n_rows_doubles,
         }
         buf ^= 1;
     }
-    if (threadIdx.x < P.world) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // all copies of this CTA have landed
+    if (!mc && threadIdx.x < P.world) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // all copies of this CTA have landed
     // ---- close
     __threadfence_system();            // this thread's stores are ordered before the flag below
     __syncthreads();

@@ -47,6 +47,7 @@ struct TessPhaseArgs {
     int wvt_update;
     double* delta_part;
     unsigned long long* range;   // published row range of the sparse exchange, or null
+    const double* staged;        // new nodes computed and broadcast by the slices' owners (multi-GPU), or null
     // label comparison
     int mask_mode;          // 0: all; 1: finite density; 2: finite signal, noise, weight
     int32_t *lab0, *lab1;
@@ -92,7 +93,8 @@ k_iteration_phases(const TESS_GRID_CONSTANT TessPhaseArgs a, int lo, int hi, int
             if (!with_update) tess_p_cell_count(a.g, a.node, a.k, a.cell_cnt, a.cell_of, nullptr, 0);
             else if (a.M == 6) tess_p_update_nodes<6>(st, a.mom, tail, a.k, a.node, a.scale, a.inv_s2, a.wvt_update, a.delta_part,
                                                       &a.g, a.cell_cnt, a.cell_of);
-            else tess_p_update_nodes<4>(st, a.mom, tail, a.k, a.node, nullptr, a.inv_s2, 0, a.delta_part, &a.g, a.cell_cnt, a.cell_of);
+            else tess_p_update_nodes<4>(st, a.mom, tail, a.k, a.node, nullptr, a.inv_s2, 0, a.delta_part, &a.g, a.cell_cnt, a.cell_of,
+                                        a.staged);
         } else if (ph == TESS_PH_FINISH) {
             // The latch AFTER this phase, from values that no longer change during it: the scan belongs
             // to the NEXT iteration and must know now, while one thread of CTA 0 is still writing the

@@ -130,7 +130,8 @@ TESS_DEVFN double2 tess_ld2(const double* p) {
 template <int M>
 TESS_DEVFN void tess_p_update_nodes(TessState* st, const double* mom, const double* mom_tail, int k, double* node,
                                     double* scale, double* inv_s2, int wvt_update, double* delta_part,
-                                    const TessGrid* g = nullptr, int* cell_cnt = nullptr, int* cell_of = nullptr) {
+                                    const TessGrid* g = nullptr, int* cell_cnt = nullptr, int* cell_of = nullptr,
+                                    const double* staged = nullptr) {
     __shared__ double s_red[8];
     const bool changed = mom_tail[TESS_TAIL_CHANGED] != 0.0;
     if (changed) {
@@ -141,17 +142,28 @@ TESS_DEVFN void tess_p_update_nodes(TessState* st, const double* mom, const doub
         // bytes, 16-byte aligned -- and the old node) are loaded together, and those of the thread's
         // NEXT generator are requested before this one is worked on: issued after the divide (one more
         // dependent DRAM round trip, interleaved with the node stores) the kernel measured 5x slower
+        // `staged` (multi-GPU, tess_peer.cuh): the new nodes were computed by the rank that owns the bin's
+        // slice of the moment vector -- by the very rule below, from the totals -- and broadcast; they
+        // are taken as they are (16 bytes per bin instead of the 32-byte row)
         double2 n01 = make_double2(0.0, 0.0), n23 = n01, nold = n01;
-        if (j < k) { n01 = tess_ld2(mom + j * M); n23 = tess_ld2(mom + j * M + 2); nold = tess_ld2(node + 2 * j); }
+        if (j < k) {
+            if (staged) n23 = tess_ld2(staged + 2 * j);
+            else { n01 = tess_ld2(mom + j * M); n23 = tess_ld2(mom + j * M + 2); }
+            nold = tess_ld2(node + 2 * j);
+        }
         for (; j < k; j += stride) {
             const double* m = mom + j * M;
             const double2 m01 = n01, m23 = n23, old = nold;
             if (j + stride < k) {
-                n01 = tess_ld2(mom + (j + stride) * M); n23 = tess_ld2(mom + (j + stride) * M + 2); nold = tess_ld2(node + 2 * (j + stride));
+                if (staged) n23 = tess_ld2(staged + 2 * (j + stride));
+                else { n01 = tess_ld2(mom + (j + stride) * M); n23 = tess_ld2(mom + (j + stride) * M + 2); }
+                nold = tess_ld2(node + 2 * (j + stride));
             }
             double2* np = reinterpret_cast<double2*>(node) + j;
             double nx = 0.0, ny = 0.0;
-            if (m01.x > 0.0) {   // population test, not weight (lloyd.pyx:68)
+            if (staged) {
+                nx = m23.x; ny = m23.y;
+            } else if (m01.x > 0.0) {   // population test, not weight (lloyd.pyx:68)
                 nx = __ddiv_rn(m23.x, m01.y);
                 ny = __ddiv_rn(m23.y, m01.y);
             }

@@ -194,6 +194,11 @@ class Engine(object):
         buffer (tess_peer_publish_range); read by the peers' sparse exchange."""
         self.api.call("tess_peer_publish_range", self.ctx, self._stream())
 
+    def peer_set_multicast(self, multicast_ptr):
+        """tess_peer_set_multicast: the sparse exchange broadcasts through the NVLS multicast mapping
+        (0 / None: peer-to-peer copies)."""
+        self.api.call("tess_peer_set_multicast", self.ctx, multicast_ptr if multicast_ptr else None)
+
     def peer_allreduce_sparse(self, world, rank, peer_ptrs, n_doubles):
         """tess_peer_allreduce_sparse: rows are read only from the peers whose published range holds them."""
         self.api.call("tess_peer_allreduce_sparse", self.ctx, int(world), int(rank), peer_ptrs, int(n_doubles),

@@ -94,6 +94,7 @@ class ShardedLloyd(object):
         self._perm = None        # internal id -> caller id (None: identity)
         self._inv = None         # caller id -> internal id
         self._sparse = False
+        self._owner = False
         self._peer = None
         self.exchange = "backend all_reduce (NCCL on GPUs)" if self._want == "nccl" else "undecided"
 
@@ -179,13 +180,14 @@ class ShardedLloyd(object):
                 hdl = symm.rendezvous(buf, grp)
                 ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs])
                 mc = int(hdl.multicast_ptr) if getattr(hdl, "has_multicast_support", False) and hdl.multicast_ptr else 0
+                mc_raw = mc
                 # fp64 multimem operations are 8 bytes each (no vector form): measured 126 us per 32 MB
                 # exchange at 8 GPUs against 141 us for the two-shot kernel and 147 us for NCCL, but
                 # 128 us against 83 / 80 us at 2 GPUs -- the switch reduction pays from 8 ranks on
                 force = os.environ.get("TESS_PEER_NO_MC", "")
                 if force == "1" or (force != "0" and self.world < 8):
                     mc = 0
-                peer = dict(buf=buf, hdl=hdl, ptrs=ptrs, mc=mc, n=need)
+                peer = dict(buf=buf, hdl=hdl, ptrs=ptrs, mc=mc, mc_raw=mc_raw, n=need)
             except Exception as e:
                 err = str(e).splitlines()[0][:120] if str(e) else type(e).__name__
         else:
@@ -200,8 +202,20 @@ class ShardedLloyd(object):
             self._view = None
             import os
             self._sparse = self._perm is not None and os.environ.get("TESS_PEER_DENSE", "") != "1"
+            use_mc = self._sparse and peer["mc_raw"] and os.environ.get("TESS_SPARSE_MC", "0") == "1"
+            self.eng.peer_set_multicast(peer["mc_raw"] if use_mc else 0)
+            # owner-computed update: the owner of a slice broadcasts the new nodes of its bins (16 bytes
+            # each) instead of the rows of totals (the library applies it to 4-moment rows without WVT
+            # scale updates and falls back to the rows otherwise)
+            self._owner = self._sparse and os.environ.get("TESS_OWNER_UPDATE", "1") != "0"
+            from . import _capi
+            self.eng.set_option(_capi.OPT_OWNER_UPDATE, 1 if self._owner else 0)
             if self._sparse:
                 self.exchange = "own kernel, two-shot over NVLink peer memory, sparse reduce (spatially numbered bins)"
+                if self._owner:
+                    self.exchange += ", owner-computed nodes broadcast (16 B per bin; 4-moment rows)"
+                if use_mc:
+                    self.exchange += ", broadcast through the NVLS multicast mapping"
             else:
                 self.exchange = ("own kernel, NVLS multicast reduction (multimem.ld_reduce/st)" if peer["mc"]
                                  else "own kernel, two-shot over NVLink peer memory")
@@ -279,6 +293,18 @@ class ShardedLloyd(object):
     def moments(self):
         """Global per-bin moments [k, 6] (identical on all ranks after a step)."""
         m = self.eng.moments()
+        if self._owner and self._peer is not None and self.eng.api.moments_ptr(self.eng.ctx)[2] == 4 \
+                and not getattr(self.eng, "_wvt_update", False):
+            # owner-computed update: the totals of a bin live in the copy of the rank that owns its slice
+            # (rows [r * ceil(k / world), ...)); collect the slices
+            k = self.eng.k
+            per = (k + self.world - 1) // self.world
+            lo, hi = min(per * self.rank, k), min(per * (self.rank + 1), k)
+            mine = self.torch.zeros((per, m.shape[1]), dtype=m.dtype, device=m.device)
+            mine[:hi - lo] = m[lo:hi]
+            parts = [self.torch.empty_like(mine) for _ in range(self.world)]
+            self.dist.all_gather(parts, mine, group=self.group)
+            m = self.torch.cat(parts, dim=0)[:k]
         return m if self._inv is None else m[self._inv]
 
     def gather_labels(self, dst=0):

@@ -612,6 +612,49 @@ def test_external_moment_buffer_and_peer_allreduce_world1(eng, engine_cls):
     e2.close()
 
 
+def test_sparse_exchange_and_owner_computed_update_world1(engine_cls):
+    """tess_peer_allreduce_sparse on one GPU (world = 1: the rank owns the whole vector), with rows of
+    totals and with TESS_OPT_OWNER_UPDATE -- the owner forms the new nodes (lloyd.pyx:66-74) and
+    tess_lloyd_update takes them from the node area of the caller's buffer: generators equal to
+    the single-context iteration (1e-9 px; labels bit-identical), empty bins to (0, 0) included.  k > 512 so that the slice spans
+    several 16 KB chunks; the multi-rank runs are checked by bench.py --gpus N (parity_check)."""
+    import ctypes
+    import torch
+    from tess_b200 import _capi
+    N, k = 384, 1500
+    w = gaussian_image(N) + 0.5
+    seeds = sampled_seeds(w, k, seed=4)
+    seeds[7] = [-500.0, -500.0]                 # never nearest: an empty bin
+    e1 = engine_cls(0)
+    e1.set_image(density=w)
+    e1.set_generators(seeds)
+    e1.step(3)
+    want_g, want_m = e1.generators().clone(), e1.moments().clone()
+    assert torch.equal(want_g[7], torch.zeros(2, dtype=torch.float64, device="cuda")) or float(want_m[7, 0]) > 0
+    for owner in (0, 1):
+        e2 = engine_cls(0)
+        buf = torch.zeros((6 * k + 2 + 34,), dtype=torch.float64, device="cuda")
+        e2.set_image(density=w)
+        e2.set_generators(seeds)
+        e2.set_moment_buffer(buf, buf.numel())
+        e2.set_option(_capi.OPT_OWNER_UPDATE, owner)
+        ptr, n, m = e2.api.moments_ptr(e2.ctx)
+        ptrs = (ctypes.c_void_p * 1)(buf.data_ptr())
+        for _ in range(3):
+            e2.accumulate()
+            e2.peer_allreduce_sparse(1, 0, ptrs, n)
+            e2.update()
+        torch.cuda.synchronize()
+        # (two contexts sum in different orders: last-bit differences in the moments, none in the labels)
+        np.testing.assert_allclose(h(e2.generators()), h(want_g), rtol=0, atol=1e-9, err_msg=str(owner))
+        assert torch.equal(e2.labels(), e1.labels()), owner
+        np.testing.assert_allclose(h(e2.moments()), h(want_m), rtol=1e-12, atol=0, err_msg=str(owner))   # (world = 1: the owner's copy holds every total)
+        assert e2.stats()[2] == 3
+        e2.set_moment_buffer(None, 0)
+        e2.close()
+    e1.close()
+
+
 def test_randomised_parity_short():
     """tools/fuzz_parity.py for a few seconds: random shapes, origins, densities (thousands of px per
     bin down to one), ties, duplicates, scales and modes against the exhaustive scan."""

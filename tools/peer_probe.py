@@ -15,9 +15,9 @@ eng = Engine(local)
 rng = np.random.default_rng(0)
 node = rng.uniform(0, 4096, (k, 2))
 dens = torch.rand((256, 4096), dtype=torch.float64, device="cuda") + 0.5
-for mode in ("peer", "peer_p2p", "nccl"):
+for mode in ("peer", "peer_sparse_mc", "nccl"):
     os.environ["TESS_EXCHANGE"] = "nccl" if mode == "nccl" else "peer"
-    os.environ["TESS_PEER_NO_MC"] = "1" if mode == "peer_p2p" else "0"
+    os.environ["TESS_SPARSE_MC"] = "1" if mode == "peer_sparse_mc" else "0"
     try:
         drv = ShardedLloyd(eng)
         drv.set_image_rows(density=dens, row0=256 * rank, total_rows=256 * world)
