@@ -32,7 +32,7 @@ def shard_rows(H, world, align=64):
 COST_MODEL = (2.56, 39.1, 0.40)
 
 
-def balanced_row_shards(generators, H, W, world, x0=0.0, y0=0.0, align=64, model=None):
+def balanced_row_shards(generators, H, W, world, x0=0.0, y0=0.0, align=64, model=None, measured=None):
     """Row ranges whose estimated cost is equal: the time per pixel of one accumulate (list building +
     image kernel) grows with the local generator density rho (generators per pixel) like
     2.56 + 39.1 rho^0.40 ps/px -- a least-squares fit to the per-rank accumulate times of the C4 map
@@ -42,7 +42,11 @@ def balanced_row_shards(generators, H, W, world, x0=0.0, y0=0.0, align=64, model
     max / mean = 1.027; a refit to 96 strips of 512 and 2048 rows, 2.28 + 63.5 rho^0.50, predicts the
     same cuts to within one tile row, i.e. the model is at the noise limit of the measurements).
     `generators` is the (k, 2) table (host array); boundaries fall on multiples of `align` rows;
-    `model` = (a, b, p) overrides COST_MODEL."""
+    `model` = (a, b, p) overrides COST_MODEL.
+    `measured` = (shards, times): row ranges in use and the accumulate time every rank measured with
+    them (ShardedLloyd.measure_accumulate).  The model's cost of each of those shards is then scaled to
+    its measured share before the rows are cut again -- the model is good to a few per cent, a GPU of
+    the box may be a few per cent slower than its peers, and the slowest rank sets the iteration."""
     ca, cb, cp = model if model is not None else COST_MODEL
     import numpy as np
     g = np.asarray(generators, dtype=np.float64)
@@ -54,6 +58,15 @@ def balanced_row_shards(generators, H, W, world, x0=0.0, y0=0.0, align=64, model
     cnt = np.bincount(iy * ntx + ix, minlength=nty * ntx).reshape(nty, ntx).astype(np.float64)
     tile_px = float(align * align)
     cost = (tile_px * (ca + cb * (cnt / tile_px) ** cp)).sum(axis=1)     # per tile row
+    if measured is not None:
+        old_shards, times = measured
+        times = np.asarray(times, dtype=np.float64)
+        if len(old_shards) == len(times) and np.all(times > 0):
+            for (a0, a1), t in zip(old_shards, times):
+                t0, t1 = a0 // align, (a1 + align - 1) // align
+                c = cost[t0:t1].sum()
+                if c > 0:
+                    cost[t0:t1] *= (t / times.sum()) / (c / cost.sum() if cost.sum() > 0 else 1.0)
     cum = np.concatenate(([0.0], np.cumsum(cost)))
     cuts = [0]
     for r in range(1, world):
@@ -240,6 +253,26 @@ class ShardedLloyd(object):
             self.eng.accumulate()
             self.exchange_moments()
             self.eng.update()
+
+    def measure_accumulate(self, n=3, skip=1):
+        """Device time of one local accumulate on every rank (mean of n, after `skip` untimed ones; the
+        exchange and update run in between as in a real iteration): the input of
+        balanced_row_shards(measured=...).  Collective; returns the same list on every rank."""
+        t = self.torch
+        if not isinstance(self.eng.generators(), t.Tensor):
+            return None
+        ev = [(t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)) for _ in range(n + skip)]
+        for a, b in ev:
+            a.record()
+            self.eng.accumulate()
+            b.record()
+            self.exchange_moments()
+            self.eng.update()
+        t.cuda.synchronize()
+        mine = t.tensor([sum(a.elapsed_time(b) for a, b in ev[skip:]) / n], dtype=t.float64, device=self.eng.generators().device)
+        allt = [t.zeros_like(mine) for _ in range(self.world)]
+        self.dist.all_gather(allt, mine, group=self.group)
+        return [float(x.item()) for x in allt]
 
     def exchange_moments(self):
         """The one cross-rank step: every rank ends with the bit-identical sum of the moment vectors."""
