@@ -13,8 +13,8 @@ python bench.py --impl reference --steps 2 --warmup 1 > ${P}_bench_reference_arm
 python tools/regime_bench.py 8192 > ${P}_regimes_8192.jsonl 2> ${P}_regimes.err
 TESS_NO_TMA=1 python tools/regime_bench.py 8192 12000,150000 > ${P}_regimes_8192_no_tma_prefetch.jsonl 2>> ${P}_regimes.err
 python tools/other_configs.py > ${P}_other_configs.jsonl 2> ${P}_other.err
-timeout 300 python tools/dense_probe.py > ${P}_small_bins_1024.jsonl 2>&1
-timeout 300 python tools/dense_centre_probe.py > ${P}_dense_centre_4096.jsonl 2>&1
+timeout 200 python tools/dense_probe.py > ${P}_small_bins_1024.jsonl 2>&1
+timeout 200 python tools/dense_centre_probe.py > ${P}_dense_centre_4096.jsonl 2>&1
 B="python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-clocks --no-extras"
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 80 --csv --log-file ${P}_launches_c3.csv $B > ${P}_ncu.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_image_main -s 4 -c 1 -f -o ${P}_full_main_c3_cvt $B >> ${P}_ncu.log 2>&1
