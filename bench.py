@@ -360,7 +360,7 @@ def main():
         # the cost model behind the cuts is good to a few per cent (and GPUs of one box differ by as
         # much): measure one round of accumulates, scale every shard's modelled cost to its measured
         # share, cut again, set up again -- all before the warm-up, nothing of it is timed
-        for _ in range(2):                        # (a second cut takes out what the first left)
+        for _ in range(3):                        # (the later cuts take out what the first left: one tile row at a time)
             t_acc = drv.measure_accumulate(n=6, skip=args.warmup)      # the iterations the timed region will see
             if not t_acc or max(t_acc) <= 1.01 * (sum(t_acc) / len(t_acc)):
                 break

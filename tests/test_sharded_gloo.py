@@ -101,3 +101,28 @@ def test_two_rank_row_sharded_lloyd_matches_reference():
     assert np.array_equal(res[0]["nodes"], res[1]["nodes"]) and np.array_equal(res[0]["mom"], res[1]["mom"])
     assert np.array_equal(res[0]["labels"].ravel(), g["labels"][-1].astype(np.int32))
     assert res[0]["mom"][:, 0].sum() == 64 * 64
+
+
+def test_balanced_row_shards_and_recut_from_measured_times():
+    """Host logic of the row sharding: cuts on tile rows, cover the image, follow the generator density;
+    a re-cut from measured accumulate times shrinks the shards that ran long and leaves a balanced
+    measurement alone."""
+    import numpy as np
+    from tess_b200.sharded import balanced_row_shards, shard_rows
+    rng = np.random.default_rng(3)
+    H = W = 4096
+    g = np.clip(rng.normal(H / 2, H / 8, (20000, 2)), 0, H - 1)
+    cuts = balanced_row_shards(g, H, W, 8)
+    assert cuts[0][0] == 0 and cuts[-1][1] == H and all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+    assert all(r0 % 64 == 0 and r1 > r0 for r0, r1 in cuts)
+    rows = [r1 - r0 for r0, r1 in cuts]
+    assert rows[0] > rows[3] and rows[7] > rows[4]                      # sparse outskirts get more rows
+    assert balanced_row_shards(g, H, W, 1) == shard_rows(H, 1)
+    same = balanced_row_shards(g, H, W, 8, measured=(cuts, [1.0] * 8))
+    # equal measured times: the modelled cost is rescaled to equal shares -> the cuts stay within a tile row
+    assert all(abs(a[1] - b[1]) <= 64 for a, b in zip(cuts, same))
+    slow0 = balanced_row_shards(g, H, W, 8, measured=(cuts, [1.3] + [1.0] * 7))
+    assert slow0[0][1] < cuts[0][1]                                      # rank 0 ran long: fewer rows for it
+    assert slow0[-1][1] == H and all(a[1] == b[0] for a, b in zip(slow0, slow0[1:]))
+    # a density-independent model gives equal rows
+    assert balanced_row_shards(g, H, W, 8, model=(1.0, 0.0, 1.0)) == shard_rows(H, 8)
