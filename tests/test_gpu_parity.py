@@ -638,6 +638,7 @@ def test_sparse_exchange_and_owner_computed_update_world1(engine_cls):
         e2.set_generators(seeds)
         e2.set_moment_buffer(buf, buf.numel())
         e2.set_option(_capi.OPT_OWNER_UPDATE, owner)
+        e2.peer_set_multicast(0)                  # (no multicast mapping on one GPU: peer-to-peer copies)
         ptr, n, m = e2.api.moments_ptr(e2.ctx)
         ptrs = (ctypes.c_void_p * 1)(buf.data_ptr())
         for _ in range(3):
