@@ -6,30 +6,33 @@
 // generator rasterisation behind VoronoiTessellation.segmap (tess/voronoi.py:75-114).
 //
 // Work unit: one WARP per 32x32-px quadrant, warps fully independent (no CTA barrier anywhere).
-// A warp's first two quadrants are fixed (q, q + stride), the following ones are drawn from a device
-// queue (one atomic per quadrant, requested a whole quadrant before its value is needed), so no warp
-// idles while others still have work.  The quadrant's candidate list (k_build_qlists: arena records
-// in no particular order) is copied into the warp's shared-memory buffer with cp.async one quadrant
-// AHEAD, so list latency is hidden behind the previous quadrant's arithmetic.
-// For each of its four 32x8 warp tiles the warp narrows the list per 16x16 block (long lists only)
-// and per 8x8 leaf (8 lanes per leaf) with the centre + radius test
+// A warp's first chunk of quadrants is fixed (its global warp index), the following ones are drawn
+// from a device queue (one atomic per chunk of TESS_CHUNK quadrants, requested a whole chunk before
+// its value is needed and never touched in between), so no warp idles while others still have work.
+// The quadrant's candidate list (k_build_qlists: arena records in no particular order) is copied
+// into the warp's shared-memory buffer with cp.async one quadrant AHEAD, so list latency is hidden
+// behind the previous quadrant's arithmetic; the next quadrant's pixel tile is requested from DRAM
+// into L2 by one TMA prefetch.
+// Once per quadrant the candidate sets of its sixteen 8x8 leaves are formed -- lane pair (2L, 2L+1)
+// measures the list (lists longer than 64: the list of the leaf's 16x16 block) against leaf L's centre
+// with the centre + radius test
 //     keep g  iff  u(c,g) <= min_h u(c,h) + 2 rho / s_min        (u = distance / scale)
-// which can never drop the true nearest generator of any pixel of the rectangle, evaluates the
-// survivors with the pinned fp64 formula (an exact tie is detected and then resolved to the lowest
-// generator index) and writes labels as one coalesced 128-byte line per row.
+// which can never drop the true nearest generator of any pixel of the rectangle -- and kept as 64-bit
+// masks over the list.  For each of its four 32x8 warp tiles the warp then evaluates the set bits of
+// every lane's leaf mask with the pinned fp64 formula (an exact tie is detected and then resolved to
+// the lowest generator index) and writes labels as one coalesced 128-byte line per row.  A quadrant
+// whose leaves all end with the same single candidate is one bin: constant labels, closed-form sums.
 //
 // Moments ("segmented reduction"): every lane owns a 2-column x 4-row pixel patch per warp tile and
-// keeps ONE running same-bin sum in registers across the warp tiles of the quadrant (labels are
-// spatially coherent, so most patches extend the current run); a patch is summed in patch-local
-// coordinates and shifted once.  When a lane's run ends, its sums go to the warp's shared-memory
-// table of per-candidate accumulators; lanes that retire the same bin in the same round take turns
-// through a claim slot (warp-level aggregation, no atomics: the table is private to the warp).  At
-// the end of the quadrant the live runs are merged across the warp with shuffles and the table goes
-// to the global moment vector -- one fp64 reduction per (quadrant, bin, moment).  The fold is written
-// without lane-divergent branches.
+// keeps ONE running same-bin sum in registers, keyed by generator id, across warp tiles AND
+// quadrants (labels are spatially coherent, so most patches extend the current run); a patch is
+// summed in patch-local coordinates and shifted once.  When a lane's run ends, its sums go straight
+// to the bin's row of the global moment vector as fire-and-forget fp64 reductions; when many lanes
+// retire at once (a warp leaving a large bin) they are merged with a shuffle tree first, because
+// same-address reductions serialise in L2.  The fold is written without lane-divergent branches.
 //
-// Tail phase: quadrants off this fast path (list longer than the table, or a tile that overflowed
-// the builder) are queued by the builder; after their own quadrants all warps of the grid take
+// Tail phase: quadrants off this fast path (list longer than the staged capacity, or a tile that
+// overflowed the builder) are queued by the builder; after their own quadrants all warps of the grid take
 // 2-row strips of them (list scan from L2, or the per-pixel ring search over the generator grid).
 //
 // Algorithmic HBM traffic per pixel: MODE 1: 8 B (density) + 4 B (label) = 12 B;
