@@ -201,6 +201,7 @@ static inline double __longlong_as_double(long long l) { double r; std::memcpy(&
 static inline float __int_as_float(int i) { float r; std::memcpy(&r, &i, 4); return r; }
 static inline int __float_as_int(float f) { int r; std::memcpy(&r, &f, 4); return r; }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
+static inline int __double2hiint(double d) { long long r; std::memcpy(&r, &d, 8); return (int)(r >> 32); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
