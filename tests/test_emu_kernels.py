@@ -356,3 +356,57 @@ def test_zero_weight_bin_updates_every_other_node(eng):
     assert eng.status() == (False, True) and eng.stats()[2] == 1
     eng.step(1)                                         # error flag up: further steps are no-ops
     assert eng.stats()[2] == 1
+
+
+def test_long_lists_block_lists_and_their_overflow():
+    """Quadrant lists of 65 .. 128 candidates (bins of 45 .. 110 px) take the 16x16 block lists; a block
+    list that outgrows its capacity sends the quadrant through the exact per-pixel scan of the whole
+    list.  That overflow needs > 64 generators around one 16x16 block, so it is forced here with a
+    second emulator build whose block lists hold 16 entries (TESS_BCAP=16): labels bit-exact and moments
+    to 1e-12 against the oracle for both builds.  Runs in subprocesses (one library per process)."""
+    import os, subprocess, sys, textwrap
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(here)
+    small = os.path.join(here, "emu", "_build", "libtess_emu_bcap16.so")
+    srcs = [os.path.join(root, "tess_b200", "csrc", f) for f in os.listdir(os.path.join(root, "tess_b200", "csrc"))]
+    if not os.path.exists(small) or any(os.path.getmtime(small) < os.path.getmtime(f) for f in srcs):
+        os.makedirs(os.path.dirname(small), exist_ok=True)
+        subprocess.check_call(["g++", "-std=c++20", "-O2", "-pthread", "-DTESS_EMU", "-DTESS_BCAP=16", "-include",
+                               os.path.join(here, "emu", "cuda_emu.h"), "-x", "c++",
+                               os.path.join(root, "tess_b200", "csrc", "tess_b200.cu"), "-shared", "-fPIC", "-o", small])
+    prog = textwrap.dedent("""
+        import sys, numpy as np
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        from emu.harness import EmuEngine
+        from oracle import oracle as O
+        eng = EmuEngine()
+        rng = np.random.default_rng(11)
+        cases = []
+        for area, scaled in ((50, False), (70, True), (100, False)):
+            H, W = int(rng.integers(70, 120)), int(rng.integers(70, 120))
+            k = int(H * W / area)
+            g = np.column_stack((rng.uniform(-3, W + 3, k), rng.uniform(-3, H + 3, k)))
+            g[: k // 10] = np.round(g[: k // 10])                       # some exact ties
+            cases.append((H, W, g, rng.uniform(0.8, 1.3, k) if scaled else None))
+        # 72 generators inside one 16x16 block of a 64x64 tile
+        cases.append((64, 64, np.vstack((rng.uniform(16.2, 31.8, (72, 2)), rng.uniform(0, 63, (30, 2)))), None))
+        for H, W, g, scale in cases:
+            w = rng.uniform(0.5, 1.5, (H, W))
+            x, y = np.meshgrid(np.arange(W, dtype=float), np.arange(H, dtype=float))
+            pts = np.column_stack((x.ravel(), y.ravel()))
+            ref = O.c_assign_points(pts, g, scale=scale).reshape(H, W)
+            eng.set_image(density=w)
+            eng.set_generators(g, scale=scale)
+            eng.accumulate()
+            assert np.array_equal(eng.labels(), ref), (H, W, len(g))
+            rm = O.np_moments(pts, w.ravel(), ref.ravel(), len(g))
+            assert np.allclose(eng.moments()[:, :4], rm[:, :4], rtol=1e-12, atol=1e-12), (H, W, len(g))
+        print("ok")
+        """) % (root, here)
+    for lib in (None, small):
+        env = dict(os.environ)
+        env.pop("TESS_EMU_LIB", None)
+        if lib:
+            env["TESS_EMU_LIB"] = lib
+        r = subprocess.run([sys.executable, "-c", prog], env=env, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0 and r.stdout.strip().endswith("ok"), (lib, r.stdout[-500:], r.stderr[-1500:])
